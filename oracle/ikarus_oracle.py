@@ -1,0 +1,741 @@
+"""CPU oracle for the Ikarus global-assembly hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a numpy restatement of the reference algorithm for global FEM assembly
+(K, R, E), the three Dirichlet modes and the Newton/LoadControl drivers.  It is the
+*checker* for the CUDA path in ``ikarus_b200``; nothing in the product imports it.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` leg
+may import this module.
+
+The reference itself (header-only C++ over DUNE + Eigen + dune-localfefunctions)
+cannot be compiled or imported here (no DUNE/Eigen in the image), so
+this oracle is a restatement.  It is pinned against the reference's own known-answer
+tests (see ``tests/test_oracle_anchors.py``):
+
+* A1/A2  cantilever Hex8+EAS21 / Quad4+EAS4, NeoHooke and SVK: 80 Newton iterations and
+         max|d| to 1e-10                       (tests/src/testcantileverbeamEAS.cpp:20-32,61-70)
+* A3/A4  vertex stress tables of the unit square / cube (tests/src/resultcollection.hh:19-51,150-163)
+* A5     K_nonlinear(u=0) == K_linear          (tests/src/testnonlinearelasticity.hh:194-246)
+* A6     assembler invariants Raw/Full/Reduced (tests/src/testassembler.cpp:122-201)
+* A7     EAS: int M dV = 0, eas(0) == plain element, K symmetric (tests/src/testeas.hh:50-85)
+* A8     R = dE/dd, K = dR/dd by finite differences (tests/src/testnonlinearelasticity.hh:340-369)
+
+The element math deliberately follows the reference's *generic* formulation
+(Voigt B-operator, 6x6 tangent, B^T C B + geometric stiffness) and not the factored
+spatial form the CUDA kernels use, so the two are independent derivations.
+
+All `file:line` citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Quadrature and shape functions (DUNE conventions)
+# --------------------------------------------------------------------------------------
+
+
+def gauss_legendre_01(n: int):
+    """n-point Gauss-Legendre rule on [0,1] (DUNE QuadratureRules on the reference cube;
+    restated in ikarus/utils/quadraturerulehelper.hh:29-48)."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def tensor_rule(dim: int, n: int):
+    """Tensor Gauss rule, first coordinate fastest. Point order only changes the
+    summation order (<=1e-15 effects); the reference default is order 2*basisOrder
+    (ikarus/finiteelements/mechanics/nonlinearelastic.hh:121-124)."""
+    x, w = gauss_legendre_01(n)
+    pts, wts = [], []
+    for idx in itertools.product(range(n), repeat=dim):
+        idx = idx[::-1]  # first coordinate fastest
+        pts.append([x[i] for i in idx])
+        wts.append(np.prod([w[i] for i in idx]))
+    return np.array(pts), np.array(wts)
+
+
+def _lagrange1d(order: int, xi: float):
+    if order == 1:
+        return np.array([1.0 - xi, xi]), np.array([-1.0, 1.0])
+    if order == 2:
+        v = np.array([2.0 * (xi - 0.5) * (xi - 1.0), 4.0 * xi * (1.0 - xi), 2.0 * xi * (xi - 0.5)])
+        d = np.array([4.0 * xi - 3.0, 4.0 - 8.0 * xi, 4.0 * xi - 1.0])
+        return v, d
+    raise NotImplementedError(order)
+
+
+def shape_functions(dim: int, order: int, xi):
+    """Lagrange cube shape functions N[a] and reference gradients dN[a, k], node index
+    lexicographic with x fastest (DUNE LagrangeCube local order)."""
+    n1 = order + 1
+    vals = [_lagrange1d(order, xi[k]) for k in range(dim)]
+    nn = n1**dim
+    N = np.empty(nn)
+    dN = np.empty((nn, dim))
+    for a in range(nn):
+        idx = [(a // n1**k) % n1 for k in range(dim)]
+        N[a] = np.prod([vals[k][0][idx[k]] for k in range(dim)])
+        for k in range(dim):
+            dN[a, k] = np.prod([vals[m][1][idx[m]] if m == k else vals[m][0][idx[m]] for m in range(dim)])
+    return N, dN
+
+
+# --------------------------------------------------------------------------------------
+# Voigt helpers (ikarus/utils/tensorutils.hh:180-326)
+# --------------------------------------------------------------------------------------
+
+VOIGT3 = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
+VOIGT2 = [(0, 0), (1, 1), (0, 1)]
+
+
+def voigt_pairs(dim):
+    return VOIGT3 if dim == 3 else VOIGT2
+
+
+def to_voigt(E, strain=True):
+    """Batched matrix -> Voigt (tensorutils.hh:248-276); shear entries doubled for strains."""
+    dim = E.shape[-1]
+    f = 2.0 if strain else 1.0
+    cols = [E[..., i, j] * (1.0 if i == j else f) for (i, j) in voigt_pairs(dim)]
+    return np.stack(cols, axis=-1)
+
+
+def from_voigt(v, strain=True):
+    """Batched Voigt -> matrix (tensorutils.hh:293-326)."""
+    s = v.shape[-1]
+    dim = 3 if s == 6 else 2
+    f = 0.5 if strain else 1.0
+    E = np.zeros(v.shape[:-1] + (dim, dim))
+    for q, (i, j) in enumerate(voigt_pairs(dim)):
+        val = v[..., q] * (1.0 if i == j else f)
+        E[..., i, j] = val
+        E[..., j, i] = val
+    return E
+
+
+def tensor4_to_voigt(T):
+    """(…,3,3,3,3) -> (…,6,6) (tensorutils.hh:219-227)."""
+    out = np.zeros(T.shape[:-4] + (6, 6))
+    for p, (i, j) in enumerate(VOIGT3):
+        for q, (k, l) in enumerate(VOIGT3):
+            out[..., p, q] = T[..., i, j, k, l]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Materials (ikarus/finiteelements/mechanics/materials/*)
+# --------------------------------------------------------------------------------------
+
+
+def lame_from_E_nu(E, nu):
+    """physicshelper.hh:276-281."""
+    lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    mu = E / (2.0 * (1.0 + nu))
+    return lam, mu
+
+
+@dataclass
+class Material:
+    """kind in {'linear', 'svk', 'neohooke'}; plane_strain wraps the 3D law in the
+    VanishingStrain reduction (materials/vanishingstrain.hh:79-120)."""
+
+    kind: str
+    lam: float
+    mu: float
+    plane_strain: bool = False
+
+    # --- 3D law on Voigt GL strain (batched: E6[..., 6]) --------------------------------
+    def _law3d(self, E6):
+        lam, mu = self.lam, self.mu
+        if self.kind in ("linear", "svk"):
+            # svk.hh:77-164 ; linearelasticity.hh forwards to SVK
+            C = np.zeros(E6.shape[:-1] + (6, 6))
+            C[..., :3, :3] = lam
+            for i in range(3):
+                C[..., i, i] += 2.0 * mu
+                C[..., 3 + i, 3 + i] = mu
+            S = np.einsum("...pq,...q->...p", C, E6)
+            tr = E6[..., :3].sum(-1)
+            psi = 0.5 * lam * tr**2 + mu * ((E6[..., :3] ** 2).sum(-1) + 0.5 * (E6[..., 3:] ** 2).sum(-1))
+            return psi, S, C
+        if self.kind == "neohooke":
+            # neohooke.hh:79-142 with C = 2E + I (strainconversions.hh:88-106)
+            Cm = 2.0 * from_voigt(E6, strain=True) + np.eye(3)
+            detC = np.linalg.det(Cm)
+            if np.any(detC <= 1e-10):  # materialhelpers.hh:120-126 (abort in the reference)
+                raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
+            logJ = np.log(np.sqrt(detC))
+            invC = np.linalg.inv(Cm)
+            I = np.eye(3)
+            trC = np.trace(Cm, axis1=-2, axis2=-1)
+            psi = 0.5 * mu * (trC - 3.0 - 2.0 * logJ) + 0.5 * lam * logJ**2
+            Sm = mu * (I - invC) + (lam * logJ)[..., None, None] * invC
+            dy = np.einsum("...ij,...kl->...ijkl", invC, invC)
+            ikjl = np.einsum("...ik,...jl->...ijkl", invC, invC)
+            iljk = np.einsum("...il,...jk->...ijkl", invC, invC)
+            T = lam * dy + (2.0 * (mu - lam * logJ))[..., None, None, None, None] * 0.5 * (ikjl + iljk)
+            return psi, to_voigt(Sm, strain=False), tensor4_to_voigt(T)
+        raise NotImplementedError(self.kind)
+
+    def evaluate(self, Ev):
+        """Return (psi, S_voigt, C_voigt) for Voigt strain Ev[..., s], s = 3 (2D) or 6."""
+        if Ev.shape[-1] == 6:
+            assert not self.plane_strain
+            return self._law3d(Ev)
+        assert self.plane_strain, "2D elements need a reduced material (planeStrain)"
+        free = [0, 1, 5]  # vanishingstrain.hh: fixed Voigt indices {2,3,4}
+        E6 = np.zeros(Ev.shape[:-1] + (6,))
+        E6[..., free] = Ev
+        psi, S6, C6 = self._law3d(E6)
+        return psi, S6[..., free], C6[..., free, :][..., :, free]
+
+
+# --------------------------------------------------------------------------------------
+# EAS ansatz (strainenhancements/easvariants/linearandglstrains.hh:71-328)
+# --------------------------------------------------------------------------------------
+
+# (row in Voigt, polynomial as tuple of reference directions) per column
+_EAS_TABLE = {
+    (2, 4): [(0, (0,)), (1, (1,)), (2, (0,)), (2, (1,))],
+    (2, 5): [(0, (0,)), (1, (1,)), (2, (0,)), (2, (1,)), (2, (0, 1))],
+    (2, 7): [(0, (0,)), (1, (1,)), (2, (0,)), (2, (1,)), (0, (0, 1)), (1, (0, 1)), (2, (0, 1))],
+    (3, 9): [(0, (0,)), (1, (1,)), (2, (2,)), (3, (1,)), (3, (2,)), (4, (0,)), (4, (2,)), (5, (0,)), (5, (1,))],
+}
+_EAS_TABLE[(3, 21)] = _EAS_TABLE[(3, 9)] + [
+    (3, (0, 1)), (3, (0, 2)), (4, (0, 1)), (4, (1, 2)), (5, (0, 2)), (5, (1, 2)),
+    (0, (0, 1)), (0, (0, 2)), (1, (0, 1)), (1, (1, 2)), (2, (0, 2)), (2, (1, 2)),
+]
+
+
+def eas_table(dim, m):
+    if m == 0:
+        return []
+    if (dim, m) not in _EAS_TABLE:
+        raise NotImplementedError(f"EAS variant E{m} in {dim}D")  # enhancedassumedstrains.hh:250-256
+    return _EAS_TABLE[(dim, m)]
+
+
+def eas_Mhat(dim, m, xi):
+    s = dim * (dim + 1) // 2
+    M = np.zeros((s, m))
+    t = 2.0 * np.asarray(xi) - 1.0
+    for j, (row, dirs) in enumerate(eas_table(dim, m)):
+        M[row, j] = np.prod([t[k] for k in dirs])
+    return M
+
+
+def transformation_matrix(Jt):
+    """Voigt transformation matrix from the transposed Jacobian (tensorutils.hh:408-465).
+    Batched over leading dims of Jt[..., d, d] with Jt[i, j] = dx_j/dxi_i."""
+    d = Jt.shape[-1]
+    if d == 2:
+        J11, J12, J21, J22 = Jt[..., 0, 0], Jt[..., 0, 1], Jt[..., 1, 0], Jt[..., 1, 1]
+        rows = [[J11 * J11, J12 * J12, J11 * J12],
+                [J21 * J21, J22 * J22, J21 * J22],
+                [2 * J11 * J21, 2 * J12 * J22, J21 * J12 + J11 * J22]]
+    else:
+        J11, J12, J13 = Jt[..., 0, 0], Jt[..., 0, 1], Jt[..., 0, 2]
+        J21, J22, J23 = Jt[..., 1, 0], Jt[..., 1, 1], Jt[..., 1, 2]
+        J31, J32, J33 = Jt[..., 2, 0], Jt[..., 2, 1], Jt[..., 2, 2]
+        rows = [
+            [J11 * J11, J12 * J12, J13 * J13, J12 * J13, J11 * J13, J11 * J12],
+            [J21 * J21, J22 * J22, J23 * J23, J22 * J23, J21 * J23, J21 * J22],
+            [J31 * J31, J32 * J32, J33 * J33, J32 * J33, J31 * J33, J31 * J32],
+            [2 * J21 * J31, 2 * J22 * J32, 2 * J23 * J33, J22 * J33 + J32 * J23, J31 * J23 + J21 * J33, J21 * J32 + J31 * J22],
+            [2 * J11 * J31, 2 * J12 * J32, 2 * J13 * J33, J12 * J33 + J32 * J13, J11 * J33 + J31 * J13, J11 * J32 + J31 * J12],
+            [2 * J11 * J21, 2 * J12 * J22, 2 * J13 * J23, J12 * J23 + J22 * J13, J11 * J23 + J21 * J13, J11 * J22 + J12 * J21],
+        ]
+    return np.stack([np.stack(r, axis=-1) for r in rows], axis=-2)
+
+
+# --------------------------------------------------------------------------------------
+# Element kernels, batched over elements
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class ElementKind:
+    """dim, basis order (1 = Q1, 2 = Q2), strain ('linear' | 'gl'), EAS parameter count."""
+
+    dim: int
+    order: int = 1
+    strain: str = "gl"
+    eas_m: int = 0
+    quad_n: int | None = None  # points per direction; default = order+1 (rule of order 2*order)
+
+    @property
+    def nodes(self):
+        return (self.order + 1) ** self.dim
+
+    @property
+    def ndof(self):
+        return self.nodes * self.dim
+
+    @property
+    def corners(self):
+        return 2**self.dim
+
+    def rule(self):
+        return tensor_rule(self.dim, self.quad_n or (self.order + 1))
+
+
+def _geometry(kind: ElementKind, X, xi):
+    """Multilinear cube geometry from the 2^d corners X[e, c, d] (the *grid* geometry is
+    used also for Q2 elements, nonlinearelastic.hh:117).  Returns Jt[e, i, j] = dx_j/dxi_i,
+    its inverse and |det|."""
+    _, dNg = shape_functions(kind.dim, 1, xi)
+    Jt = np.einsum("ci,ecj->eij", dNg, X)
+    detJ = np.abs(np.linalg.det(Jt))
+    return Jt, np.linalg.inv(Jt), detJ
+
+
+def _b_operator(kind: ElementKind, gradN, F):
+    """B[e, a, s, d] = dE_voigt/dd_a (restated in the reference in
+    strainenhancements/easfunctions/displacementgradient.hh:123-147).  For linear strains
+    F is the identity (linearelastic.hh strainFunction)."""
+    d = kind.dim
+    ne, nn = gradN.shape[0], gradN.shape[1]
+    s = d * (d + 1) // 2
+    B = np.zeros((ne, nn, s, d))
+    for q, (i, j) in enumerate(voigt_pairs(d)):
+        if i == j:
+            # N_a,i * g_i^T   with g_i = column i of F
+            B[:, :, q, :] = gradN[:, :, i, None] * F[:, None, :, i]
+        else:
+            B[:, :, q, :] = gradN[:, :, j, None] * F[:, None, :, i] + gradN[:, :, i, None] * F[:, None, :, j]
+    return B
+
+
+def element_quantities(kind: ElementKind, mat: Material, X, u, alpha=None, want=("K", "R", "E")):
+    """Per-element tangent K[e, ndof, ndof], residual R[e, ndof], energy E[e].
+
+    Follows NonLinearElastic/LinearElastic::calculate{Matrix,Vector,Scalar}Impl
+    (mechanics/nonlinearelastic.hh:376-430, mechanics/linearelastic.hh:354-405) and, with
+    eas_m > 0, EnhancedAssumedStrains (mechanics/enhancedassumedstrains.hh:258-348,378-434).
+
+    X: corner coordinates [e, 2^d, d]; u: nodal displacements [e, nodes, d];
+    alpha: EAS parameters [e, m].
+    Also returns the EAS blocks (D, L, Rtilde) when eas_m > 0.
+    """
+    d, nn, nd, m = kind.dim, kind.nodes, kind.ndof, kind.eas_m
+    s = d * (d + 1) // 2
+    ne = X.shape[0]
+    pts, wts = kind.rule()
+    K = np.zeros((ne, nn, d, nn, d))
+    R = np.zeros((ne, nn, d))
+    En = np.zeros(ne)
+    if m:
+        if alpha is None:
+            alpha = np.zeros((ne, m))
+        Dm = np.zeros((ne, m, m))
+        Lm = np.zeros((ne, m, nn, d))
+        Rt = np.zeros((ne, m))
+        # EX ctor: T0InverseTransformed = (T(center) * detJ0)^-1   (easvariants/helperfunctions.hh:18-25)
+        Jt0, _, detJ0 = _geometry(kind, X, np.full(d, 0.5))
+        T0inv = np.linalg.inv(transformation_matrix(Jt0) * detJ0[:, None, None])
+    I = np.eye(d)
+    for xi, w in zip(pts, wts):
+        _, dN = shape_functions(d, kind.order, xi)
+        Jt, Jtinv, detJ = _geometry(kind, X, xi)
+        gradN = np.einsum("eji,ai->eaj", Jtinv, dN)  # dN_a/dx_j
+        H = np.einsum("eac,eaj->ecj", u, gradN)  # H[c, j] = du_c/dx_j
+        if kind.strain == "gl":
+            F = I + H
+            Em = 0.5 * (H + np.swapaxes(H, -1, -2) + np.einsum("eki,ekj->eij", H, H))
+        else:
+            F = np.broadcast_to(I, H.shape)
+            Em = 0.5 * (H + np.swapaxes(H, -1, -2))
+        Ev = to_voigt(Em, strain=True)
+        if m:
+            Mh = eas_Mhat(d, m, xi)
+            M = np.einsum("epq,qm->epm", T0inv, Mh) / detJ[:, None, None]  # linandglstrains.hh E*::operator()
+            Ev = Ev + np.einsum("epm,em->ep", M, alpha)
+        psi, S, C = mat.evaluate(Ev)
+        if kind.strain == "linear":
+            # LinearElastic: stress = C*eps, energy = 0.5 eps.C.eps (linearelastic.hh:158-177)
+            S = np.einsum("epq,eq->ep", C, Ev)
+            psi = 0.5 * np.einsum("ep,ep->e", Ev, S)
+        B = _b_operator(kind, gradN, F)
+        wd = w * detJ
+        if "K" in want:
+            K += np.einsum("eapi,epq,ebqk,e->eaibk", B, C, B, wd, optimize=True)
+            if kind.strain == "gl":
+                Sm = from_voigt(S, strain=False)
+                kg = np.einsum("eai,eij,ebj,e->eab", gradN, Sm, gradN, wd, optimize=True)
+                for c in range(d):
+                    K[:, :, c, :, c] += kg
+        if "R" in want or m:
+            R += np.einsum("eapi,ep,e->eai", B, S, wd)
+        if "E" in want:
+            En += psi * wd
+        if m:
+            CM = np.einsum("epq,eqm->epm", C, M)
+            Dm += np.einsum("epm,epn,e->emn", M, CM, wd)
+            Lm += np.einsum("epm,eapi,e->emai", CM, B, wd)
+            Rt += np.einsum("epm,ep,e->em", M, S, wd)
+    K = K.reshape(ne, nd, nd)
+    R = R.reshape(ne, nd)
+    out = {}
+    if m:
+        Lf = Lm.reshape(ne, m, nd)
+        Dinv = np.linalg.inv(Dm)
+        # K.upper -= L^T D^-1 L ; lower = upper^T   (enhancedassumedstrains.hh:292-296)
+        Kc = K - np.einsum("emi,emn,enj->eij", Lf, Dinv, Lf, optimize=True)
+        iu = np.triu_indices(nd)
+        Ks = np.zeros_like(Kc)
+        Ks[:, iu[0], iu[1]] = Kc[:, iu[0], iu[1]]
+        Ks = Ks + np.swapaxes(np.triu(Ks, 1), -1, -2)
+        K = Ks
+        R = R - np.einsum("emi,emn,en->ei", Lf, Dinv, Rt, optimize=True)  # :341-345
+        out.update(D=Dm, L=Lf, Rtilde=Rt)
+        En = np.full(ne, np.nan)  # EAS elements expose no potential (:302-310)
+    out.update(K=K, R=R, E=En)
+    return out
+
+
+def eas_update_alpha(kind, mat, X, u, alpha, du):
+    """alpha -= D^-1 (Rtilde + L * du_e), all at the OLD (u, alpha)
+    (enhancedassumedstrains.hh:225-248; called on CORRECTION_UPDATED before x is updated,
+    solver/nonlinearsolver/newtonraphson.hh:230-235)."""
+    q = element_quantities(kind, mat, X, u, alpha, want=())
+    rhs = q["Rtilde"] + np.einsum("emi,ei->em", q["L"], du.reshape(du.shape[0], -1))
+    return alpha - np.linalg.solve(q["D"], rhs[..., None])[..., 0]
+
+
+def stress_at(kind, mat, X, u, xi, alpha=None):
+    """PK2/linear stress (Voigt) at local position xi for every element; with EAS and
+    linear strains alpha = -D^-1 L d as in EnhancedAssumedStrains::calculateAtImpl
+    (enhancedassumedstrains.hh:146-176)."""
+    d = kind.dim
+    _, dN = shape_functions(d, kind.order, xi)
+    Jt, Jtinv, detJ = _geometry(kind, X, np.asarray(xi, float))
+    gradN = np.einsum("eji,ai->eaj", Jtinv, dN)
+    H = np.einsum("eac,eaj->ecj", u, gradN)
+    if kind.strain == "gl":
+        Em = 0.5 * (H + np.swapaxes(H, -1, -2) + np.einsum("eki,ekj->eij", H, H))
+    else:
+        Em = 0.5 * (H + np.swapaxes(H, -1, -2))
+    Ev = to_voigt(Em)
+    if kind.eas_m:
+        if alpha is None:
+            q = element_quantities(kind, mat, X, u, np.zeros((X.shape[0], kind.eas_m)), want=())
+            alpha = -np.linalg.solve(q["D"], np.einsum("emi,ei->em", q["L"], u.reshape(u.shape[0], -1))[..., None])[..., 0]
+        Jt0, _, detJ0 = _geometry(kind, X, np.full(d, 0.5))
+        T0inv = np.linalg.inv(transformation_matrix(Jt0) * detJ0[:, None, None])
+        M = np.einsum("epq,qm->epm", T0inv, eas_Mhat(d, kind.eas_m, xi)) / detJ[:, None, None]
+        Ev = Ev + np.einsum("epm,em->ep", M, alpha)
+    psi, S, C = mat.evaluate(Ev)
+    if kind.strain == "linear":
+        S = np.einsum("epq,eq->ep", C, Ev)
+    return S
+
+
+# --------------------------------------------------------------------------------------
+# Structured meshes with YaspGrid-compatible numbering
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Mesh:
+    dim: int
+    order: int
+    node_coords: np.ndarray  # [nNodes, dim]   Lagrange node positions
+    elem_nodes: np.ndarray  # [nElem, nodes]  global node ids in DUNE local order
+    corner_coords: np.ndarray  # [nElem, 2^d, dim]
+    cells: tuple = ()
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def n_nodes(self):
+        return self.node_coords.shape[0]
+
+    @property
+    def n_elem(self):
+        return self.elem_nodes.shape[0]
+
+    def elem_dofs(self, layout="interleaved"):
+        """power<d>(lagrange<k>, FlatInterleaved) => dof = d*node + comp;
+        FlatLexicographic => comp*nNodes + node (ikarus/python/test/linearelastictest.py:213-231).
+        Element-local order is node-major, component-minor (finiteelements/fehelper.hh:145-153)."""
+        d = self.dim
+        if layout == "interleaved":
+            return (self.elem_nodes[:, :, None] * d + np.arange(d)[None, None, :]).reshape(self.n_elem, -1)
+        return (np.arange(d)[None, None, :] * self.n_nodes + self.elem_nodes[:, :, None]).reshape(self.n_elem, -1)
+
+
+def structured_mesh(cells, bbox, order=1, mapping=None) -> Mesh:
+    """YaspGrid(bbox, cells): axis-aligned cells, vertices and elements numbered
+    lexicographically with x fastest; lagrange<1> global index = vertex index.
+    For order 2 the nodes live on the (2n+1)^d lattice numbered lexicographically
+    (NOT dune-functions' vertex/edge/face/cell ordering, which cannot be cross-checked
+    here -- the device code consumes elemDofs and is numbering-agnostic)."""
+    cells = tuple(int(c) for c in cells)
+    dim = len(cells)
+    npts = [order * c + 1 for c in cells]
+    grids = [np.linspace(0.0, bbox[k], npts[k]) for k in range(dim)]
+    # lexicographic, x fastest
+    mg = np.meshgrid(*grids, indexing="ij")
+    coords = np.stack([g.reshape(-1, order="F") for g in mg], axis=-1)
+    stride = np.cumprod([1] + npts[:-1])
+    eidx = np.stack([g.reshape(-1, order="F") for g in np.meshgrid(*[np.arange(c) for c in cells], indexing="ij")], axis=-1)
+    n1 = order + 1
+    loc = np.array([[(a // n1**k) % n1 for k in range(dim)] for a in range(n1**dim)])
+    elem_nodes = ((eidx[:, None, :] * order + loc[None, :, :]) * stride[None, None, :]).sum(-1)
+    cloc = np.array([[(a >> k) & 1 for k in range(dim)] for a in range(2**dim)]) * order
+    corner_nodes = ((eidx[:, None, :] * order + cloc[None, :, :]) * stride[None, None, :]).sum(-1)
+    if mapping is not None:
+        coords = mapping(coords)
+    return Mesh(dim, order, coords, elem_nodes.astype(np.int64), coords[corner_nodes], cells)
+
+
+def boundary_nodes(mesh: Mesh, axis: int, value: float, tol=1e-8):
+    return np.nonzero(np.abs(mesh.node_coords[:, axis] - value) < tol)[0]
+
+
+def fix_nodes(mesh: Mesh, nodes, layout="interleaved", comps=None):
+    """Dirichlet flags (utils/dirichletvalues.hh:111-131 fixBoundaryDOFs equivalent)."""
+    d = mesh.dim
+    flags = np.zeros(mesh.n_nodes * d, dtype=bool)
+    comps = range(d) if comps is None else comps
+    for c in comps:
+        if layout == "interleaved":
+            flags[np.asarray(nodes) * d + c] = True
+        else:
+            flags[c * mesh.n_nodes + np.asarray(nodes)] = True
+    return flags
+
+
+# --------------------------------------------------------------------------------------
+# Flat assembler (ikarus/assembler/interface.hh, simpleassemblers.inl)
+# --------------------------------------------------------------------------------------
+
+
+def constraints_below(flags):
+    """constraintsBelow_[i] = number of fixed dofs with index < i (assembler/interface.hh:51-62)."""
+    f = np.asarray(flags, dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(f)[:-1]])
+
+
+def build_pattern(elem_dofs, n, flags=None):
+    """Sparsity pattern as Eigen's setFromTriplets leaves it (compressed, inner indices
+    sorted) -- simpleassemblers.inl:206-251.  The pattern is structurally symmetric, so
+    the CSC arrays Eigen holds equal the CSR arrays returned here.  With flags: the
+    Reduced pattern (rows/cols of fixed dofs dropped, index i - constraintsBelow(i)).
+    Returns (outer[n+1] int64, inner[nnz] int32)."""
+    ed = np.asarray(elem_dofs, dtype=np.int64)
+    if flags is not None:
+        cb = constraints_below(flags)
+        keep = ~np.asarray(flags)[ed]
+        red = ed - cb[ed]
+        n = int(n - np.count_nonzero(flags))
+    ne, nd = ed.shape
+    rows_l, cols_l = [], []
+    chunk = max(1, 2_000_000 // (nd * nd))
+    keys = []
+    for s in range(0, ne, chunk):
+        e = ed[s:s + chunk]
+        if flags is None:
+            r = np.repeat(e, nd, axis=1).ravel()
+            c = np.tile(e, (1, nd)).ravel()
+        else:
+            k = keep[s:s + chunk]
+            rr = red[s:s + chunk]
+            msk = (k[:, :, None] & k[:, None, :]).ravel()
+            r = np.repeat(rr, nd, axis=1).ravel()[msk]
+            c = np.tile(rr, (1, nd)).ravel()[msk]
+        keys.append(np.unique(r * n + c))
+    key = np.unique(np.concatenate(keys)) if keys else np.zeros(0, np.int64)
+    rows = key // n
+    inner = (key % n).astype(np.int32)
+    outer = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(outer, rows + 1, 1)
+    outer = np.cumsum(outer)
+    return outer, inner
+
+
+def linear_indices(elem_dofs, outer, inner):
+    """Position of (row r, col c) in the value array (utils/eigensparseaddon.hh:19-31)."""
+    ed = np.asarray(elem_dofs, dtype=np.int64)
+    ne, nd = ed.shape
+    r = np.repeat(ed, nd, axis=1)
+    c = np.tile(ed, (1, nd))
+    n = outer.shape[0] - 1
+    key = outer[:-1].repeat(np.diff(outer)) * 0  # placeholder to keep dtype
+    rowkey = np.repeat(np.arange(n, dtype=np.int64), np.diff(outer)) * n + inner
+    pos = np.searchsorted(rowkey, (r * n + c).ravel())
+    return pos.reshape(ne, nd * nd)
+
+
+class FlatAssembler:
+    """Restatement of Sparse/DenseFlatAssembler for one element kind + material on a mesh.
+
+    matrix()/vector()/scalar() mirror assembler/interface.hh:300-462; DBC modes follow
+    simpleassemblers.inl:59-204 (sparse) and :301-375 (dense).
+    `fext` is the lambda-proportional external load vector (host-sampled volume/Neumann
+    loads and point loads): R = F_int - lambda * fext.
+    """
+
+    def __init__(self, mesh: Mesh, kind: ElementKind, mat: Material, flags, layout="interleaved", fext=None):
+        self.mesh, self.kind, self.mat = mesh, kind, mat
+        self.flags = np.asarray(flags, dtype=bool)
+        self.elem_dofs = mesh.elem_dofs(layout)
+        self.n = mesh.n_nodes * mesh.dim
+        self.cb = constraints_below(self.flags)
+        self.n_red = self.n - int(self.flags.sum())
+        self.fext = np.zeros(self.n) if fext is None else np.asarray(fext, float)
+        self.alpha = np.zeros((mesh.n_elem, kind.eas_m)) if kind.eas_m else None
+        self._pat = {}
+
+    # -- maps ---------------------------------------------------------------------------
+    def size(self):
+        return self.n
+
+    def reduced_size(self):
+        return self.n_red
+
+    def create_full_vector(self, red):
+        full = np.zeros(self.n)
+        full[~self.flags] = red
+        return full
+
+    def create_reduced_vector(self, full):
+        return np.asarray(full)[~self.flags].copy()
+
+    def pattern(self, dbc="raw"):
+        key = "reduced" if dbc == "reduced" else "raw"
+        if key not in self._pat:
+            self._pat[key] = build_pattern(self.elem_dofs, self.n, self.flags if key == "reduced" else None)
+        return self._pat[key]
+
+    # -- element sweep ------------------------------------------------------------------
+    def _local(self, d, want):
+        u = d[self.elem_dofs].reshape(self.mesh.n_elem, self.kind.nodes, self.kind.dim)
+        return element_quantities(self.kind, self.mat, self.mesh.corner_coords, u, self.alpha, want)
+
+    def scalar(self, d, lam):
+        q = self._local(np.asarray(d, float), ("E",))
+        return float(q["E"].sum() - lam * self.fext @ d)
+
+    def vector(self, d, lam, dbc="full"):
+        q = self._local(np.asarray(d, float), ("R",))
+        R = np.zeros(self.n)
+        np.add.at(R, self.elem_dofs.ravel(), q["R"].ravel())
+        R -= lam * self.fext
+        if dbc == "raw":
+            return R
+        if dbc == "full":
+            R[self.flags] = 0.0
+            return R
+        return R[~self.flags]
+
+    def matrix_values(self, d, lam, dbc="full"):
+        """CSR/CSC value array in the pattern of `pattern(dbc)`."""
+        q = self._local(np.asarray(d, float), ("K",))
+        Ke = q["K"]
+        nd = self.kind.ndof
+        if dbc == "reduced":
+            outer, inner = self.pattern("reduced")
+            n = self.n_red
+            keep = ~self.flags[self.elem_dofs]
+            red = self.elem_dofs - self.cb[self.elem_dofs]
+            r = np.repeat(red, nd, axis=1)
+            c = np.tile(red, (1, nd))
+            msk = (keep[:, :, None] & keep[:, None, :]).reshape(self.mesh.n_elem, -1)
+            rowkey = np.repeat(np.arange(n, dtype=np.int64), np.diff(outer)) * n + inner
+            pos = np.searchsorted(rowkey, (r * n + c)[msk])
+            vals = np.zeros(inner.shape[0])
+            np.add.at(vals, pos, Ke.reshape(self.mesh.n_elem, -1)[msk])
+            return vals
+        outer, inner = self.pattern("raw")
+        pos = linear_indices(self.elem_dofs, outer, inner)
+        vals = np.zeros(inner.shape[0])
+        np.add.at(vals, pos.ravel(), Ke.reshape(-1))
+        if dbc == "full":
+            rows = np.repeat(np.arange(self.n), np.diff(outer))
+            kill = self.flags[rows] | self.flags[inner]
+            vals[kill] = 0.0
+            vals[(rows == inner) & self.flags[rows]] = 1.0
+        return vals
+
+    def matrix(self, d, lam, dbc="full"):
+        import scipy.sparse as sp
+
+        outer, inner = self.pattern(dbc)
+        n = self.n_red if dbc == "reduced" else self.n
+        return sp.csr_matrix((self.matrix_values(d, lam, dbc), inner, outer), shape=(n, n))
+
+    def dense_matrix(self, d, lam, dbc="full"):
+        """DenseFlatAssembler (simpleassemblers.inl:301-375)."""
+        q = self._local(np.asarray(d, float), ("K",))
+        A = np.zeros((self.n, self.n))
+        for e in range(self.mesh.n_elem):
+            idx = self.elem_dofs[e]
+            A[np.ix_(idx, idx)] += q["K"][e]
+        if dbc == "full":
+            A[:, self.flags] = 0.0
+            A[self.flags, :] = 0.0
+            A[self.flags, self.flags] = 1.0
+        elif dbc == "reduced":
+            A = A[np.ix_(~self.flags, ~self.flags)]
+        return A
+
+    def update_eas(self, d, correction_full):
+        if not self.kind.eas_m:
+            return
+        sh = (self.mesh.n_elem, self.kind.nodes, self.kind.dim)
+        u = np.asarray(d)[self.elem_dofs].reshape(sh)
+        du = np.asarray(correction_full)[self.elem_dofs].reshape(sh)
+        self.alpha = eas_update_alpha(self.kind, self.mat, self.mesh.corner_coords, u, self.alpha, du)
+
+
+# --------------------------------------------------------------------------------------
+# NewtonRaphson + LoadControl (solver/nonlinearsolver/newtonraphson.hh:196-257,
+# controlroutines/loadcontrol.inl:21-57)
+# --------------------------------------------------------------------------------------
+
+
+def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full", linear_solver=None):
+    import scipy.sparse.linalg as spla
+
+    if linear_solver is None:
+        linear_solver = lambda A, b: spla.spsolve(A.tocsc(), b)
+    d = np.array(d, float)
+    r = asm.vector(d, lam, dbc)
+    A = asm.matrix(d, lam, dbc)
+    rnorm = np.linalg.norm(r)
+    it = 0
+    while rnorm > tol and it < max_iter:
+        corr = linear_solver(A, -r)
+        full = corr if dbc != "reduced" else asm.create_full_vector(corr)
+        asm.update_eas(d, full)  # CORRECTION_UPDATED before the solution update (:230-235)
+        d = d + full
+        r = asm.vector(d, lam, dbc)
+        A = asm.matrix(d, lam, dbc)
+        rnorm = np.linalg.norm(r)
+        it += 1
+    return d, dict(iterations=it, success=it != max_iter, residual_norm=rnorm)
+
+
+def load_control(asm: FlatAssembler, d, load_steps, t_begin, t_end, lam0=0.0, **nr):
+    """LoadControl::run: initial solve at the current lambda, then loadSteps increments."""
+    step = (t_end - t_begin) / load_steps
+    lam = lam0
+    total = 0
+    d, info = newton_raphson(asm, d, lam, **nr)
+    total += info["iterations"]
+    curve = [(lam, float(np.abs(d).max()))]
+    ok = info["success"]
+    per_step = [info["iterations"]]
+    for _ in range(load_steps):
+        if not ok:
+            break
+        lam += step
+        d, info = newton_raphson(asm, d, lam, **nr)
+        total += info["iterations"]
+        per_step.append(info["iterations"])
+        ok = info["success"]
+        curve.append((lam, float(np.abs(d).max())))
+    return d, lam, dict(total_iterations=total, success=ok, curve=curve, per_step=per_step)

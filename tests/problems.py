@@ -1,0 +1,37 @@
+"""Shared problem builders for the parity tests (oracle side only builds inputs)."""
+import numpy as np
+
+import ikarus_oracle as o
+
+
+def cantilever(dim, mat_kind, eas_m, cells=None, E=100.0, nu=0.3, L=10.0, h=2.0):
+    """tests/src/testcantileverbeam.hh:83-198 of the reference."""
+    if cells is None:
+        cells = (10, 1, 1) if dim == 3 else (10, 1)
+    bbox = (L, h, h) if dim == 3 else (L, h)
+    mesh = o.structured_mesh(cells, bbox)
+    lam, mu = o.lame_from_E_nu(E, nu)
+    mat = o.Material(mat_kind, lam, mu, plane_strain=(dim == 2))
+    kind = o.ElementKind(dim, 1, "gl", eas_m)
+    flags = o.fix_nodes(mesh, o.boundary_nodes(mesh, 0, 0.0))
+    fext = np.zeros(mesh.n_nodes * dim)
+    X = mesh.node_coords
+    pts = [(L, h, h), (L, h, 0.0)] if dim == 3 else [(L, h)]
+    for p in pts:
+        n = np.nonzero(np.all(np.abs(X - np.array(p)) < 1e-9, axis=1))[0][0]
+        fext[n * dim + 1] = -1.0  # vec[idx] -= -lambda  (testcantileverbeam.hh:56-80)
+    return mesh, kind, mat, flags, fext
+
+
+def distorted(mesh, amp, seed):
+    """Randomly perturb interior-and-boundary vertices (same idea as
+    tests/src/testcommon.hh:179-248 createUGGridFromCorners with random distortion)."""
+    rng = np.random.default_rng(seed)
+    hmin = min(b / c for b, c in zip(mesh.node_coords.max(0), mesh.cells))
+    coords = mesh.node_coords + amp * hmin * rng.uniform(-1, 1, mesh.node_coords.shape)
+    n1 = mesh.order + 1
+    # corner nodes of each element in local lexicographic order
+    dim = mesh.dim
+    cidx = [sum(((a >> k) & 1) * mesh.order * n1**k for k in range(dim)) for a in range(2**dim)]
+    corner_nodes = mesh.elem_nodes[:, cidx]
+    return o.Mesh(mesh.dim, mesh.order, coords, mesh.elem_nodes, coords[corner_nodes], mesh.cells)
