@@ -1,0 +1,13 @@
+"""ikarus_b200: B200-native drop-in for Ikarus' global FEM assembly hot path.
+
+Host-side mirror of the reference's assembler interface over the C-ABI in include/ikb200.h.
+"""
+from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, DeviceMatrix, FERequirements,  # noqa: F401
+                        MatrixAffordance, ScalarAffordance, SparseFlatAssembler, VectorAffordance, elastoStatics,
+                        makeDenseFlatAssembler, makeSparseFlatAssembler)
+from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, nonLinearElastic,  # noqa: F401
+                 planeStrain, skills, toLamesFirstParameterAndShearModulus)
+from .solvers import (ControlInformation, DeviceLinearSolver, LoadControl, LoadControlConfig, NewtonRaphson,  # noqa: F401
+                      NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,88 @@
+"""ctypes binding of libikb200.so (include/ikb200.h).  No torch types cross this boundary."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libikb200.so")
+
+IKB_ABI_VERSION = 1
+OK, EINVAL, ECUDA, ESTATE, ENOTIMPL, EMATERIAL, ENCCL = 0, -1, -2, -3, -4, -5, -6
+STRAIN_LINEAR, STRAIN_GL = 0, 1
+MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE = 0, 1, 2
+DBC_RAW, DBC_REDUCED, DBC_FULL = 0, 1, 2
+SCALAR, VECTOR, MATRIX = 1, 2, 4
+
+
+class Desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("dim", C.c_int32), ("order", C.c_int32), ("strain", C.c_int32),
+                ("material", C.c_int32), ("plane_strain", C.c_int32), ("eas_m", C.c_int32), ("device", C.c_int32),
+                ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64)]
+
+
+# every symbol include/ikb200.h declares (tests check that the library exports all of them)
+SYMBOLS = {
+    "ikb_create": [C.POINTER(C.c_void_p), C.POINTER(Desc)],
+    "ikb_destroy": [C.c_void_p],
+    "ikb_last_error": [C.c_void_p, C.c_char_p, C.c_size_t],
+    "ikb_upload_mesh": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "ikb_upload_dirichlet": [C.c_void_p, C.c_void_p],
+    "ikb_build_pattern": [C.c_void_p],
+    "ikb_pattern_nnz": [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+    "ikb_get_pattern": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "ikb_get_constraints_below": [C.c_void_p, C.c_void_p],
+    "ikb_element_linear_indices": [C.c_void_p, C.c_int64, C.c_void_p],
+    "ikb_set_solution": [C.c_void_p, C.c_void_p],
+    "ikb_set_parameter": [C.c_void_p, C.c_double],
+    "ikb_set_external_load": [C.c_void_p, C.c_void_p, C.c_int],
+    "ikb_assemble": [C.c_void_p, C.c_uint, C.c_int],
+    "ikb_get_vector": [C.c_void_p, C.c_int, C.c_void_p],
+    "ikb_get_scalar": [C.c_void_p, C.POINTER(C.c_double)],
+    "ikb_get_matrix_values": [C.c_void_p, C.c_int, C.c_void_p],
+    "ikb_get_dense_matrix": [C.c_void_p, C.c_int, C.c_void_p],
+    "ikb_vector_norm": [C.c_void_p, C.c_int, C.POINTER(C.c_double)],
+    "ikb_eas_update": [C.c_void_p, C.c_void_p],
+    "ikb_eas_get_alpha": [C.c_void_p, C.c_void_p],
+    "ikb_eas_set_alpha": [C.c_void_p, C.c_void_p],
+    "ikb_pcg_solve": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_int),
+                      C.POINTER(C.c_double)],
+    "ikb_update_solution": [C.c_void_p, C.c_int, C.c_void_p],
+    "ikb_get_solution": [C.c_void_p, C.c_void_p],
+    "ikb_spmv": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "ikb_set_row_ownership": [C.c_void_p, C.c_int64, C.c_int64],
+    "ikb_nccl_unique_id": [C.c_void_p],
+    "ikb_comm_init": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+    "ikb_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "ikb_sync": [C.c_void_p],
+    "ikb_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
+    "ikb_device_ptr": [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)],
+    "ikb_time_phase": [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float)],
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  There is no CPU fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m ikarus_b200.build` (nvcc, sm_100a). "
+                "ikarus_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

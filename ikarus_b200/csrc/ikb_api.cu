@@ -1,0 +1,1019 @@
+// C-ABI entry points of libikb200.so (see include/ikb200.h).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include "ikb_elem_q1.cuh"
+#include "ikb_gather.cuh"
+#include "ikb_internal.cuh"
+#include "ikb_pattern.cuh"
+#include "ikb_pcg.cuh"
+
+using namespace ikb;
+
+namespace {
+
+constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs; fixed so reductions are reproducible
+
+Handle* H(ikb_handle h) { return reinterpret_cast<Handle*>(h); }
+
+int checkHandle(Handle* h) {
+  if (!h) return IKB_EINVAL;
+  cudaSetDevice(h->device);
+  return IKB_OK;
+}
+
+int dbcValid(int dbc) { return dbc == IKB_DBC_RAW || dbc == IKB_DBC_REDUCED || dbc == IKB_DBC_FULL; }
+
+int launchElements(Handle* h, unsigned what) {
+  ElemArgs A;
+  A.X = h->X.p;
+  A.elemNode = h->elemNode.p;
+  A.U = h->U.p;
+  A.Kst = h->Kst.p;
+  A.Rst = h->Rst.p;
+  A.Est = h->Est.p;
+  A.errFlag = h->errFlag.p;
+  A.nElem = h->nElem;
+  A.nNodes = h->nNodes;
+  A.layout = h->layout;
+  A.lambda = h->desc.lambda;
+  A.mu = h->desc.mu;
+  A.what = what;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (h->order == 1 && h->easM == 0) {
+    if (h->dim == 3) {
+      if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
+      if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
+      if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
+    } else {
+      if (h->form == FORM_LE) e = launchElemQ1<2, FORM_LE>(A, h->stream);
+      if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
+      if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
+    }
+  } else {
+    return fail(h, IKB_ENOTIMPL, "element kind not implemented on the device yet (order 2 / EAS)");
+  }
+  h->launches++;
+  if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("element kernel: ") + cudaGetErrorString(e));
+  return IKB_OK;
+}
+
+int ensureStaging(Handle* h) {
+  const size_t dd = (size_t)h->dim * h->dim;
+  if (!h->Kst.p) IKB_CUDA(h, h->Kst.alloc((size_t)h->nElem * h->npair * dd));
+  if (!h->Rst.p) IKB_CUDA(h, h->Rst.alloc((size_t)h->nElem * h->nd));
+  if (!h->Est.p) IKB_CUDA(h, h->Est.alloc((size_t)h->nElem));
+  return IKB_OK;
+}
+
+int ensureSolution(Handle* h) {
+  if (!h->U.p) {
+    IKB_CUDA(h, h->U.alloc((size_t)h->nDof));
+    IKB_CUDA(h, cudaMemsetAsync(h->U.p, 0, h->U.bytes(), h->stream));
+  }
+  return IKB_OK;
+}
+
+int ensureReduced(Handle* h) {
+  if (h->reducedBuilt) return IKB_OK;
+  if (!h->hasFlags) return fail(h, IKB_ESTATE, "Reduced mode needs ikb_upload_dirichlet first");
+  if (!h->patternBuilt) return fail(h, IKB_ESTATE, "pattern not built");
+  if (h->rowBegin != 0 || h->rowEnd != h->nNodes)
+    return fail(h, IKB_ENOTIMPL, "DBCOption::Reduced is only available on an unpartitioned handle");
+  const PatternView P = h->view();
+  const int64_t n = h->nDof;
+  const int tpb = 256;
+  // constraintsBelow = exclusive prefix sum of the flags (assembler/interface.hh:51-62)
+  DevBuf<int32_t> fi;
+  IKB_CUDA(h, fi.alloc((size_t)n + 1));
+  IKB_CUDA(h, cudaMemsetAsync(fi.p, 0, fi.bytes(), h->stream));
+  flags_to_int_kernel<<<gridFor(n, tpb), tpb, 0, h->stream>>>(h->flags.p, n, fi.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, h->cbelow.alloc((size_t)n + 1));
+  size_t tmpBytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, fi.p, h->cbelow.p, n + 1, h->stream);
+  DevBuf<uint8_t> tmp;
+  IKB_CUDA(h, tmp.alloc(tmpBytes));
+  IKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, fi.p, h->cbelow.p, n + 1, h->stream));
+  h->launches++;
+  int32_t nFixed = 0;
+  IKB_CUDA(h, cudaMemcpyAsync(&nFixed, h->cbelow.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->nRed = n - nFixed;
+
+  IKB_CUDA(h, h->freeCnt.alloc((size_t)h->nBlocks * h->dim));
+  IKB_CUDA(h, h->freeTot.alloc((size_t)P.nRowNodes * h->dim));
+  free_counts_kernel<<<gridFor(P.nRowNodes, tpb), tpb, 0, h->stream>>>(P, h->flags.p, h->freeCnt.p, h->freeTot.p);
+  IKB_LAUNCH_CHECK(h);
+  const int64_t nRows = P.nRowNodes * h->dim;
+  DevBuf<int64_t> rowCount;
+  IKB_CUDA(h, rowCount.alloc((size_t)nRows + 1));
+  IKB_CUDA(h, cudaMemsetAsync(rowCount.p, 0, rowCount.bytes(), h->stream));
+  row_free_count_kernel<<<gridFor(nRows, tpb), tpb, 0, h->stream>>>(P, h->flags.p, h->freeTot.p, rowCount.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, h->redRowStart.alloc((size_t)nRows + 1));
+  tmpBytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, rowCount.p, h->redRowStart.p, nRows + 1, h->stream);
+  IKB_CUDA(h, tmp.alloc(tmpBytes));
+  IKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, rowCount.p, h->redRowStart.p, nRows + 1, h->stream));
+  h->launches++;
+  IKB_CUDA(h, cudaMemcpyAsync(&h->nnzRed, h->redRowStart.p + nRows, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                              h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  IKB_CUDA(h, h->redInner.alloc((size_t)std::max<int64_t>(h->nnzRed, 1)));
+  IKB_CUDA(h, h->redOuter.alloc((size_t)h->nRed + 1));
+  reduced_inner_kernel<<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(P, h->flags.p, h->freeCnt.p, h->freeTot.p,
+                                                                        h->redRowStart.p, h->cbelow.p, h->redInner.p);
+  IKB_LAUNCH_CHECK(h);
+  reduced_outer_kernel<<<gridFor(std::max<int64_t>(nRows, 1), tpb), tpb, 0, h->stream>>>(
+      h->flags.p, h->cbelow.p, h->redRowStart.p, nRows, 0, h->redOuter.p, h->nnzRed, h->nRed);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  tmp.release();
+  fi.release();
+  rowCount.release();
+  h->reducedBuilt = true;
+  return IKB_OK;
+}
+
+int64_t rowsOf(Handle* h, int dbc) { return dbc == IKB_DBC_REDUCED ? h->nRed : h->nRowsLocal(); }
+int64_t nnzOf(Handle* h, int dbc) { return dbc == IKB_DBC_REDUCED ? h->nnzRed : h->nnzRaw(); }
+
+int launchGather(Handle* h, unsigned what, int dbc) {
+  GatherArgs G;
+  G.P = h->view();
+  G.cptr = h->cptr.p;
+  G.csrc = h->csrc.p;
+  G.Kst = h->Kst.p;
+  G.Rst = h->Rst.p;
+  G.fext = h->hasFext ? h->Fext.p : nullptr;
+  G.fextScale = h->fextScales ? h->lambda : 1.0;
+  G.flags = h->hasFlags ? h->flags.p : nullptr;
+  G.vals = (what & IKB_MATRIX) ? h->vals[dbc].p : nullptr;
+  G.vec = (what & IKB_VECTOR) ? h->vec[dbc].p : nullptr;
+  G.dbc = dbc;
+  G.npair = h->npair;
+  G.nn = h->nn;
+  G.freeCnt = h->freeCnt.p;
+  G.freeTot = h->freeTot.p;
+  G.redRowStart = h->redRowStart.p;
+  G.cbelow = h->cbelow.p;
+  G.redVecOffset = 0;
+  const int tpb = 256;
+  if (h->nBlocks == 0) return IKB_OK;
+  if (h->dim == 3)
+    gather_kernel<3><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(G);
+  else
+    gather_kernel<2><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(G);
+  IKB_LAUNCH_CHECK(h);
+  return IKB_OK;
+}
+
+int checkMaterialError(Handle* h) {
+  int32_t flag = INT_MAX;
+  IKB_CUDA(h, cudaMemcpyAsync(&flag, h->errFlag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (flag != INT_MAX) {
+    const int32_t reset = INT_MAX;
+    cudaMemcpyAsync(h->errFlag.p, &reset, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    // the reference aborts here (materials/materialhelpers.hh:120-126)
+    return fail(h, IKB_EMATERIAL,
+                "Determinant of right Cauchy Green tensor C must be greater than zero (first failing element " +
+                    std::to_string(flag) + ")");
+  }
+  return IKB_OK;
+}
+
+int deviceDot(Handle* h, int mode, const double* x, const double* y, int64_t n, double* outDev, double scale,
+              const double* addend) {
+  double* partial = h->scratch.p;
+  if (mode == 0)
+    reduce_stage1<0><<<RED_BLOCKS, 256, 0, h->stream>>>(x, y, n, partial);
+  else if (mode == 1)
+    reduce_stage1<1><<<RED_BLOCKS, 256, 0, h->stream>>>(x, y, n, partial);
+  else
+    reduce_stage1<2><<<RED_BLOCKS, 256, 0, h->stream>>>(x, y, n, partial);
+  IKB_LAUNCH_CHECK(h);
+  reduce_stage2<<<1, 256, 0, h->stream>>>(partial, RED_BLOCKS, outDev, scale, addend);
+  IKB_LAUNCH_CHECK(h);
+  return IKB_OK;
+}
+
+int launchSpmv(Handle* h, int dbc, const double* x, double* y) {
+  const int tpb = 256;
+  if (dbc == IKB_DBC_REDUCED) {
+    if (h->nRed == 0) return IKB_OK;
+    spmv_csr_kernel<8><<<gridFor(h->nRed * 8, tpb), tpb, 0, h->stream>>>(h->redOuter.p, h->redInner.p,
+                                                                         h->vals[dbc].p, h->nRed, x, y);
+  } else {
+    const PatternView P = h->view();
+    const int64_t rows = P.nRowNodes * h->dim;
+    if (rows == 0) return IKB_OK;
+    if (h->dim == 3)
+      spmv_block_kernel<3, 8><<<gridFor(rows * 8, tpb), tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y);
+    else
+      spmv_block_kernel<2, 4><<<gridFor(rows * 4, tpb), tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y);
+  }
+  IKB_LAUNCH_CHECK(h);
+  return IKB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ikb_create(ikb_handle* out, const ikb_desc* desc) {
+  if (!out || !desc) return IKB_EINVAL;
+  *out = nullptr;
+  if (desc->abi_version != IKB_ABI_VERSION) return IKB_EINVAL;
+  if (desc->dim != 2 && desc->dim != 3) return IKB_EINVAL;
+  if (desc->order != 1 && desc->order != 2) return IKB_EINVAL;
+  if (desc->n_elem < 0 || desc->n_dof <= 0 || desc->n_dof % desc->dim != 0) return IKB_EINVAL;
+  if (desc->n_dof >= (int64_t)INT32_MAX) return IKB_EINVAL;
+  int form;
+  if (desc->strain == IKB_STRAIN_LINEAR && desc->material == IKB_MAT_LINEAR_ELASTICITY)
+    form = FORM_LE;
+  else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_SVK)
+    form = FORM_SVK;
+  else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_NEOHOOKE)
+    form = FORM_NH;
+  else
+    return IKB_EINVAL;  // the reference statically rejects these strain/material pairings too
+  if (desc->dim == 2 && !desc->plane_strain) return IKB_EINVAL;  // 2D needs a reduced material
+  if (desc->dim == 3 && desc->plane_strain) return IKB_EINVAL;
+  const int m = desc->eas_m;
+  const bool easOk = m == 0 || (desc->order == 1 && ((desc->dim == 2 && (m == 4 || m == 5 || m == 7)) ||
+                                                     (desc->dim == 3 && (m == 9 || m == 21))));
+  if (!easOk) return IKB_ENOTIMPL;  // Dune::NotImplemented in the reference (enhancedassumedstrains.hh:250-256)
+
+  int dev = desc->device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return IKB_ECUDA;
+  if (cudaSetDevice(dev) != cudaSuccess) return IKB_ECUDA;
+  Handle* h = new Handle();
+  h->desc = *desc;
+  h->device = dev;
+  h->dim = desc->dim;
+  h->order = desc->order;
+  h->nn = 1;
+  for (int k = 0; k < h->dim; ++k) h->nn *= (h->order + 1);
+  h->nd = h->nn * h->dim;
+  h->nc = 1 << h->dim;
+  h->npair = h->nn * (h->nn + 1) / 2;
+  h->form = form;
+  h->easM = m;
+  h->nElem = desc->n_elem;
+  h->nDof = desc->n_dof;
+  h->nNodes = desc->n_dof / desc->dim;
+  h->rowBegin = 0;
+  h->rowEnd = h->nNodes;
+  if ((double)h->nElem * h->npair >= 2147483647.0) {
+    delete h;
+    return IKB_EINVAL;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      h->errFlag.alloc(1) != cudaSuccess || h->scratch.alloc(4 * RED_BLOCKS + 16) != cudaSuccess ||
+      h->cgScal.alloc(16) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&h->hostScal), 16 * sizeof(double)) != cudaSuccess) {
+    delete h;
+    return IKB_ECUDA;
+  }
+  const int32_t reset = INT_MAX;
+  cudaMemcpy(h->errFlag.p, &reset, sizeof(int32_t), cudaMemcpyHostToDevice);
+  cudaMemset(h->cgScal.p, 0, h->cgScal.bytes());
+  *out = reinterpret_cast<ikb_handle>(h);
+  return IKB_OK;
+}
+
+int ikb_destroy(ikb_handle hh) {
+  Handle* h = H(hh);
+  if (!h) return IKB_EINVAL;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto* b : {&h->X, &h->U, &h->Fext, &h->Corr, &h->Kst, &h->Rst, &h->Est, &h->scratch, &h->alpha, &h->cgR, &h->cgZ,
+                  &h->cgP, &h->cgQ, &h->cgX, &h->cgDinv, &h->cgB, &h->cgScal})
+    b->release();
+  for (int i = 0; i < 3; ++i) {
+    h->vals[i].release();
+    h->vec[i].release();
+  }
+  h->elemNode.release();
+  h->flags.release();
+  h->nbrPtr.release();
+  h->nbrIdx.release();
+  h->nbrRow.release();
+  h->cptr.release();
+  h->csrc.release();
+  h->cbelow.release();
+  h->freeCnt.release();
+  h->freeTot.release();
+  h->redRowStart.release();
+  h->redInner.release();
+  h->redOuter.release();
+  h->errFlag.release();
+  if (h->hostScal) cudaFreeHost(h->hostScal);
+  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->stream2);
+  delete h;
+  return IKB_OK;
+}
+
+int ikb_last_error(ikb_handle hh, char* buf, size_t len) {
+  Handle* h = H(hh);
+  if (!h || !buf || len == 0) return IKB_EINVAL;
+  std::strncpy(buf, h->lastError.c_str(), len - 1);
+  buf[len - 1] = 0;
+  return IKB_OK;
+}
+
+int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!corner || !elemDofs) return fail(h, IKB_EINVAL, "null mesh arrays");
+  const int D = h->dim, nn = h->nn, nc = h->nc, nd = h->nd;
+  const int64_t ne = h->nElem, nNodes = h->nNodes;
+  if (ne == 0) {
+    h->meshUploaded = true;
+    return IKB_OK;
+  }
+  // detect the flat power-basis layout from the first node, then verify every node
+  int layout = -1;
+  {
+    const int64_t* d0 = elemDofs;
+    bool inter = d0[0] % D == 0, lex = d0[0] < nNodes;
+    for (int c = 1; c < D; ++c) {
+      inter = inter && d0[c] == d0[0] + c;
+      lex = lex && d0[c] == d0[0] + (int64_t)c * nNodes;
+    }
+    if (inter)
+      layout = LAYOUT_INTERLEAVED;
+    else if (lex)
+      layout = LAYOUT_LEXICOGRAPHIC;
+  }
+  if (layout < 0)
+    return fail(h, IKB_ENOTIMPL, "element dofs are neither FlatInterleaved nor FlatLexicographic per Lagrange node");
+  std::vector<int32_t> en((size_t)nn * ne);
+  bool ok = true;
+  for (int64_t e = 0; e < ne && ok; ++e)
+    for (int a = 0; a < nn; ++a) {
+      const int64_t* d = elemDofs + (size_t)e * nd + (size_t)a * D;
+      int64_t node;
+      if (layout == LAYOUT_INTERLEAVED) {
+        node = d[0] / D;
+        for (int c = 0; c < D; ++c) ok = ok && d[c] == node * D + c;
+      } else {
+        node = d[0];
+        for (int c = 0; c < D; ++c) ok = ok && d[c] == node + (int64_t)c * nNodes;
+      }
+      ok = ok && node >= 0 && node < nNodes;
+      en[(size_t)a * ne + e] = (int32_t)node;
+    }
+  if (!ok) return fail(h, IKB_EINVAL, "inconsistent element dof indices");
+  std::vector<double> xs((size_t)nc * D * ne);
+  for (int64_t e = 0; e < ne; ++e)
+    for (int q = 0; q < nc * D; ++q) xs[(size_t)q * ne + e] = corner[(size_t)e * nc * D + q];
+  h->layout = layout;
+  IKB_CUDA(h, h->elemNode.alloc(en.size()));
+  IKB_CUDA(h, h->X.alloc(xs.size()));
+  IKB_CUDA(h, cudaMemcpyAsync(h->elemNode.p, en.data(), h->elemNode.bytes(), cudaMemcpyHostToDevice, h->stream));
+  IKB_CUDA(h, cudaMemcpyAsync(h->X.p, xs.data(), h->X.bytes(), cudaMemcpyHostToDevice, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->meshUploaded = true;
+  h->patternBuilt = false;
+  h->reducedBuilt = false;
+  h->stateVersion++;
+  if (h->easM) {
+    IKB_CUDA(h, h->alpha.alloc((size_t)ne * h->easM));
+    IKB_CUDA(h, cudaMemsetAsync(h->alpha.p, 0, h->alpha.bytes(), h->stream));  // initializeState (:373-376)
+  }
+  return IKB_OK;
+}
+
+int ikb_upload_dirichlet(ikb_handle hh, const uint8_t* flags) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!flags) return fail(h, IKB_EINVAL, "null flags");
+  IKB_CUDA(h, h->flags.alloc((size_t)h->nDof));
+  IKB_CUDA(h, cudaMemcpyAsync(h->flags.p, flags, h->flags.bytes(), cudaMemcpyHostToDevice, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->hasFlags = true;
+  h->reducedBuilt = false;
+  h->vals[IKB_DBC_REDUCED].release();
+  h->vec[IKB_DBC_REDUCED].release();
+  h->stateVersion++;
+  return IKB_OK;
+}
+
+int ikb_set_row_ownership(ikb_handle hh, int64_t nodeBegin, int64_t nodeEnd) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (nodeBegin < 0 || nodeEnd > h->nNodes || nodeBegin > nodeEnd) return fail(h, IKB_EINVAL, "bad node range");
+  if (h->layout == LAYOUT_LEXICOGRAPHIC && h->meshUploaded && !(nodeBegin == 0 && nodeEnd == h->nNodes))
+    return fail(h, IKB_ENOTIMPL, "row partitioning needs FlatInterleaved dofs");
+  h->rowBegin = nodeBegin;
+  h->rowEnd = nodeEnd;
+  h->patternBuilt = false;
+  h->reducedBuilt = false;
+  return IKB_OK;
+}
+
+int ikb_build_pattern(ikb_handle hh) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!h->meshUploaded) return fail(h, IKB_ESTATE, "upload the mesh first");
+  const int nn = h->nn;
+  const int64_t total = h->nElem * nn * nn;
+  const int tpb = 256;
+  const int64_t nRowNodes = h->rowEnd - h->rowBegin;
+  h->nBlocks = 0;
+  IKB_CUDA(h, h->nbrPtr.alloc((size_t)nRowNodes + 1));
+  if (total == 0) {
+    IKB_CUDA(h, cudaMemsetAsync(h->nbrPtr.p, 0, h->nbrPtr.bytes(), h->stream));
+    h->patternBuilt = true;
+    return IKB_OK;
+  }
+  DevBuf<uint64_t> keys, keysOut, ukeys;
+  DevBuf<uint32_t> vals;
+  DevBuf<int32_t> counts;
+  DevBuf<int64_t> nRuns;
+  DevBuf<uint8_t> tmp;
+  IKB_CUDA(h, keys.alloc((size_t)total));
+  IKB_CUDA(h, keysOut.alloc((size_t)total));
+  IKB_CUDA(h, vals.alloc((size_t)total));
+  IKB_CUDA(h, h->csrc.alloc((size_t)total));
+  gen_pairs_kernel<<<gridFor(total, tpb), tpb, 0, h->stream>>>(h->elemNode.p, h->nElem, nn, h->npair, h->nNodes,
+                                                              h->rowBegin, h->rowEnd, keys.p, vals.p);
+  IKB_LAUNCH_CHECK(h);
+  // key < nRowNodes*nNodes (or the all-ones sentinel of non-owned rows)
+  int endBit = 64;
+  if (h->rowBegin == 0 && h->rowEnd == h->nNodes) {
+    const double maxKey = (double)nRowNodes * (double)h->nNodes;
+    endBit = std::min(64, (int)std::ceil(std::log2(maxKey + 1.0)) + 1);
+  }
+  size_t tmpBytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysOut.p, vals.p, h->csrc.p, total, 0, endBit, h->stream);
+  IKB_CUDA(h, tmp.alloc(tmpBytes));
+  IKB_CUDA(h, cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysOut.p, vals.p, h->csrc.p, total, 0, endBit,
+                                              h->stream));
+  h->launches++;
+  vals.release();
+  // run-length encode the sorted keys: unique keys = pattern blocks, counts = contributions per block
+  IKB_CUDA(h, nRuns.alloc(1));
+  IKB_CUDA(h, counts.alloc((size_t)total + 1));
+  ukeys.p = keys.p;  // reuse the unsorted-key buffer for the unique keys
+  tmpBytes = 0;
+  cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, keysOut.p, ukeys.p, counts.p, nRuns.p, total, h->stream);
+  IKB_CUDA(h, tmp.alloc(tmpBytes));
+  IKB_CUDA(h, cub::DeviceRunLengthEncode::Encode(tmp.p, tmpBytes, keysOut.p, ukeys.p, counts.p, nRuns.p, total,
+                                                 h->stream));
+  h->launches++;
+  int64_t runs = 0;
+  IKB_CUDA(h, cudaMemcpyAsync(&runs, nRuns.p, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  // drop the sentinel run of non-owned rows (it sorts last)
+  uint64_t lastKey = 0;
+  IKB_CUDA(h, cudaMemcpy(&lastKey, ukeys.p + (runs - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (lastKey == ~0ull) runs -= 1;
+  if (runs >= (int64_t)INT32_MAX) {
+    ukeys.p = nullptr;
+    return fail(h, IKB_EINVAL, "too many pattern blocks for 32-bit block indices");
+  }
+  h->nBlocks = runs;
+  IKB_CUDA(h, h->cptr.alloc((size_t)runs + 1));
+  IKB_CUDA(h, h->nbrIdx.alloc((size_t)std::max<int64_t>(runs, 1)));
+  IKB_CUDA(h, h->nbrRow.alloc((size_t)std::max<int64_t>(runs, 1)));
+  tmpBytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts.p, h->cptr.p, runs + 1, h->stream);
+  IKB_CUDA(h, tmp.alloc(tmpBytes));
+  IKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, counts.p, h->cptr.p, runs + 1, h->stream));
+  h->launches++;
+  if (runs > 0) {
+    decode_blocks_kernel<<<gridFor(runs, tpb), tpb, 0, h->stream>>>(ukeys.p, runs, h->nNodes, h->nbrIdx.p, h->nbrRow.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  row_ptr_kernel<<<gridFor(nRowNodes + 1, tpb), tpb, 0, h->stream>>>(h->nbrRow.p, runs, nRowNodes, h->nbrPtr.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  ukeys.p = nullptr;  // aliased keys.p
+  keys.release();
+  keysOut.release();
+  counts.release();
+  nRuns.release();
+  tmp.release();
+  h->patternBuilt = true;
+  h->reducedBuilt = false;
+  for (int i = 0; i < 3; ++i) {
+    h->vals[i].release();
+    h->vec[i].release();
+    h->valsVersion[i] = h->vecVersion[i] = 0;
+  }
+  return IKB_OK;
+}
+
+int ikb_pattern_nnz(ikb_handle hh, int dbc, int64_t* rows, int64_t* nnz) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc)) return fail(h, IKB_EINVAL, "bad dbc");
+  if (!h->patternBuilt) return fail(h, IKB_ESTATE, "pattern not built");
+  if (dbc == IKB_DBC_REDUCED) {
+    int rc = ensureReduced(h);
+    if (rc) return rc;
+  }
+  if (rows) *rows = rowsOf(h, dbc);
+  if (nnz) *nnz = nnzOf(h, dbc);
+  return IKB_OK;
+}
+
+int ikb_get_pattern(ikb_handle hh, int dbc, int64_t* outer, int32_t* inner) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !outer || !inner) return fail(h, IKB_EINVAL, "bad arguments");
+  if (!h->patternBuilt) return fail(h, IKB_ESTATE, "pattern not built");
+  if (dbc == IKB_DBC_REDUCED) {
+    int rc = ensureReduced(h);
+    if (rc) return rc;
+    IKB_CUDA(h, cudaMemcpy(outer, h->redOuter.p, (size_t)(h->nRed + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (h->nnzRed)
+      IKB_CUDA(h, cudaMemcpy(inner, h->redInner.p, (size_t)h->nnzRed * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return IKB_OK;
+  }
+  const PatternView P = h->view();
+  const int64_t rows = h->nRowsLocal(), nnz = h->nnzRaw();
+  DevBuf<int64_t> o;
+  DevBuf<int32_t> in;
+  IKB_CUDA(h, o.alloc((size_t)rows + 1));
+  IKB_CUDA(h, in.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  IKB_CUDA(h, cudaMemsetAsync(o.p, 0, o.bytes(), h->stream));
+  if (h->nBlocks) {
+    raw_pattern_kernel<<<gridFor(h->nBlocks, 256), 256, 0, h->stream>>>(P, o.p, in.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  IKB_CUDA(h, cudaMemcpyAsync(outer, o.p, o.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  if (nnz) IKB_CUDA(h, cudaMemcpyAsync(inner, in.p, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  o.release();
+  in.release();
+  return IKB_OK;
+}
+
+int ikb_get_constraints_below(ikb_handle hh, int64_t* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!out) return fail(h, IKB_EINVAL, "null out");
+  int rc = ensureReduced(h);
+  if (rc) return rc;
+  std::vector<int32_t> tmp((size_t)h->nDof);
+  IKB_CUDA(h, cudaMemcpy(tmp.data(), h->cbelow.p, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
+  return IKB_OK;
+}
+
+int ikb_element_linear_indices(ikb_handle hh, int64_t elem, int64_t* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!h->patternBuilt || !out || elem < 0 || elem >= h->nElem) return fail(h, IKB_EINVAL, "bad arguments");
+  // host-side lookup in the node-block view (diagnostic path, not hot)
+  const int D = h->dim, nn = h->nn;
+  const int64_t nRowNodes = h->rowEnd - h->rowBegin;
+  std::vector<int32_t> nodes(nn);
+  for (int a = 0; a < nn; ++a)
+    IKB_CUDA(h, cudaMemcpy(&nodes[a], h->elemNode.p + (size_t)a * h->nElem + elem, sizeof(int32_t),
+                           cudaMemcpyDeviceToHost));
+  std::vector<int32_t> ptr((size_t)nRowNodes + 1);
+  IKB_CUDA(h, cudaMemcpy(ptr.data(), h->nbrPtr.p, ptr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  PatternView P = h->view();
+  P.nbrPtr = ptr.data();
+  int64_t q = 0;
+  for (int cb = 0; cb < nn; ++cb)
+    for (int ck = 0; ck < D; ++ck)
+      for (int ra = 0; ra < nn; ++ra)
+        for (int ri = 0; ri < D; ++ri, ++q) {
+          const int64_t g = nodes[ra] - h->rowBegin;
+          if (g < 0 || g >= nRowNodes) {
+            out[q] = -1;
+            continue;
+          }
+          const int nnb = ptr[g + 1] - ptr[g];
+          std::vector<int32_t> nb(nnb);
+          IKB_CUDA(h, cudaMemcpy(nb.data(), h->nbrIdx.p + ptr[g], nnb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+          const int slot = (int)(std::lower_bound(nb.begin(), nb.end(), nodes[cb]) - nb.begin());
+          out[q] = rawRowStart(P, g, ri, nnb) + rawEntryOffset(P, slot, ck, nnb);
+        }
+  return IKB_OK;
+}
+
+int ikb_set_solution(ikb_handle hh, const double* d) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!d) return fail(h, IKB_EINVAL, "null solution");
+  if (!h->U.p) IKB_CUDA(h, h->U.alloc((size_t)h->nDof));
+  IKB_CUDA(h, cudaMemcpyAsync(h->U.p, d, h->U.bytes(), cudaMemcpyHostToDevice, h->stream));
+  h->stateVersion++;
+  return IKB_OK;
+}
+
+int ikb_get_solution(ikb_handle hh, double* d) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  int rc = ensureSolution(h);
+  if (rc) return rc;
+  IKB_CUDA(h, cudaMemcpyAsync(d, h->U.p, h->U.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
+int ikb_set_parameter(ikb_handle hh, double lambda) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (lambda != h->lambda) h->stateVersion++;
+  h->lambda = lambda;
+  return IKB_OK;
+}
+
+int ikb_set_external_load(ikb_handle hh, const double* fext, int scales) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!fext) {
+    h->hasFext = false;
+    h->stateVersion++;
+    return IKB_OK;
+  }
+  if (!h->Fext.p) IKB_CUDA(h, h->Fext.alloc((size_t)h->nDof));
+  IKB_CUDA(h, cudaMemcpyAsync(h->Fext.p, fext, h->Fext.bytes(), cudaMemcpyHostToDevice, h->stream));
+  h->hasFext = true;
+  h->fextScales = scales ? 1 : 0;
+  h->stateVersion++;
+  return IKB_OK;
+}
+
+int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || (what & ~7u) || what == 0) return fail(h, IKB_EINVAL, "bad affordance/dbc");
+  if (!h->meshUploaded || !h->patternBuilt) return fail(h, IKB_ESTATE, "mesh/pattern missing");
+  if (dbc != IKB_DBC_RAW && !h->hasFlags) return fail(h, IKB_ESTATE, "Dirichlet flags missing");
+  if ((what & IKB_SCALAR) && h->easM)
+    return fail(h, IKB_ENOTIMPL,
+                "EAS element do not support any scalar calculations, i.e. they are not derivable from a potential");
+  int rc;
+  if ((rc = ensureSolution(h))) return rc;
+  if ((rc = ensureStaging(h))) return rc;
+  if (dbc == IKB_DBC_REDUCED && (rc = ensureReduced(h))) return rc;
+
+  // which outputs are stale for the current (d, lambda, alpha)?
+  unsigned needGather = 0;
+  if ((what & IKB_MATRIX) && h->valsVersion[dbc] != h->stateVersion) needGather |= IKB_MATRIX;
+  if ((what & IKB_VECTOR) && h->vecVersion[dbc] != h->stateVersion) needGather |= IKB_VECTOR;
+  const bool needEnergy = (what & IKB_SCALAR) && h->energyVersion != h->stateVersion;
+  unsigned needStage = needGather | (needEnergy ? IKB_SCALAR : 0);
+  if (h->stagedVersion == h->stateVersion) needStage &= ~h->stagedWhat;
+  if (needStage) {
+    const unsigned stageWhat = needStage;
+    if ((rc = launchElements(h, stageWhat))) return rc;
+    h->stagedWhat = (h->stagedVersion == h->stateVersion ? h->stagedWhat : 0) | stageWhat;
+    h->stagedVersion = h->stateVersion;
+  }
+  if (needGather) {
+    if ((needGather & IKB_MATRIX) && !h->vals[dbc].p)
+      IKB_CUDA(h, h->vals[dbc].alloc((size_t)std::max<int64_t>(nnzOf(h, dbc), 1)));
+    if ((needGather & IKB_VECTOR) && !h->vec[dbc].p)
+      IKB_CUDA(h, h->vec[dbc].alloc((size_t)std::max<int64_t>(rowsOf(h, dbc), 1)));
+    if ((rc = launchGather(h, needGather, dbc))) return rc;
+    if (needGather & IKB_MATRIX) h->valsVersion[dbc] = h->stateVersion;
+    if (needGather & IKB_VECTOR) h->vecVersion[dbc] = h->stateVersion;
+  }
+  if (needEnergy) {
+    double* eDev = h->cgScal.p + 8;
+    double* lDev = h->cgScal.p + 9;
+    if (h->hasFext) {
+      // E -= s * fext . d   (loads/volume.hh:67-84, traction.hh:70-105)
+      if ((rc = deviceDot(h, 1, h->Fext.p, h->U.p, h->nDof, lDev, -(h->fextScales ? h->lambda : 1.0), nullptr)))
+        return rc;
+    }
+    if ((rc = deviceDot(h, 0, h->Est.p, nullptr, h->nElem, eDev, 1.0, h->hasFext ? lDev : nullptr))) return rc;
+    h->energyVersion = h->stateVersion;
+  }
+  return IKB_OK;
+}
+
+int ikb_get_vector(ikb_handle hh, int dbc, double* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !out) return fail(h, IKB_EINVAL, "bad arguments");
+  if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "vector not assembled for the current state");
+  const int64_t n = rowsOf(h, dbc);
+  if (n) IKB_CUDA(h, cudaMemcpyAsync(out, h->vec[dbc].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return checkMaterialError(h);
+}
+
+int ikb_get_scalar(ikb_handle hh, double* e) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!e) return fail(h, IKB_EINVAL, "null out");
+  if (h->energyVersion != h->stateVersion) return fail(h, IKB_ESTATE, "scalar not assembled for the current state");
+  IKB_CUDA(h, cudaMemcpyAsync(e, h->cgScal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return checkMaterialError(h);
+}
+
+int ikb_get_matrix_values(ikb_handle hh, int dbc, double* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !out) return fail(h, IKB_EINVAL, "bad arguments");
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
+  const int64_t nnz = nnzOf(h, dbc);
+  if (nnz)
+    IKB_CUDA(h, cudaMemcpyAsync(out, h->vals[dbc].p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return checkMaterialError(h);
+}
+
+int ikb_get_dense_matrix(ikb_handle hh, int dbc, double* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !out) return fail(h, IKB_EINVAL, "bad arguments");
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
+  const int64_t rows = rowsOf(h, dbc);
+  if (rows == 0) return IKB_OK;
+  if ((double)rows * rows * 8.0 > 8e9) return fail(h, IKB_EINVAL, "dense matrix too large");
+  DevBuf<double> dense;
+  IKB_CUDA(h, dense.alloc((size_t)rows * rows));
+  IKB_CUDA(h, cudaMemsetAsync(dense.p, 0, dense.bytes(), h->stream));
+  DevBuf<int64_t> o;
+  DevBuf<int32_t> in;
+  const int64_t* outer;
+  const int32_t* inner;
+  if (dbc == IKB_DBC_REDUCED) {
+    outer = h->redOuter.p;
+    inner = h->redInner.p;
+  } else {
+    IKB_CUDA(h, o.alloc((size_t)rows + 1));
+    IKB_CUDA(h, in.alloc((size_t)h->nnzRaw()));
+    raw_pattern_kernel<<<gridFor(h->nBlocks, 256), 256, 0, h->stream>>>(h->view(), o.p, in.p);
+    IKB_LAUNCH_CHECK(h);
+    outer = o.p;
+    inner = in.p;
+  }
+  csr_to_dense_kernel<<<gridFor(rows, 128), 128, 0, h->stream>>>(outer, inner, h->vals[dbc].p, rows, dense.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, cudaMemcpyAsync(out, dense.p, dense.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  dense.release();
+  o.release();
+  in.release();
+  return IKB_OK;
+}
+
+int ikb_vector_norm(ikb_handle hh, int dbc, double* norm) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !norm) return fail(h, IKB_EINVAL, "bad arguments");
+  if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "vector not assembled for the current state");
+  const int64_t n = rowsOf(h, dbc);
+  int rc = deviceDot(h, 2, h->vec[dbc].p, nullptr, n, h->cgScal.p + 10, 1.0, nullptr);
+  if (rc) return rc;
+  double s = 0.0;
+  IKB_CUDA(h, cudaMemcpyAsync(&s, h->cgScal.p + 10, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  rc = checkMaterialError(h);
+  *norm = std::sqrt(s);
+  return rc;
+}
+
+int ikb_eas_update(ikb_handle hh, const double*) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!h->easM) return IKB_OK;
+  return fail(h, IKB_ENOTIMPL, "EAS update not implemented yet");
+}
+int ikb_eas_get_alpha(ikb_handle hh, double* alpha) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!h->easM || !alpha) return fail(h, IKB_EINVAL, "no EAS state");
+  IKB_CUDA(h, cudaMemcpyAsync(alpha, h->alpha.p, h->alpha.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+int ikb_eas_set_alpha(ikb_handle hh, const double* alpha) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!h->easM || !alpha) return fail(h, IKB_EINVAL, "no EAS state");
+  IKB_CUDA(h, cudaMemcpyAsync(h->alpha.p, alpha, h->alpha.bytes(), cudaMemcpyHostToDevice, h->stream));
+  h->stateVersion++;
+  return IKB_OK;
+}
+
+int ikb_spmv(ikb_handle hh, int dbc, const double* x, double* y) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !x || !y) return fail(h, IKB_EINVAL, "bad arguments");
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
+  const int64_t n = rowsOf(h, dbc);
+  if (n == 0) return IKB_OK;
+  const int64_t nx = dbc == IKB_DBC_REDUCED ? h->nRed : h->nDof;
+  if (h->cgP.n < (size_t)nx) IKB_CUDA(h, h->cgP.alloc((size_t)nx));
+  if (h->cgQ.n < (size_t)n) IKB_CUDA(h, h->cgQ.alloc((size_t)n));
+  IKB_CUDA(h, cudaMemcpyAsync(h->cgP.p, x, (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p);
+  if (rc) return rc;
+  IKB_CUDA(h, cudaMemcpyAsync(y, h->cgQ.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
+int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double relTol, int maxIt, int* itersOut,
+                  double* relResOut) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (dbc != IKB_DBC_FULL && dbc != IKB_DBC_REDUCED) return fail(h, IKB_EINVAL, "PCG needs the Full or Reduced matrix");
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
+  if (h->rowBegin != 0 || h->rowEnd != h->nNodes) return fail(h, IKB_ENOTIMPL, "partitioned PCG: use the distributed driver");
+  const int64_t n = rowsOf(h, dbc);
+  if (itersOut) *itersOut = 0;
+  if (relResOut) *relResOut = 0.0;
+  if (n == 0) return IKB_OK;
+  for (auto* b : {&h->cgR, &h->cgZ, &h->cgP, &h->cgQ, &h->cgX, &h->cgDinv})
+    if (b->n < (size_t)n) IKB_CUDA(h, b->alloc((size_t)n));
+  if (h->Corr.n < (size_t)h->nDof) IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
+  const int tpb = 256;
+  int rc;
+  // r = b (x0 = 0)
+  if (rhs) {
+    IKB_CUDA(h, cudaMemcpyAsync(h->cgR.p, rhs, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "resident residual not assembled");
+    vec_scale_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, -1.0, h->vec[dbc].p, h->cgR.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  IKB_CUDA(h, cudaMemsetAsync(h->cgX.p, 0, (size_t)n * sizeof(double), h->stream));
+  if (dbc == IKB_DBC_REDUCED) {
+    diag_inv_csr_kernel<<<gridFor(n, tpb), tpb, 0, h->stream>>>(h->redOuter.p, h->redInner.p, h->vals[dbc].p, n,
+                                                                h->cgDinv.p);
+  } else if (h->dim == 3) {
+    diag_inv_block_kernel<3><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+  } else {
+    diag_inv_block_kernel<2><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+  }
+  IKB_LAUNCH_CHECK(h);
+  double* scal = h->cgScal.p;
+  // z = Dinv r ; p = z ; rz = r.z ; bb = r.r
+  vec_mul_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, h->cgDinv.p, h->cgR.p, h->cgZ.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, cudaMemcpyAsync(h->cgP.p, h->cgZ.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = deviceDot(h, 1, h->cgR.p, h->cgZ.p, n, scal + 0, 1.0, nullptr))) return rc;
+  if ((rc = deviceDot(h, 2, h->cgR.p, nullptr, n, scal + 4, 1.0, nullptr))) return rc;
+  double bb = 0.0;
+  IKB_CUDA(h, cudaMemcpyAsync(&bb, scal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int it = 0;
+  double rr = bb;
+  // Eigen's criterion: stop when |r|^2 < tol^2 |b|^2 (ConjugateGradient.h), x = 0 for b = 0
+  const double threshold = std::max(relTol * relTol * bb, 1e-300);
+  if (bb > 0.0) {
+    while (it < maxIt && rr >= threshold) {
+      if ((rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p))) return rc;
+      if ((rc = deviceDot(h, 1, h->cgP.p, h->cgQ.p, n, scal + 1, 1.0, nullptr))) return rc;
+      cg_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgP.p, h->cgQ.p, h->cgDinv.p, h->cgX.p, h->cgR.p,
+                                                          h->cgZ.p, h->scratch.p + 2 * RED_BLOCKS);
+      IKB_LAUNCH_CHECK(h);
+      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(h->scratch.p + 2 * RED_BLOCKS, RED_BLOCKS, scal, nullptr);
+      IKB_LAUNCH_CHECK(h);
+      IKB_CUDA(h, cudaMemcpyAsync(h->hostScal, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      cg_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgZ.p, h->cgP.p);
+      IKB_LAUNCH_CHECK(h);
+      cg_shift_kernel<<<1, 1, 0, h->stream>>>(scal);
+      IKB_LAUNCH_CHECK(h);
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      rr = h->hostScal[0];
+      ++it;
+      if (!(rr == rr)) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
+    }
+  }
+  if (itersOut) *itersOut = it;
+  if (relResOut) *relResOut = bb > 0.0 ? std::sqrt(rr / bb) : 0.0;
+  // keep the correction resident at full size for ikb_update_solution / ikb_eas_update
+  if (dbc == IKB_DBC_REDUCED) {
+    expand_reduced_kernel<<<gridFor(h->nDof, tpb), tpb, 0, h->stream>>>(h->nDof, h->flags.p, h->cbelow.p, h->cgX.p,
+                                                                        h->Corr.p);
+    IKB_LAUNCH_CHECK(h);
+  } else {
+    IKB_CUDA(h, cudaMemcpyAsync(h->Corr.p, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (x) IKB_CUDA(h, cudaMemcpyAsync(x, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
+int ikb_update_solution(ikb_handle hh, int dbc, const double* correction) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc)) return fail(h, IKB_EINVAL, "bad dbc");
+  int rc = ensureSolution(h);
+  if (rc) return rc;
+  const int tpb = 256;
+  if (h->Corr.n < (size_t)h->nDof) {
+    if (!correction) return fail(h, IKB_ESTATE, "no resident correction");
+    IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
+  }
+  if (correction) {
+    if (dbc == IKB_DBC_REDUCED) {
+      if ((rc = ensureReduced(h))) return rc;
+      if (h->cgX.n < (size_t)h->nRed) IKB_CUDA(h, h->cgX.alloc((size_t)std::max<int64_t>(h->nRed, 1)));
+      IKB_CUDA(h, cudaMemcpyAsync(h->cgX.p, correction, (size_t)h->nRed * sizeof(double), cudaMemcpyHostToDevice,
+                                  h->stream));
+      expand_reduced_kernel<<<gridFor(h->nDof, tpb), tpb, 0, h->stream>>>(h->nDof, h->flags.p, h->cbelow.p, h->cgX.p,
+                                                                          h->Corr.p);
+      IKB_LAUNCH_CHECK(h);
+    } else {
+      IKB_CUDA(h, cudaMemcpyAsync(h->Corr.p, correction, (size_t)h->nDof * sizeof(double), cudaMemcpyHostToDevice,
+                                  h->stream));
+    }
+  }
+  vec_axpy_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(h->nDof, 1.0, h->Corr.p, h->U.p);
+  IKB_LAUNCH_CHECK(h);
+  h->stateVersion++;
+  return IKB_OK;
+}
+
+int ikb_nccl_unique_id(void*) { return IKB_ENOTIMPL; }
+int ikb_comm_init(ikb_handle hh, const void*, int, int) { return fail(H(hh), IKB_ENOTIMPL, "NCCL layer not built yet"); }
+
+int ikb_stream(ikb_handle hh, void** s) {
+  Handle* h = H(hh);
+  if (!h || !s) return IKB_EINVAL;
+  *s = reinterpret_cast<void*>(h->stream);
+  return IKB_OK;
+}
+int ikb_sync(ikb_handle hh) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  return checkMaterialError(h);
+}
+int ikb_launch_count(ikb_handle hh, int64_t* n) {
+  Handle* h = H(hh);
+  if (!h || !n) return IKB_EINVAL;
+  *n = h->launches;
+  return IKB_OK;
+}
+int ikb_device_ptr(ikb_handle hh, const char* what, int dbc, void** ptr) {
+  Handle* h = H(hh);
+  if (!h || !what || !ptr || !dbcValid(dbc)) return IKB_EINVAL;
+  const std::string w(what);
+  if (w == "solution")
+    *ptr = h->U.p;
+  else if (w == "residual")
+    *ptr = h->vec[dbc].p;
+  else if (w == "values")
+    *ptr = h->vals[dbc].p;
+  else if (w == "correction")
+    *ptr = h->Corr.p;
+  else
+    return fail(h, IKB_EINVAL, "unknown array");
+  return IKB_OK;
+}
+
+int ikb_time_phase(ikb_handle hh, const char* phase, int dbc, int reps, float* ms) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!phase || !ms || reps <= 0 || !dbcValid(dbc)) return fail(h, IKB_EINVAL, "bad arguments");
+  const std::string p(phase);
+  cudaEvent_t e0, e1;
+  IKB_CUDA(h, cudaEventCreate(&e0));
+  IKB_CUDA(h, cudaEventCreate(&e1));
+  int rc = IKB_OK;
+  DevBuf<double> tmp;
+  if (p == "dfma_peak") IKB_CUDA(h, tmp.alloc((size_t)148 * 16 * 256));
+  if (p == "elements" || p == "gather") {
+    if ((rc = ikb_assemble(hh, IKB_MATRIX | IKB_VECTOR, dbc))) return rc;
+  } else if (p == "spmv") {
+    if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "assemble first");
+    const int64_t n = std::max(rowsOf(h, dbc), h->nDof);
+    if (h->cgP.n < (size_t)n) IKB_CUDA(h, h->cgP.alloc((size_t)n));
+    if (h->cgQ.n < (size_t)n) IKB_CUDA(h, h->cgQ.alloc((size_t)n));
+    IKB_CUDA(h, cudaMemsetAsync(h->cgP.p, 0, h->cgP.bytes(), h->stream));
+  }
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  IKB_CUDA(h, cudaEventRecord(e0, h->stream));
+  for (int r = 0; r < reps && rc == IKB_OK; ++r) {
+    if (p == "elements")
+      rc = launchElements(h, IKB_MATRIX | IKB_VECTOR);
+    else if (p == "gather")
+      rc = launchGather(h, IKB_MATRIX | IKB_VECTOR, dbc);
+    else if (p == "spmv")
+      rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p);
+    else if (p == "dfma_peak") {
+      dfma_peak_kernel<<<148 * 16, 256, 0, h->stream>>>(tmp.p, 2048);
+      h->launches++;
+    } else
+      rc = fail(h, IKB_EINVAL, "unknown phase");
+  }
+  IKB_CUDA(h, cudaEventRecord(e1, h->stream));
+  IKB_CUDA(h, cudaEventSynchronize(e1));
+  float t = 0.f;
+  IKB_CUDA(h, cudaEventElapsedTime(&t, e0, e1));
+  *ms = t / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  tmp.release();
+  return rc;
+}
+
+}  // extern "C"

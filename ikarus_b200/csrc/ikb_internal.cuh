@@ -1,0 +1,171 @@
+// Internal state of a device flat assembler handle (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/ikb200.h"
+
+namespace ikb {
+
+enum Form { FORM_LE = 0, FORM_SVK = 1, FORM_NH = 2 };
+enum Layout { LAYOUT_INTERLEAVED = 0, LAYOUT_LEXICOGRAPHIC = 1 };
+
+constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
+constexpr uint32_t SRC_MASK = 0x7fffffffu;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// Node-block view of the sparsity pattern.  Scalar CSR positions are analytic in it:
+//   interleaved   : row d*ga+i starts at d*d*nbrPtr[ga] + i*d*nnb(ga); entry (slot,k) at +d*slot+k
+//   lexicographic : row i*nNodes+ga starts at i*d*nBlocks + d*nbrPtr[ga]; entry (k,slot) at +k*nnb(ga)+slot
+struct PatternView {
+  int dim;
+  int layout;
+  int64_t nNodes;     // global node count (columns)
+  int64_t rowBegin;   // first owned node-row
+  int64_t nRowNodes;  // owned node-rows
+  int64_t nBlocks;
+  const int32_t* nbrPtr;  // [nRowNodes+1]
+  const int32_t* nbrIdx;  // [nBlocks] global neighbour node, sorted per row
+  const int32_t* nbrRow;  // [nBlocks] local row-node of the block
+};
+
+__host__ __device__ inline int64_t rawRowStart(const PatternView& P, int64_t gaLocal, int i, int nnb) {
+  const int d = P.dim;
+  if (P.layout == LAYOUT_INTERLEAVED) return (int64_t)d * d * P.nbrPtr[gaLocal] + (int64_t)i * d * nnb;
+  return (int64_t)i * d * P.nBlocks + (int64_t)d * P.nbrPtr[gaLocal];
+}
+__host__ __device__ inline int64_t rawEntryOffset(const PatternView& P, int slot, int k, int nnb) {
+  if (P.layout == LAYOUT_INTERLEAVED) return (int64_t)P.dim * slot + k;
+  return (int64_t)k * nnb + slot;
+}
+__host__ __device__ inline int64_t dofOf(int layout, int dim, int64_t nNodes, int64_t node, int c) {
+  return layout == LAYOUT_INTERLEAVED ? node * dim + c : (int64_t)c * nNodes + node;
+}
+
+struct Handle {
+  ikb_desc desc{};
+  int dim = 0, order = 0, nn = 0, nd = 0, nc = 0, npair = 0, form = 0, easM = 0;
+  int layout = 0;
+  int64_t nElem = 0, nDof = 0, nNodes = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;
+  std::string lastError;
+  int64_t launches = 0;
+
+  // mesh
+  DevBuf<double> X;         // [nc*dim][nElem]  corner coordinates, element fastest
+  DevBuf<int32_t> elemNode; // [nn][nElem]      global node ids, element fastest
+  bool meshUploaded = false;
+
+  // row ownership (multi-GPU); defaults to all nodes
+  int64_t rowBegin = 0, rowEnd = -1;
+
+  // state
+  DevBuf<double> U, Fext, Corr;
+  double lambda = 0.0;
+  int fextScales = 1;
+  bool hasFext = false;
+  DevBuf<uint8_t> flags;
+  bool hasFlags = false;
+  uint64_t stateVersion = 1;  // bumped on every change of d / lambda / alpha / fext
+
+  // pattern (node-block) + gather map
+  bool patternBuilt = false;
+  int64_t nBlocks = 0;
+  DevBuf<int32_t> nbrPtr, nbrIdx, nbrRow, cptr;
+  DevBuf<uint32_t> csrc;
+  // reduced-mode structures
+  bool reducedBuilt = false;
+  int64_t nRed = 0, nnzRed = 0;
+  DevBuf<int32_t> cbelow;       // constraintsBelow [nDof]
+  DevBuf<uint16_t> freeCnt;     // [nBlocks][dim]
+  DevBuf<uint16_t> freeTot;     // [nRowNodes][dim]
+  DevBuf<int64_t> redRowStart;  // [nDofLocalRows+1] indexed by local scalar row (row order), exclusive scan
+  DevBuf<int32_t> redInner;     // [nnzRed]
+  DevBuf<int64_t> redOuter;     // [nRed+1]
+
+  // staging + results
+  DevBuf<double> Kst, Rst, Est;
+  DevBuf<double> vals[3];      // indexed by IKB_DBC_*
+  DevBuf<double> vec[3];
+  uint64_t valsVersion[3] = {0, 0, 0}, vecVersion[3] = {0, 0, 0}, energyVersion = 0;
+  uint64_t stagedVersion = 0;
+  unsigned stagedWhat = 0;
+  double energy = 0.0;
+  DevBuf<double> scratch;      // reductions
+  DevBuf<int32_t> errFlag;     // first failing element (material abort), INT_MAX if none
+
+  // EAS
+  DevBuf<double> alpha;        // [nElem][m]
+
+  // PCG work
+  DevBuf<double> cgR, cgZ, cgP, cgQ, cgX, cgDinv, cgB;
+  DevBuf<double> cgScal;       // device scalars
+  double* hostScal = nullptr;  // pinned
+
+  // NCCL
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  PatternView view() const {
+    PatternView P;
+    P.dim = dim;
+    P.layout = layout;
+    P.nNodes = nNodes;
+    P.rowBegin = rowBegin;
+    P.nRowNodes = rowEnd - rowBegin;
+    P.nBlocks = nBlocks;
+    P.nbrPtr = nbrPtr.p;
+    P.nbrIdx = nbrIdx.p;
+    P.nbrRow = nbrRow.p;
+    return P;
+  }
+  int64_t nnzRaw() const { return (int64_t)dim * dim * nBlocks; }
+  int64_t nRowsLocal() const { return (rowEnd - rowBegin) * dim; }
+};
+
+inline int fail(Handle* h, int code, const std::string& msg) {
+  if (h) h->lastError = msg;
+  return code;
+}
+
+#define IKB_CUDA(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ikb::fail(h, IKB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+#define IKB_LAUNCH_CHECK(h)                                                                       \
+  do {                                                                                            \
+    (h)->launches++;                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ikb::fail(h, IKB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e));    \
+  } while (0)
+
+inline unsigned gridFor(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+}  // namespace ikb

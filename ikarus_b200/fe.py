@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's element description API (no arithmetic on the hot path here).
+
+`makeFE(basis, skills(...))` + `fe.bind(element)` of the reference
+(ikarus/finiteelements/fefactory.hh:67-72, febase.hh:114-117) become one `FEContainer`: the
+walk over the grid that collects corner coordinates and `FEHelper::globalIndices` per element
+(ikarus/finiteelements/fehelper.hh:194-197) is done once by the caller (or by
+include/ikarus_b200/deviceflatassembler.hh when DUNE is present) and handed over as arrays.
+"""
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _capi as capi
+
+
+# ---------------------------------------------------------------------------------- materials
+@dataclass(frozen=True)
+class LamesFirstParameterAndShearModulus:
+    """ikarus/finiteelements/physicshelper.hh:53-57"""
+    lambda_: float
+    mu: float
+
+
+def toLamesFirstParameterAndShearModulus(emodul: float, nu: float) -> LamesFirstParameterAndShearModulus:
+    """ikarus/finiteelements/physicshelper.hh:276-281"""
+    return LamesFirstParameterAndShearModulus(emodul * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), emodul / (2.0 * (1.0 + nu)))
+
+
+@dataclass(frozen=True)
+class _Material:
+    name: str
+    code: int
+    strain: int
+    params: LamesFirstParameterAndShearModulus
+    reduced: bool = False  # planeStrain wrapper
+
+    def materialParameters(self):
+        return self.params
+
+
+class Materials:
+    """Materials::LinearElasticity / StVenantKirchhoff / NeoHooke
+    (mechanics/materials/linearelasticity.hh, svk.hh, hyperelastic/neohooke.hh)."""
+
+    @staticmethod
+    def LinearElasticity(p):
+        return _Material("LinearElasticity", capi.MAT_LINEAR, capi.STRAIN_LINEAR, p)
+
+    @staticmethod
+    def StVenantKirchhoff(p):
+        return _Material("StVenantKirchhoff", capi.MAT_SVK, capi.STRAIN_GL, p)
+
+    @staticmethod
+    def NeoHooke(p):
+        return _Material("NeoHooke", capi.MAT_NEOHOOKE, capi.STRAIN_GL, p)
+
+
+def planeStrain(mat: _Material) -> _Material:
+    """Materials::planeStrain (mechanics/materials/vanishingstrain.hh:147-198)."""
+    return _Material(mat.name, mat.code, mat.strain, mat.params, True)
+
+
+# ------------------------------------------------------------------------------------- skills
+@dataclass(frozen=True)
+class _Solid:
+    strain: int
+    material: _Material
+
+
+@dataclass(frozen=True)
+class _EAS:
+    m: int
+    enhanced: str = "GreenLagrangeStrain"
+
+
+@dataclass(frozen=True)
+class _VolumeLoad:
+    fn: Callable  # f(x[dim], lambda) -> force density [dim]
+
+
+def linearElastic(mat):
+    """mechanics/linearelastic.hh linearElastic(mat): small strains; needs a linear-strain material."""
+    if mat.strain != capi.STRAIN_LINEAR:
+        raise TypeError("linearElastic needs a material with StrainTags::linear")
+    return _Solid(capi.STRAIN_LINEAR, mat)
+
+
+def nonLinearElastic(mat):
+    """mechanics/nonlinearelastic.hh nonLinearElastic(mat): Green-Lagrange strains."""
+    if mat.strain != capi.STRAIN_GL:
+        raise TypeError("nonLinearElastic needs a material with StrainTags::greenLagrangian")
+    return _Solid(capi.STRAIN_GL, mat)
+
+
+def eas(numberOfInternalVariables=0, enhanced="GreenLagrangeStrain"):
+    """mechanics/enhancedassumedstrains.hh eas<ES>(m) with ES in {LinearStrain, GreenLagrangeStrain}."""
+    if enhanced not in ("GreenLagrangeStrain", "LinearStrain"):
+        raise NotImplementedError(f"EAS enhancement {enhanced} is outside the device hot path (SURVEY 8f)")
+    return _EAS(int(numberOfInternalVariables), enhanced)
+
+
+def volumeLoad(fn):
+    """mechanics/loads/volume.hh volumeLoad<dim>(f): f(x, lambda) sampled on the host."""
+    return _VolumeLoad(fn)
+
+
+def skills(*s):
+    """finiteelements/mixin.hh:354-357"""
+    return tuple(s)
+
+
+# ------------------------------------------------------------------- host shape functions (loads only)
+def _gauss01(n):
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def _lag1d(order, xi):
+    if order == 1:
+        return np.array([1.0 - xi, xi])
+    return np.array([2.0 * (xi - 0.5) * (xi - 1.0), 4.0 * xi * (1.0 - xi), 2.0 * xi * (xi - 0.5)])
+
+
+def _shape(dim, order, xi):
+    n1 = order + 1
+    v = [_lag1d(order, xi[k]) for k in range(dim)]
+    return np.array([np.prod([v[k][(a // n1**k) % n1] for k in range(dim)]) for a in range(n1**dim)])
+
+
+def _dshape_q1(dim, xi):
+    out = np.zeros((2**dim, dim))
+    for a in range(2**dim):
+        for i in range(dim):
+            t = 1.0 if (a >> i) & 1 else -1.0
+            for k in range(dim):
+                if k != i:
+                    t *= xi[k] if (a >> k) & 1 else 1.0 - xi[k]
+            out[a, i] = t
+    return out
+
+
+@dataclass
+class FEContainer:
+    """A bound container of identical finite elements: the `std::vector<FE>` the reference hands to
+    makeSparseFlatAssembler (assembler/simpleassemblers.hh:174-177)."""
+    dim: int
+    order: int
+    n_dof: int
+    corner_coords: np.ndarray  # [nElem, 2^dim, dim]
+    elem_dofs: np.ndarray  # [nElem, nodes*dim]
+    solid: _Solid = None
+    eas: Optional[_EAS] = None
+    loads: tuple = ()
+    extra: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return self.corner_coords.shape[0]
+
+    @property
+    def nodes(self):
+        return (self.order + 1) ** self.dim
+
+    def numberOfInternalVariables(self):
+        return self.eas.m if self.eas else 0
+
+    def sample_external_load(self, lam=1.0):
+        """R_e -= N_i f(x_gp, lambda) detJ w summed over elements (loads/volume.hh:86-106) -> fext[n_dof]."""
+        fext = np.zeros(self.n_dof)
+        vl = [s for s in self.loads if isinstance(s, _VolumeLoad)]
+        if not vl:
+            return fext
+        d, order = self.dim, self.order
+        x1, w1 = _gauss01(order + 1)
+        import itertools
+        X = self.corner_coords
+        for idx in itertools.product(range(order + 1), repeat=d):
+            xi = np.array([x1[i] for i in idx])
+            w = np.prod([w1[i] for i in idx])
+            N = _shape(d, order, xi)
+            Ng = _shape(d, 1, xi)
+            dNg = _dshape_q1(d, xi)
+            Jt = np.einsum("ci,ecj->eij", dNg, X)
+            detJ = np.abs(np.linalg.det(Jt))
+            xg = np.einsum("c,ecj->ej", Ng, X)
+            f = np.zeros_like(xg)
+            for s in vl:
+                f += np.array([np.asarray(s.fn(p, lam), float) for p in xg])
+            contrib = (N[None, :, None] * f[:, None, :] * (detJ * w)[:, None, None]).reshape(len(self), -1)
+            np.add.at(fext, self.elem_dofs.ravel(), contrib.ravel())
+        return fext
+
+
+def makeFE(basis, sk, corner_coords=None, elem_dofs=None):
+    """makeFE(basisHandler, skills(...)) (finiteelements/fefactory.hh:67-72) followed by bind over all
+    grid elements.  `basis` is a dict/obj with dim, order, n_dof."""
+    dim, order, n_dof = basis["dim"], basis["order"], basis["n_dof"]
+    solid = [s for s in sk if isinstance(s, _Solid)]
+    if len(solid) != 1:
+        raise TypeError("exactly one solid skill (linearElastic / nonLinearElastic) is required")
+    e = [s for s in sk if isinstance(s, _EAS)]
+    loads = tuple(s for s in sk if isinstance(s, _VolumeLoad))
+    mat = solid[0].material
+    if dim == 2 and not mat.reduced:
+        raise TypeError("2D elements need a reduced material (planeStrain)")
+    if dim == 3 and mat.reduced:
+        raise TypeError("3D elements need a full 3D material")
+    return FEContainer(dim, order, n_dof, np.ascontiguousarray(corner_coords, float),
+                       np.ascontiguousarray(elem_dofs, np.int64), solid[0], e[0] if e else None, loads)
+
+
+class DirichletValues:
+    """utils/dirichletvalues.hh:73-311 (flags only; inhomogeneous BC functions are SURVEY 8f 'next')."""
+
+    def __init__(self, n_dof):
+        self._flags = np.zeros(int(n_dof), dtype=bool)
+
+    def fixDOFs(self, f):
+        f(self._flags)
+
+    def setSingleDOF(self, i, flag=True):
+        self._flags[i] = flag
+
+    def fixIthDOF(self, i):
+        self._flags[i] = True
+
+    def isConstrained(self, i):
+        return bool(self._flags[i])
+
+    def fixedDOFsize(self):
+        return int(self._flags.sum())
+
+    def size(self):
+        return self._flags.shape[0]
+
+    def container(self):
+        return self._flags

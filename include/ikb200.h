@@ -1,0 +1,165 @@
+/*
+ * ikb200.h -- C-ABI of the B200 device flat assembler (libikb200.so).
+ *
+ * This is the drop-in boundary for the one hot path of Ikarus that this project
+ * accelerates: global FEM assembly of tangent K, residual R and energy E plus the
+ * Jacobi-PCG solve that consumes them.  The reference has no FFI of its own; its
+ * boundary is the C++ concept Concepts::MatrixFlatAssembler
+ * (ikarus/utils/concepts.hh:517-585).  Each entry point below names the reference
+ * member function it replaces (paths relative to the reference root).
+ * include/ikarus_b200/deviceflatassembler.hh wraps this ABI back into that concept.
+ *
+ * Conventions
+ *  - every function returns IKB_OK (0) or a negative IKB_E* code; ikb_last_error()
+ *    gives the message.  No exceptions cross the boundary.
+ *  - all pointers are caller-owned HOST buffers unless the name says "device".
+ *  - a handle owns one CUDA device + one stream; calls on a handle are serialised by
+ *    the caller (the reference assembler is single-threaded and not re-entrant,
+ *    ikarus/assembler/simpleassemblers.hh:90-92).
+ *  - element-local dof order is node-major/component-minor, i*dim + c
+ *    (ikarus/finiteelements/fehelper.hh:145-153).
+ *  - matrices use the compressed layout Eigen::SparseMatrix<double> (column-major,
+ *    sorted inner indices) has after setFromTriplets
+ *    (ikarus/assembler/simpleassemblers.inl:206-251).  The pattern is structurally
+ *    symmetric and K is symmetric, so the same arrays are a valid CSR view.
+ */
+#ifndef IKB200_H
+#define IKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IKB_ABI_VERSION 1
+
+typedef struct ikb_handle_s* ikb_handle;
+
+enum { IKB_OK = 0, IKB_EINVAL = -1, IKB_ECUDA = -2, IKB_ESTATE = -3, IKB_ENOTIMPL = -4, IKB_EMATERIAL = -5, IKB_ENCCL = -6 };
+
+/* strain measure of the solid skill: linearElastic (mechanics/linearelastic.hh) or
+ * nonLinearElastic (mechanics/nonlinearelastic.hh) */
+enum { IKB_STRAIN_LINEAR = 0, IKB_STRAIN_GREEN_LAGRANGE = 1 };
+/* Materials::LinearElasticity / StVenantKirchhoff / NeoHooke
+ * (mechanics/materials/linearelasticity.hh, svk.hh, hyperelastic/neohooke.hh) */
+enum { IKB_MAT_LINEAR_ELASTICITY = 0, IKB_MAT_SVK = 1, IKB_MAT_NEOHOOKE = 2 };
+/* DBCOption (assembler/dirichletbcenforcement.hh) */
+enum { IKB_DBC_RAW = 0, IKB_DBC_REDUCED = 1, IKB_DBC_FULL = 2 };
+/* affordance bits: ScalarAffordance::mechanicalPotentialEnergy, VectorAffordance::forces,
+ * MatrixAffordance::stiffness (finiteelements/ferequirements.hh:35-89) */
+enum { IKB_SCALAR = 1, IKB_VECTOR = 2, IKB_MATRIX = 4 };
+
+typedef struct ikb_desc {
+  int32_t abi_version;  /* IKB_ABI_VERSION */
+  int32_t dim;          /* 2 | 3 */
+  int32_t order;        /* Lagrange order of the power basis: 1 (Quad4/Hex8) | 2 (Quad9/Hex27) */
+  int32_t strain;       /* IKB_STRAIN_* */
+  int32_t material;     /* IKB_MAT_* */
+  int32_t plane_strain; /* 2D only: Materials::planeStrain(mat) (materials/vanishingstrain.hh) */
+  int32_t eas_m;        /* eas<...>(m): 0 | 4,5,7 (2D Q1) | 9,21 (3D Q1)  (easvariants/linearandglstrains.hh) */
+  int32_t device;       /* CUDA ordinal, -1 = current device */
+  double lambda;        /* Lame's first parameter (physicshelper.hh:53-57) */
+  double mu;            /* shear modulus */
+  int64_t n_elem;       /* elements owned by this handle */
+  int64_t n_dof;        /* global dofs = basis.flat().size() */
+} ikb_desc;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+/* replaces makeSparseFlatAssembler / SparseFlatAssembler ctor (assembler/simpleassemblers.hh:174-177) */
+int ikb_create(ikb_handle* h, const ikb_desc* desc);
+int ikb_destroy(ikb_handle h);
+int ikb_last_error(ikb_handle h, char* buf, size_t len);
+
+/* ---- one-time uploads ----------------------------------------------------------- */
+/* corner_coords[n_elem][2^dim][dim]: fe.gridElement().geometry().corner(c) (nonlinearelastic.hh:117);
+ * elem_dofs[n_elem][nodes*dim]: FEHelper::globalIndices(fe, dofs) (finiteelements/fehelper.hh:194-197).
+ * The dofs of one Lagrange node must be FlatInterleaved (dim*node+c) or FlatLexicographic
+ * (c*nNodes+node); anything else returns IKB_ENOTIMPL. */
+int ikb_upload_mesh(ikb_handle h, const double* corner_coords, const int64_t* elem_dofs);
+/* DirichletValues flags (utils/dirichletvalues.hh:73-131); constraintsBelow is derived
+ * on the device (FlatAssemblerBase ctor, assembler/interface.hh:51-62). */
+int ikb_upload_dirichlet(ikb_handle h, const uint8_t* flags);
+/* createOccupationPattern + createLinearDOFsPerElement (+ the Reduced variants)
+ * (assembler/simpleassemblers.inl:206-299): builds the sparsity pattern and the
+ * deterministic element->CSR gather map on the device. */
+int ikb_build_pattern(ikb_handle h);
+int ikb_pattern_nnz(ikb_handle h, int dbc, int64_t* rows, int64_t* nnz);
+/* outer[rows+1], inner[nnz]: for bit-exact comparison with Eigen's outerIndexPtr/innerIndexPtr */
+int ikb_get_pattern(ikb_handle h, int dbc, int64_t* outer, int32_t* inner);
+/* constraintsBelow(i) for all i (assembler/interface.hh:124-132) */
+int ikb_get_constraints_below(ikb_handle h, int64_t* out);
+/* ikb_element_linear_indices: elementLinearIndices_[e] as createLinearDOFsPerElement builds it
+ * (column-major over A: for c, for r; simpleassemblers.inl:253-266); Raw pattern only. */
+int ikb_element_linear_indices(ikb_handle h, int64_t elem, int64_t* out);
+
+/* ---- per-solve state ------------------------------------------------------------ */
+/* FERequirements::globalSolution()/parameter() (finiteelements/ferequirements.hh:222-407) */
+int ikb_set_solution(ikb_handle h, const double* d);
+int ikb_set_parameter(ikb_handle h, double lambda);
+/* Host-sampled volume/Neumann/point loads (mechanics/loads/volume.hh:67-106,
+ * loads/traction.hh:70-138): R = F_int - s*fext, E -= s*fext.d with s = lambda when
+ * scales_with_lambda else 1. */
+int ikb_set_external_load(ikb_handle h, const double* fext, int scales_with_lambda);
+
+/* ---- the hot path --------------------------------------------------------------- */
+/* One fused element sweep producing any of K, R, E for one DBC mode; replaces
+ * getRawMatrixImpl/getMatrixImpl/getReducedMatrixImpl, get*VectorImpl and getScalarImpl
+ * (assembler/simpleassemblers.inl:17-24, 59-204).  Results stay on the device. */
+int ikb_assemble(ikb_handle h, unsigned what, int dbc);
+int ikb_get_vector(ikb_handle h, int dbc, double* out);       /* N or N_red doubles */
+int ikb_get_scalar(ikb_handle h, double* energy);
+int ikb_get_matrix_values(ikb_handle h, int dbc, double* out); /* nnz doubles, Eigen value order */
+/* DenseFlatAssembler (assembler/simpleassemblers.inl:301-375): column-major rows x rows */
+int ikb_get_dense_matrix(ikb_handle h, int dbc, double* out);
+/* 2-norm of the assembled vector (NewtonRaphson needs ||rx|| on the host,
+ * solver/nonlinearsolver/newtonraphson.hh:206) */
+int ikb_vector_norm(ikb_handle h, int dbc, double* norm);
+
+/* ---- EAS internal variables ----------------------------------------------------- */
+/* EnhancedAssumedStrains::updateStateImpl on CORRECTION_UPDATED
+ * (mechanics/enhancedassumedstrains.hh:225-248); correction has N entries (DBCOption::Full). */
+int ikb_eas_update(ikb_handle h, const double* correction);
+int ikb_eas_get_alpha(ikb_handle h, double* alpha /* [n_elem][m] */);
+int ikb_eas_set_alpha(ikb_handle h, const double* alpha);
+
+/* ---- linear solve --------------------------------------------------------------- */
+/* Jacobi-preconditioned CG on the assembled matrix of mode dbc (Full or Reduced); the
+ * analogue of LinearSolver(SolverTypeTag::si_ConjugateGradient)
+ * (solver/linearsolver/linearsolver.cpp:23-24).  rhs == NULL solves K x = -R with the
+ * resident residual.  Stops at ||r|| <= rel_tol*||rhs||. */
+int ikb_pcg_solve(ikb_handle h, int dbc, const double* rhs, double* x, double rel_tol, int max_it, int* iters,
+                  double* rel_res);
+/* x += correction on the resident solution (NonlinearSolverFactory update functor,
+ * solver/nonlinearsolver/nonlinearsolverfactory.hh:33-56); correction lives on the device
+ * (last PCG result) when correction == NULL. dbc selects Reduced->Full expansion. */
+int ikb_update_solution(ikb_handle h, int dbc, const double* correction);
+int ikb_get_solution(ikb_handle h, double* d);
+/* y = K x for the assembled matrix of mode dbc (host in/out); used by tests and by
+ * utils::obtainForcesDueToIDBC-style callers (utils/functionhelper.hh:170-185). */
+int ikb_spmv(ikb_handle h, int dbc, const double* x, double* y);
+
+/* ---- multi-GPU (element partition, row-block ownership) ------------ */
+/* Restricts the handle to the rows of nodes [node_begin, node_end) (a contiguous
+ * row block); elements uploaded must be all elements touching an owned node
+ * (owner-computes with one ghost layer).  Must precede ikb_build_pattern. */
+int ikb_set_row_ownership(ikb_handle h, int64_t node_begin, int64_t node_end);
+int ikb_nccl_unique_id(void* id128 /* 128 bytes */);
+int ikb_comm_init(ikb_handle h, const void* id128, int rank, int nranks);
+
+/* ---- introspection for benchmarks ------------------------------------------------ */
+int ikb_stream(ikb_handle h, void** cuda_stream);
+int ikb_sync(ikb_handle h);
+/* number of kernel launches issued by this handle since creation */
+int ikb_launch_count(ikb_handle h, int64_t* n);
+/* device pointers of resident arrays: what = "solution" | "residual" | "values" | "correction" */
+int ikb_device_ptr(ikb_handle h, const char* what, int dbc, void** ptr);
+/* time `reps` back-to-back launches of one phase with CUDA events on the handle's
+ * stream: phase = "elements" | "gather" | "spmv" | "dfma_peak" ; returns mean ms */
+int ikb_time_phase(ikb_handle h, const char* phase, int dbc, int reps, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IKB200_H */
