@@ -37,6 +37,7 @@ SYMBOLS = {
     "ikb_set_parameter": [C.c_void_p, C.c_double],
     "ikb_set_external_load": [C.c_void_p, C.c_void_p, C.c_int],
     "ikb_assemble": [C.c_void_p, C.c_uint, C.c_int],
+    "ikb_invalidate": [C.c_void_p],
     "ikb_get_vector": [C.c_void_p, C.c_int, C.c_void_p],
     "ikb_get_scalar": [C.c_void_p, C.POINTER(C.c_double)],
     "ikb_get_matrix_values": [C.c_void_p, C.c_int, C.c_void_p],

@@ -114,7 +114,7 @@ class DeviceMatrix:
 
 
 class _FlatAssemblerBase:
-    def __init__(self, fes: FEContainer, dirichletValues: DirichletValues, device=-1, mode="mirror"):
+    def __init__(self, fes: FEContainer, dirichletValues: DirichletValues, device=-1, mode="mirror", rows=None):
         if mode not in ("mirror", "resident"):
             raise ValueError(mode)
         self._lib = capi.load()
@@ -142,6 +142,10 @@ class _FlatAssemblerBase:
         self._check(self._lib.ikb_upload_mesh(self._h, capi.ptr(fes.corner_coords), capi.ptr(fes.elem_dofs)))
         self._flags_u8 = np.ascontiguousarray(flags, dtype=np.uint8)
         self._check(self._lib.ikb_upload_dirichlet(self._h, capi.ptr(self._flags_u8)))
+        if rows is not None:
+            # element-partitioned run: this handle owns the rows of nodes [rows[0], rows[1])
+            self._check(self._lib.ikb_set_row_ownership(self._h, int(rows[0]), int(rows[1])))
+        self._rows = rows
         self._check(self._lib.ikb_build_pattern(self._h))
         self._fext_lambda = None
         self._last_d = None

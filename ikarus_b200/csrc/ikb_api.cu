@@ -697,6 +697,13 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
   return IKB_OK;
 }
 
+int ikb_invalidate(ikb_handle hh) {
+  Handle* h = H(hh);
+  if (!h) return IKB_EINVAL;
+  h->stateVersion++;
+  return IKB_OK;
+}
+
 int ikb_get_vector(ikb_handle hh, int dbc, double* out) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;

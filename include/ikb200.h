@@ -108,6 +108,9 @@ int ikb_set_external_load(ikb_handle h, const double* fext, int scales_with_lamb
  * getRawMatrixImpl/getMatrixImpl/getReducedMatrixImpl, get*VectorImpl and getScalarImpl
  * (assembler/simpleassemblers.inl:17-24, 59-204).  Results stay on the device. */
 int ikb_assemble(ikb_handle h, unsigned what, int dbc);
+/* Marks every cached result stale so that the next ikb_assemble recomputes even if d, lambda and alpha
+ * are unchanged (the reference recomputes on every call; the cache is an optimisation of this layer). */
+int ikb_invalidate(ikb_handle h);
 int ikb_get_vector(ikb_handle h, int dbc, double* out);       /* N or N_red doubles */
 int ikb_get_scalar(ikb_handle h, double* energy);
 int ikb_get_matrix_values(ikb_handle h, int dbc, double* out); /* nnz doubles, Eigen value order */
