@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "ikb_elem_eas.cuh"
 #include "ikb_elem_q1.cuh"
 #include "ikb_gather.cuh"
 #include "ikb_internal.cuh"
@@ -26,7 +27,26 @@ int checkHandle(Handle* h) {
 
 int dbcValid(int dbc) { return dbc == IKB_DBC_RAW || dbc == IKB_DBC_REDUCED || dbc == IKB_DBC_FULL; }
 
-int launchElements(Handle* h, unsigned what) {
+template <int D, int M>
+cudaError_t launchEasForm(Handle* h, const EasArgs& EA) {
+  if (h->form == FORM_LE) return launchElemEas<D, FORM_LE, M>(EA, h->stream);
+  if (h->form == FORM_SVK) return launchElemEas<D, FORM_SVK, M>(EA, h->stream);
+  return launchElemEas<D, FORM_NH, M>(EA, h->stream);
+}
+
+cudaError_t launchEas(Handle* h, const EasArgs& EA) {
+  if (h->dim == 2) {
+    if (h->easM == 4) return launchEasForm<2, 4>(h, EA);
+    if (h->easM == 5) return launchEasForm<2, 5>(h, EA);
+    if (h->easM == 7) return launchEasForm<2, 7>(h, EA);
+  } else {
+    if (h->easM == 9) return launchEasForm<3, 9>(h, EA);
+    if (h->easM == 21) return launchEasForm<3, 21>(h, EA);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   ElemArgs A;
   A.X = h->X.p;
   A.elemNode = h->elemNode.p;
@@ -52,8 +72,16 @@ int launchElements(Handle* h, unsigned what) {
       if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
       if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
     }
+  } else if (h->order == 1) {
+    EasArgs EA;
+    EA.E = A;
+    EA.T0inv = h->T0inv.p;
+    EA.alpha = h->alpha.p;
+    EA.dU = dU;
+    EA.updateMode = dU ? 1 : 0;
+    e = launchEas(h, EA);
   } else {
-    return fail(h, IKB_ENOTIMPL, "element kind not implemented on the device yet (order 2 / EAS)");
+    return fail(h, IKB_ENOTIMPL, "element kind not implemented on the device yet (order 2)");
   }
   h->launches++;
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("element kernel: ") + cudaGetErrorString(e));
@@ -386,6 +414,79 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   if (h->easM) {
     IKB_CUDA(h, h->alpha.alloc((size_t)ne * h->easM));
     IKB_CUDA(h, cudaMemsetAsync(h->alpha.p, 0, h->alpha.bytes(), h->stream));  // initializeState (:373-376)
+    // EX ctor: T0InverseTransformed = (transformationMatrix(geo, center) * detJ0)^-1
+    // (easvariants/helperfunctions.hh:18-25, utils/tensorutils.hh:408-465); one-time, on the host
+    const int S = D * (D + 1) / 2;
+    std::vector<double> t0((size_t)S * S * ne);
+    for (int64_t e = 0; e < ne; ++e) {
+      double J[3][3] = {{0}};
+      for (int c = 0; c < nc; ++c)
+        for (int i = 0; i < D; ++i) {
+          double dn = ((c >> i) & 1) ? 1.0 : -1.0;
+          for (int k = 0; k < D; ++k)
+            if (k != i) dn *= 0.5;
+          for (int k = 0; k < D; ++k) J[i][k] += dn * corner[(size_t)e * nc * D + c * D + k];
+        }
+      double T[6][6], Ti[6][6];
+      double det;
+      if (D == 2) {
+        det = std::fabs(J[0][0] * J[1][1] - J[0][1] * J[1][0]);
+        const double J11 = J[0][0], J12 = J[0][1], J21 = J[1][0], J22 = J[1][1];
+        const double t[3][3] = {{J11 * J11, J12 * J12, J11 * J12},
+                                {J21 * J21, J22 * J22, J21 * J22},
+                                {2 * J11 * J21, 2 * J12 * J22, J21 * J12 + J11 * J22}};
+        for (int p = 0; p < 3; ++p)
+          for (int q = 0; q < 3; ++q) T[p][q] = t[p][q] * det;
+      } else {
+        const double J11 = J[0][0], J12 = J[0][1], J13 = J[0][2], J21 = J[1][0], J22 = J[1][1], J23 = J[1][2],
+                     J31 = J[2][0], J32 = J[2][1], J33 = J[2][2];
+        det = std::fabs(J11 * (J22 * J33 - J23 * J32) - J12 * (J21 * J33 - J23 * J31) + J13 * (J21 * J32 - J22 * J31));
+        const double t[6][6] = {
+            {J11 * J11, J12 * J12, J13 * J13, J12 * J13, J11 * J13, J11 * J12},
+            {J21 * J21, J22 * J22, J23 * J23, J22 * J23, J21 * J23, J21 * J22},
+            {J31 * J31, J32 * J32, J33 * J33, J32 * J33, J31 * J33, J31 * J32},
+            {2 * J21 * J31, 2 * J22 * J32, 2 * J23 * J33, J22 * J33 + J32 * J23, J31 * J23 + J21 * J33,
+             J21 * J32 + J31 * J22},
+            {2 * J11 * J31, 2 * J12 * J32, 2 * J13 * J33, J12 * J33 + J32 * J13, J11 * J33 + J31 * J13,
+             J11 * J32 + J31 * J12},
+            {2 * J11 * J21, 2 * J12 * J22, 2 * J13 * J23, J12 * J23 + J22 * J13, J11 * J23 + J21 * J13,
+             J11 * J22 + J12 * J21}};
+        for (int p = 0; p < 6; ++p)
+          for (int q = 0; q < 6; ++q) T[p][q] = t[p][q] * det;
+      }
+      // Gauss-Jordan with partial pivoting
+      for (int p = 0; p < S; ++p)
+        for (int q = 0; q < S; ++q) Ti[p][q] = p == q ? 1.0 : 0.0;
+      for (int col = 0; col < S; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < S; ++r)
+          if (std::fabs(T[r][col]) > std::fabs(T[piv][col])) piv = r;
+        if (T[piv][col] == 0.0) return fail(h, IKB_EINVAL, "singular EAS transformation matrix (degenerate element)");
+        if (piv != col)
+          for (int q = 0; q < S; ++q) {
+            std::swap(T[piv][q], T[col][q]);
+            std::swap(Ti[piv][q], Ti[col][q]);
+          }
+        const double ip = 1.0 / T[col][col];
+        for (int q = 0; q < S; ++q) {
+          T[col][q] *= ip;
+          Ti[col][q] *= ip;
+        }
+        for (int r = 0; r < S; ++r) {
+          if (r == col) continue;
+          const double f = T[r][col];
+          if (f == 0.0) continue;
+          for (int q = 0; q < S; ++q) {
+            T[r][q] -= f * T[col][q];
+            Ti[r][q] -= f * Ti[col][q];
+          }
+        }
+      }
+      for (int p = 0; p < S; ++p)
+        for (int q = 0; q < S; ++q) t0[(size_t)(p * S + q) * ne + e] = Ti[p][q];
+    }
+    IKB_CUDA(h, h->T0inv.alloc(t0.size()));
+    IKB_CUDA(h, cudaMemcpy(h->T0inv.p, t0.data(), h->T0inv.bytes(), cudaMemcpyHostToDevice));
   }
   return IKB_OK;
 }
@@ -785,11 +886,25 @@ int ikb_vector_norm(ikb_handle hh, int dbc, double* norm) {
   return rc;
 }
 
-int ikb_eas_update(ikb_handle hh, const double*) {
+int ikb_eas_update(ikb_handle hh, const double* correction) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;
   if (!h->easM) return IKB_OK;
-  return fail(h, IKB_ENOTIMPL, "EAS update not implemented yet");
+  if (!h->meshUploaded) return fail(h, IKB_ESTATE, "mesh missing");
+  int rc;
+  if ((rc = ensureSolution(h))) return rc;
+  if ((rc = ensureStaging(h))) return rc;
+  if (h->Corr.n < (size_t)h->nDof) {
+    if (!correction) return fail(h, IKB_ESTATE, "no resident correction");
+    IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
+  }
+  if (correction)
+    IKB_CUDA(h, cudaMemcpyAsync(h->Corr.p, correction, (size_t)h->nDof * sizeof(double), cudaMemcpyHostToDevice,
+                                h->stream));
+  // D, L, Rtilde at the OLD (d, alpha): must run before ikb_update_solution / ikb_set_solution of the new d
+  if ((rc = launchElements(h, 0, h->Corr.p))) return rc;
+  h->stateVersion++;
+  return IKB_OK;
 }
 int ikb_eas_get_alpha(ikb_handle hh, double* alpha) {
   Handle* h = H(hh);

@@ -119,6 +119,7 @@ struct Handle {
 
   // EAS
   DevBuf<double> alpha;        // [nElem][m]
+  DevBuf<double> T0inv;        // [S*S][nElem] (T(center) detJ0)^-1 per element
 
   // PCG work
   DevBuf<double> cgR, cgZ, cgP, cgQ, cgX, cgDinv, cgB;

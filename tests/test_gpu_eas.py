@@ -1,0 +1,110 @@
+"""GPU parity for the EAS kernels (enhanced strain, static condensation, internal-variable update) and the
+reference's own cantilever known-answer tests driven through the device assembler."""
+import numpy as np
+import pytest
+
+import ikarus_b200 as ik
+import ikarus_oracle as o
+from devproblems import device_assembler, entry_error
+from problems import cantilever, distorted
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+EAS_CASES = [(3, 21, "neohooke", "gl"), (3, 9, "svk", "gl"), (3, 9, "neohooke", "gl"), (2, 4, "neohooke", "gl"),
+             (2, 5, "svk", "gl"), (2, 7, "neohooke", "gl"), (2, 4, "linear", "linear"), (3, 9, "linear", "linear")]
+
+
+def _setup(dim, m, matk, strain, seed=0, nu=0.3):
+    cells = (3, 2, 2) if dim == 3 else (4, 3)
+    mesh = distorted(o.structured_mesh(cells, tuple(float(c) for c in cells)), 0.15, seed + 2)
+    lam, mu = o.lame_from_E_nu(1000.0, nu)
+    mat = o.Material(matk, lam, mu, dim == 2)
+    kind = o.ElementKind(dim, 1, strain, m)
+    flags = o.fix_nodes(mesh, o.boundary_nodes(o.structured_mesh(cells, tuple(float(c) for c in cells)), 0, 0.0))
+    rng = np.random.default_rng(seed)
+    n = flags.shape[0]
+    d = 0.03 * rng.uniform(-1, 1, n)
+    alpha = 0.01 * rng.uniform(-1, 1, (mesh.n_elem, m))
+    ref = o.FlatAssembler(mesh, kind, mat, flags)
+    dev = device_assembler(mesh, kind, mat, flags)
+    return mesh, ref, dev, d, alpha, rng
+
+
+@pytest.mark.parametrize("case", EAS_CASES, ids=lambda c: f"{c[0]}d-E{c[1]}-{c[2]}")
+def test_eas_matrix_vector_and_alpha_update(case):
+    mesh, ref, dev, d, alpha, rng = _setup(*case)
+    ref.alpha = alpha.copy()
+    dev.setInternalVariables(alpha)
+    req = ik.FERequirements(d, 0.0)
+    for mode, dbc in (("raw", ik.DBCOption.Raw), ("full", ik.DBCOption.Full), ("reduced", ik.DBCOption.Reduced)):
+        K = dev.matrix(req, ik.MatrixAffordance.stiffness, dbc)
+        outer, inner = ref.pattern(mode)
+        assert np.array_equal(K.indptr, outer) and np.array_equal(K.indices, inner)
+        rows = np.repeat(np.arange(outer.shape[0] - 1), np.diff(outer))
+        assert entry_error(K.data, ref.matrix_values(d, 0.0, mode), rows) <= 5e-12, mode
+        R = dev.vector(req, ik.VectorAffordance.forces, dbc)
+        Rr = ref.vector(d, 0.0, mode)
+        assert np.abs(R - Rr).max() <= 5e-12 * np.abs(Rr).max(), mode
+    Kd = dev.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Raw).toarray()
+    assert np.array_equal(Kd, Kd.T)  # condensed K mirrored from the upper triangle (:294-295)
+    # alpha update at the old (d, alpha)
+    corr = 0.01 * rng.uniform(-1, 1, d.shape[0])
+    dev.updateInternalVariables(req, corr)
+    ref.update_eas(d, corr)
+    a_dev = dev.internalVariables()
+    assert np.abs(a_dev - ref.alpha).max() <= 1e-11 * max(1.0, np.abs(ref.alpha).max())
+    # a reduced-size correction is rejected like in the reference (:231-235)
+    with pytest.raises(NotImplementedError):
+        dev.updateInternalVariables(req, corr[: dev.reducedSize()])
+    # EAS elements expose no potential (:302-310)
+    with pytest.raises(NotImplementedError):
+        dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+
+
+def test_eas_zero_parameters_is_plain_element():
+    # testnonlineareas.cpp:145-189: eas(0) == displacement element; here E9 with alpha = 0 at d = 0 has the same R
+    mesh, ref, dev, d, alpha, rng = _setup(3, 9, "neohooke", "gl")
+    plain = device_assembler(mesh, o.ElementKind(3, 1, "gl", 0), ref.mat, ref.flags)
+    z = np.zeros_like(d)
+    req = ik.FERequirements(z, 0.0)
+    assert np.abs(dev.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Raw)
+                  - plain.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Raw)).max() <= 1e-12
+
+
+@pytest.mark.parametrize(
+    "dim,matk,m,iters,maxd",
+    [
+        (3, "neohooke", 21, 80, 4.781820664768682),  # tests/src/testcantileverbeamEAS.cpp:66-67
+        (3, "svk", 21, 80, 4.7692391315649365),  # :64-65
+        (2, "neohooke", 4, 80, 4.479930218997457),  # :28-29
+        (2, "svk", 4, 80, 4.459851990257645),  # :26-27
+    ],
+)
+def test_reference_cantilever_known_answers_on_device(dim, matk, m, iters, maxd):
+    """The reference's own golden values (80 Newton iterations, max|d| to 1e-10) with the device assembler
+    behind NewtonRaphson + LoadControl, DBCOption::Full, direct host solve as in the reference test."""
+    mesh, kind, mat, flags, fext = cantilever(dim, matk, m)
+    dev = device_assembler(mesh, kind, mat, flags, fext=fext)
+    req = ik.FERequirements(np.zeros(flags.shape[0]), 0.0)
+    dev.bind(req, ik.AffordanceCollection(vector=ik.VectorAffordance.forces, matrix=ik.MatrixAffordance.stiffness),
+             ik.DBCOption.Full)
+    nr = ik.NewtonRaphson(dev, ik.NewtonRaphsonConfig(ik.NRSettings(tol=1e-10)))
+    lc = ik.LoadControl(nr, ik.LoadControlConfig(20, 0.0, 1.0))
+    info = lc.run(req)
+    assert info.success
+    assert info.totalIterations == iters
+    assert abs(np.abs(req.globalSolution()).max() - maxd) < 1e-10
+    assert abs(req.parameter() - 1.0) < 1e-10
+
+
+def test_cantilever_with_device_pcg_matches_golden_iterations():
+    mesh, kind, mat, flags, fext = cantilever(3, "neohooke", 21)
+    dev = device_assembler(mesh, kind, mat, flags, fext=fext, mode="resident")
+    req = ik.FERequirements(np.zeros(flags.shape[0]), 0.0)
+    dev.bind(req, ik.AffordanceCollection(vector=ik.VectorAffordance.forces, matrix=ik.MatrixAffordance.stiffness),
+             ik.DBCOption.Full)
+    nr = ik.NewtonRaphson(dev, ik.NewtonRaphsonConfig(ik.NRSettings(tol=1e-10), ik.DeviceLinearSolver(1e-14)))
+    info = ik.LoadControl(nr, ik.LoadControlConfig(20, 0.0, 1.0)).run(req)
+    assert info.success and info.totalIterations == 80
+    assert abs(np.abs(req.globalSolution()).max() - 4.781820664768682) < 1e-8
