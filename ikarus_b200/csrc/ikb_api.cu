@@ -6,6 +6,7 @@
 
 #include "ikb_elem_eas.cuh"
 #include "ikb_elem_q1.cuh"
+#include "ikb_elem_q2.cuh"
 #include "ikb_gather.cuh"
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
@@ -80,8 +81,18 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
     EA.dU = dU;
     EA.updateMode = dU ? 1 : 0;
     e = launchEas(h, EA);
+  } else if (h->order == 2 && h->easM == 0) {
+    if (h->dim == 3) {
+      if (h->form == FORM_LE) e = launchElemQ2<3, FORM_LE>(A, h->stream);
+      if (h->form == FORM_SVK) e = launchElemQ2<3, FORM_SVK>(A, h->stream);
+      if (h->form == FORM_NH) e = launchElemQ2<3, FORM_NH>(A, h->stream);
+    } else {
+      if (h->form == FORM_LE) e = launchElemQ2<2, FORM_LE>(A, h->stream);
+      if (h->form == FORM_SVK) e = launchElemQ2<2, FORM_SVK>(A, h->stream);
+      if (h->form == FORM_NH) e = launchElemQ2<2, FORM_NH>(A, h->stream);
+    }
   } else {
-    return fail(h, IKB_ENOTIMPL, "element kind not implemented on the device yet (order 2)");
+    return fail(h, IKB_ENOTIMPL, "EAS is only supported for Q1 and H1 elements");
   }
   h->launches++;
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("element kernel: ") + cudaGetErrorString(e));

@@ -18,6 +18,13 @@ CASES = [
     (2, (5, 4), 1, "gl", "neohooke"),
     (2, (5, 4), 1, "gl", "svk"),
     (2, (6, 3), 1, "linear", "linear"),
+    # Q2 (Quad9 / Hex27, 81-dof elements)
+    (3, (2, 2, 2), 2, "gl", "svk"),
+    (3, (2, 2, 1), 2, "gl", "neohooke"),
+    (3, (2, 1, 1), 2, "linear", "linear"),
+    (2, (3, 2), 2, "gl", "neohooke"),
+    (2, (3, 2), 2, "gl", "svk"),
+    (2, (3, 2), 2, "linear", "linear"),
 ]
 
 
@@ -41,7 +48,7 @@ def _setup(dim, cells, order, strain, matk, layout="interleaved", distort=0.15, 
 
 
 @pytest.mark.parametrize("layout", ["interleaved", "lexicographic"])
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-{c[3]}-{c[4]}")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-Q{c[2]}-{c[3]}-{c[4]}")
 def test_pattern_bit_exact_and_values(case, layout):
     mesh, ref, dev, d = _setup(*case, layout=layout)
     lam = 0.7
