@@ -1,0 +1,434 @@
+// SPDX-License-Identifier: LGPL-3.0-or-later
+/**
+ * \file deviceflatassembler.hh
+ * \brief Header-only C++20 host side of the B200 device flat assembler.
+ *
+ * DeviceSparseFlatAssembler<FEC, DV> models the reference's Concepts::MatrixFlatAssembler
+ * (ikarus/utils/concepts.hh:517-585) with the semantics of FlatAssemblerBase / ScalarAssembler /
+ * VectorAssembler / MatrixAssembler (ikarus/assembler/interface.hh:28-468) and SparseFlatAssembler
+ * (ikarus/assembler/simpleassemblers.hh:106-177), but every get*Impl is one call into libikb200.so
+ * (include/ikb200.h) instead of a serial loop over finite elements.
+ *
+ * Two build modes:
+ *   - with Ikarus/DUNE/Eigen on the include path (IKB_HAVE_IKARUS, auto-detected): VectorType is
+ *     Eigen::VectorXd, MatrixType is Eigen::SparseMatrix<double> ("mirror mode": the device writes the
+ *     values in Eigen's compressed order and they are copied into valuePtr()), exceptions are Dune's,
+ *     and the element walk uses FEHelper::globalIndices / geometry().corner().  NewtonRaphson,
+ *     TrustRegion and LoadControl then drive this class unchanged.
+ *   - standalone (this repository, no DUNE in the image): the same class over the small value types of
+ *     ikarus_b200/hosttypes.hh, used by tests/cpp.
+ * The element container is adapted through ElementAccess<FE> (customisation point below).
+ */
+#pragma once
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../ikb200.h"
+#include "hosttypes.hh"
+
+namespace Ikarus::B200 {
+
+/** Thrown where the reference throws Dune::InvalidStateException / Dune::NotImplemented. */
+#if IKB_HAVE_IKARUS
+using InvalidState   = Dune::InvalidStateException;
+using NotImplemented = Dune::NotImplemented;
+  #define IKB_THROW(Type, msg) DUNE_THROW(Type, msg)
+#else
+struct InvalidState : std::logic_error
+{
+  using std::logic_error::logic_error;
+};
+struct NotImplemented : std::logic_error
+{
+  using std::logic_error::logic_error;
+};
+  #define IKB_THROW(Type, msg) throw Type(std::string(msg))
+#endif
+/** The reference aborts the process on det C <= 0 (materials/materialhelpers.hh:120-126); here it is an exception. */
+struct MaterialFailure : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+/**
+ * \brief Customisation point: how to read one finite element.  Specialise for your FE type, or provide the
+ * members used by the primary template (the standalone HostFE of hosttypes.hh does).
+ */
+template <typename FE>
+struct ElementAccess
+{
+  static int dim(const FE& fe) { return fe.dim; }
+  static int order(const FE& fe) { return fe.order; }
+  static int strain(const FE& fe) { return fe.strain; }      // IKB_STRAIN_*
+  static int material(const FE& fe) { return fe.material; }  // IKB_MAT_*
+  static bool planeStrain(const FE& fe) { return fe.planeStrain; }
+  static double lambda(const FE& fe) { return fe.lambda; }
+  static double mu(const FE& fe) { return fe.mu; }
+  static int numberOfInternalVariables(const FE& fe) { return fe.easM; }
+  /** FEHelper::globalIndices(fe, dofs) (finiteelements/fehelper.hh:194-197), flat index [0] */
+  static void globalIndices(const FE& fe, std::vector<std::int64_t>& dofs) {
+    dofs.insert(dofs.end(), fe.dofs.begin(), fe.dofs.end());
+  }
+  /** fe.gridElement().geometry().corner(c)[k], c-major */
+  static void corners(const FE& fe, std::vector<double>& x) { x.insert(x.end(), fe.corners.begin(), fe.corners.end()); }
+};
+
+#if IKB_HAVE_IKARUS
+/** Adapter for real Ikarus finite elements FE<PreFE, Skills...> (finiteelements/mixin.hh, febase.hh). */
+template <typename FE>
+requires requires(const FE& fe) { fe.localView(); fe.material(); }
+struct ElementAccess<FE>
+{
+  static int dim(const FE&) { return FE::Traits::mydim; }
+  static int order(const FE& fe) { return fe.order(); }
+  static int strain(const FE&) {
+    return FE::Material::strainTag == Ikarus::StrainTags::linear ? IKB_STRAIN_LINEAR : IKB_STRAIN_GREEN_LAGRANGE;
+  }
+  static int material(const FE& fe) {
+    const std::string n = fe.material().name();
+    if (n.find("NeoHooke") != std::string::npos) return IKB_MAT_NEOHOOKE;
+    if (n.find("StVenantKirchhoff") != std::string::npos) return IKB_MAT_SVK;
+    if (n.find("LinearElasticity") != std::string::npos) return IKB_MAT_LINEAR_ELASTICITY;
+    IKB_THROW(NotImplemented, "material " + n + " is outside the device hot path");
+  }
+  static bool planeStrain(const FE&) { return FE::Material::isReduced; }
+  static double lambda(const FE& fe) { return fe.material().materialParameters().lambda; }
+  static double mu(const FE& fe) { return fe.material().materialParameters().mu; }
+  static int numberOfInternalVariables(const FE& fe) {
+    if constexpr (requires { fe.numberOfInternalVariables(); })
+      return fe.numberOfInternalVariables();
+    else
+      return 0;
+  }
+  static void globalIndices(const FE& fe, std::vector<std::int64_t>& dofs) {
+    std::vector<typename FE::GlobalIndex> ids;
+    Ikarus::FEHelper::globalIndices(fe, ids);
+    for (auto& id : ids)
+      dofs.push_back(static_cast<std::int64_t>(id[0]));
+  }
+  static void corners(const FE& fe, std::vector<double>& x) {
+    const auto geo = fe.gridElement().geometry();
+    for (int c = 0; c < geo.corners(); ++c)
+      for (int k = 0; k < FE::Traits::worlddim; ++k)
+        x.push_back(geo.corner(c)[k]);
+  }
+};
+#endif
+
+/**
+ * \brief Device matrix handle: what DeviceSparseFlatAssembler::deviceMatrix() returns; the JacobianType when
+ * NewtonRaphson runs in resident mode (matrix() may return any type, utils/concepts.hh:575-585).
+ */
+struct DeviceMatrixHandle
+{
+  ikb_handle handle{nullptr};
+  int dbc{IKB_DBC_FULL};
+  std::int64_t rows{0};
+};
+
+template <typename FEC, typename DV>
+class DeviceSparseFlatAssembler
+{
+public:
+  using FEContainer              = FEC;
+  using FE                       = std::remove_cvref_t<decltype(*std::begin(std::declval<FEC&>()))>;
+  using FERequirement            = HostTraits::template Requirement<FE>;
+  using DirichletValuesType      = DV;
+  using SizeType                 = std::size_t;
+  using AffordanceCollectionType = HostTraits::AffordanceCollection;
+  using ScalarType               = double;
+  using VectorType               = HostTraits::Vector;
+  using MatrixType               = HostTraits::SparseMatrix;
+  using DBCOption                = HostTraits::DBCOption;
+
+  /** FlatAssemblerBase ctor (assembler/interface.hh:51-62) + one-time device upload. */
+  DeviceSparseFlatAssembler(FEC&& fes, const DV& dirichletValues, int device = -1)
+      : fes_{std::forward<FEC>(fes)},
+        dirichletValues_{dirichletValues} {
+    const std::size_t n = dirichletValues_.size();
+    constraintsBelow_.reserve(n);
+    std::size_t counter = 0;
+    std::vector<std::uint8_t> flags(n);
+    for (std::size_t i = 0; i < n; ++i) {
+      constraintsBelow_.push_back(counter);
+      if (dirichletValues_.isConstrained(i)) {
+        ++counter;
+        flags[i] = 1;
+      }
+    }
+    fixedDofs_ = dirichletValues_.fixedDOFsize();
+
+    // single walk over the container: connectivity + corner coordinates
+    std::vector<std::int64_t> dofs;
+    std::vector<double> corners;
+    std::int64_t nElem = 0;
+    ikb_desc desc{};
+    desc.abi_version = IKB_ABI_VERSION;
+    for (const auto& fe : fes_) {
+      using A = ElementAccess<FE>;
+      if (nElem == 0) {
+        desc.dim          = A::dim(fe);
+        desc.order        = A::order(fe);
+        desc.strain       = A::strain(fe);
+        desc.material     = A::material(fe);
+        desc.plane_strain = A::planeStrain(fe) ? 1 : 0;
+        desc.eas_m        = A::numberOfInternalVariables(fe);
+        desc.lambda       = A::lambda(fe);
+        desc.mu           = A::mu(fe);
+      }
+      A::globalIndices(fe, dofs);
+      A::corners(fe, corners);
+      ++nElem;
+    }
+    desc.device = device;
+    desc.n_elem = nElem;
+    desc.n_dof  = static_cast<std::int64_t>(n);
+    const int rc = ikb_create(&h_, &desc);
+    if (rc == IKB_ENOTIMPL)
+      IKB_THROW(NotImplemented, "EAS is only supported for Q1, Q2 and H1 elements");
+    if (rc != IKB_OK)
+      IKB_THROW(InvalidState, "ikb_create failed (" + std::to_string(rc) + "): unsupported element description");
+    check(ikb_upload_mesh(h_, corners.data(), dofs.data()));
+    check(ikb_upload_dirichlet(h_, flags.data()));
+    check(ikb_build_pattern(h_));
+  }
+  ~DeviceSparseFlatAssembler() {
+    if (h_)
+      ikb_destroy(h_);
+  }
+  DeviceSparseFlatAssembler(const DeviceSparseFlatAssembler&)            = delete;
+  DeviceSparseFlatAssembler& operator=(const DeviceSparseFlatAssembler&) = delete;
+
+  // ---- FlatAssemblerBase (assembler/interface.hh:68-132) ------------------------------------------
+  std::size_t size() const { return dirichletValues_.size(); }
+  std::size_t reducedSize() const { return size() - fixedDofs_; }
+  auto& finiteElements() const { return fes_; }
+  const auto& dirichletValues() const { return dirichletValues_; }
+  std::size_t constraintsBelow(std::size_t i) const { return constraintsBelow_[i]; }
+  bool isConstrained(std::size_t i) const { return dirichletValues_.isConstrained(i); }
+  std::size_t estimateOfConnectivity() const { return fes_.size() * 8; }
+
+  VectorType createFullVector(const VectorType& reducedVector) const {
+    assert(static_cast<std::size_t>(reducedVector.size()) == reducedSize() &&
+           "The reduced vector you passed has the wrong dimensions.");
+    VectorType full(size());
+    std::size_t reducedCounter = 0;
+    for (std::size_t i = 0; i < size(); ++i) {
+      if (isConstrained(i)) {
+        ++reducedCounter;
+        full[i] = 0.0;
+      } else
+        full[i] = reducedVector[i - reducedCounter];
+    }
+    return full;
+  }
+  VectorType createReducedVector(const VectorType& fullVector) const {
+    assert(static_cast<std::size_t>(fullVector.size()) == size() &&
+           "The full vector you passed has the wrong dimensions.");
+    VectorType red(reducedSize());
+    std::size_t reducedCounter = 0;
+    for (std::size_t i = 0; i < size(); ++i) {
+      if (isConstrained(i))
+        ++reducedCounter;
+      else
+        red[i - reducedCounter] = fullVector[i];
+    }
+    return red;
+  }
+
+  // ---- binding (assembler/interface.hh:150-256) ----------------------------------------------------
+  void bind(const FERequirement& req, AffordanceCollectionType aff, DBCOption dbc = DBCOption::Full) {
+    req_ = std::cref(req);
+    aff_ = aff;
+    dbc_ = dbc;
+  }
+  void bind(const FERequirement& req) { req_ = std::cref(req); }
+  void bind(AffordanceCollectionType aff) { aff_ = aff; }
+  void bind(DBCOption dbc) { dbc_ = dbc; }
+  bool bound() const { return boundToRequirement() and boundToAffordanceCollection() and boundToDBCOption(); }
+  bool boundToRequirement() const { return req_.has_value(); }
+  bool boundToAffordanceCollection() const { return aff_.has_value(); }
+  bool boundToDBCOption() const { return dbc_.has_value(); }
+  const FERequirement& requirement() const {
+    if (req_.has_value())
+      return req_.value().get();
+    IKB_THROW(InvalidState, "The requirement can only be obtained after binding");
+  }
+  AffordanceCollectionType affordanceCollection() const {
+    if (aff_.has_value())
+      return aff_.value();
+    IKB_THROW(InvalidState, "The affordance can only be obtained after binding");
+  }
+  DBCOption dBCOption() const {
+    if (dbc_.has_value())
+      return dbc_.value();
+    IKB_THROW(InvalidState, "The dBCOption can only be obtained after binding");
+  }
+
+  // ---- ScalarAssembler / VectorAssembler / MatrixAssembler (interface.hh:300-462) -----------------
+  const ScalarType& scalar(const FERequirement& req, HostTraits::ScalarAffordance aff) {
+    if (aff != HostTraits::ScalarAffordance::mechanicalPotentialEnergy)
+      IKB_THROW(NotImplemented, "ScalarAffordance not implemented");
+    push(req);
+    check(ikb_assemble(h_, IKB_SCALAR, IKB_DBC_RAW));
+    check(ikb_get_scalar(h_, &scal_));
+    return scal_;
+  }
+  const ScalarType& scalar() { return scalar(requirement(), affordanceCollection().scalarAffordance()); }
+
+  const VectorType& vector(const FERequirement& req, HostTraits::VectorAffordance aff,
+                           DBCOption dbc = DBCOption::Full) {
+    if (aff != HostTraits::VectorAffordance::forces)
+      IKB_THROW(NotImplemented, "VectorAffordance not implemented");
+    push(req);
+    const int d = toCode(dbc);
+    // K and R leave the same fused sweep; the matrix call that follows in every Newton iteration
+    // (solver/nonlinearsolver/newtonraphson.hh:242-243) is then served from the device cache.
+    check(ikb_assemble(h_, IKB_VECTOR | IKB_MATRIX, d));
+    VectorType& out = vec_[d];
+    out.resize(dbc == DBCOption::Reduced ? reducedSize() : size());
+    check(ikb_get_vector(h_, d, out.data()));
+    return out;
+  }
+  const VectorType& vector(DBCOption dbc) { return vector(requirement(), affordanceCollection().vectorAffordance(), dbc); }
+  const VectorType& vector() { return vector(dBCOption()); }
+
+  const MatrixType& matrix(const FERequirement& req, HostTraits::MatrixAffordance aff,
+                           DBCOption dbc = DBCOption::Full) {
+    if (aff != HostTraits::MatrixAffordance::stiffness)
+      IKB_THROW(NotImplemented, "MatrixAffordance not implemented");
+    push(req);
+    const int d = toCode(dbc);
+    check(ikb_assemble(h_, IKB_MATRIX | IKB_VECTOR, d));
+    MatrixType& A = mat_[d];
+    if (not patternReady_[d]) {  // preProcessSparseMatrix(Reduced) (simpleassemblers.inl:289-299)
+      std::int64_t rows = 0, nnz = 0;
+      check(ikb_pattern_nnz(h_, d, &rows, &nnz));
+      std::vector<std::int64_t> outer(rows + 1);
+      std::vector<std::int32_t> inner(nnz);
+      check(ikb_get_pattern(h_, d, outer.data(), inner.data()));
+      HostTraits::setPattern(A, rows, outer, inner);
+      patternReady_[d] = true;
+    }
+    check(ikb_get_matrix_values(h_, d, HostTraits::valuePtr(A)));
+    return A;
+  }
+  const MatrixType& matrix(DBCOption dbc) { return matrix(requirement(), affordanceCollection().matrixAffordance(), dbc); }
+  const MatrixType& matrix() { return matrix(dBCOption()); }
+
+  // ---- resident mode ---------------------------------------------------------------------------------
+  /** Assemble on the device and return a handle instead of mirroring K to the host. */
+  DeviceMatrixHandle deviceMatrix(const FERequirement& req, DBCOption dbc = DBCOption::Full) {
+    push(req);
+    check(ikb_assemble(h_, IKB_MATRIX | IKB_VECTOR, toCode(dbc)));
+    return {h_, toCode(dbc), static_cast<std::int64_t>(dbc == DBCOption::Reduced ? reducedSize() : size())};
+  }
+  /** Jacobi-PCG on the device for the currently assembled matrix: returns K^-1 rhs (host vector). */
+  VectorType solve(DBCOption dbc, const VectorType& rhs, double relTol = 1e-13, int maxIt = -1, int* iterations = nullptr) {
+    VectorType x(rhs.size());
+    int it = 0;
+    double rel = 0;
+    check(ikb_pcg_solve(h_, toCode(dbc), rhs.data(), x.data(), relTol, maxIt < 0 ? 2 * static_cast<int>(rhs.size()) : maxIt,
+                        &it, &rel));
+    if (iterations)
+      *iterations = it;
+    return x;
+  }
+
+  // ---- EAS state (mechanics/enhancedassumedstrains.hh:225-248, 350-359) -----------------------------
+  /** One call replaces the per-element CORRECTION_UPDATED subscriptions (controlroutinefactory.hh:43-46). */
+  void updateInternalVariables(const FERequirement& req, const VectorType& correction) {
+    if (static_cast<std::size_t>(correction.size()) != size())
+      IKB_THROW(NotImplemented,
+                "Solution vector and correction vector should be of the same size. Check if DBCOption::Full is used.");
+    push(req);
+    check(ikb_eas_update(h_, correction.data()));
+  }
+#if IKB_HAVE_IKARUS
+  /** Register ONE listener on a nonlinear solver / broadcaster for CORRECTION_UPDATED. */
+  template <typename BC>
+  auto subscribeTo(BC& bc) {
+    using NLSState = typename BC::State;
+    return bc.template station<Ikarus::NonLinearSolverMessages>().registerListener(
+        [this](Ikarus::NonLinearSolverMessages message, const NLSState& state) {
+          if (message == Ikarus::NonLinearSolverMessages::CORRECTION_UPDATED)
+            this->updateInternalVariables(state.domain, state.correction);
+        });
+  }
+#endif
+  /** lambda-proportional external nodal loads sampled on the host (loads/volume.hh, loads/traction.hh). */
+  void setExternalLoad(const VectorType& fext, bool scalesWithLambda = true) {
+    check(ikb_set_external_load(h_, fext.data(), scalesWithLambda ? 1 : 0));
+  }
+  ikb_handle handle() const { return h_; }
+
+private:
+  static int toCode(DBCOption dbc) {
+    return dbc == DBCOption::Raw ? IKB_DBC_RAW : (dbc == DBCOption::Reduced ? IKB_DBC_REDUCED : IKB_DBC_FULL);
+  }
+  void push(const FERequirement& req) {
+    const auto& d = req.globalSolution();
+    assert(static_cast<std::size_t>(d.size()) == size());
+    check(ikb_set_solution(h_, d.data()));
+    check(ikb_set_parameter(h_, req.parameter()));
+  }
+  void check(int rc) const {
+    if (rc == IKB_OK)
+      return;
+    char buf[512];
+    ikb_last_error(h_, buf, sizeof(buf));
+    if (rc == IKB_EMATERIAL)
+      throw MaterialFailure(buf);
+    if (rc == IKB_ENOTIMPL)
+      IKB_THROW(NotImplemented, buf);
+    IKB_THROW(InvalidState, std::string("libikb200: ") + buf);
+  }
+
+  FEC fes_;
+  DV dirichletValues_;  // copied like in the reference (interface.hh:260)
+  std::optional<std::reference_wrapper<const FERequirement>> req_;
+  std::optional<AffordanceCollectionType> aff_;
+  std::optional<DBCOption> dbc_;
+  std::vector<std::size_t> constraintsBelow_;
+  std::size_t fixedDofs_{};
+  ikb_handle h_{nullptr};
+  ScalarType scal_{0.0};
+  VectorType vec_[3];
+  MatrixType mat_[3];
+  bool patternReady_[3]{false, false, false};
+};
+
+/** makeSparseFlatAssembler analogue (assembler/simpleassemblers.hh:174-177). */
+template <typename FEC, typename DV>
+auto makeDeviceSparseFlatAssembler(FEC&& fes, const DV& dirichletValues, int device = -1) {
+  return std::make_shared<DeviceSparseFlatAssembler<FEC, DV>>(std::forward<FEC>(fes), dirichletValues, device);
+}
+
+/**
+ * \brief Linear-solver callable for NewtonRaphson: `correction_ = -linearSolver_(rx, Ax)`
+ * (solver/nonlinearsolver/newtonraphson.hh:152, 221-226).  Runs Jacobi-PCG on the device on the matrix the
+ * assembler holds; Ax is only used for its type.  The analogue of SolverTypeTag::si_ConjugateGradient.
+ */
+template <typename Assembler>
+struct DevicePCG
+{
+  std::shared_ptr<Assembler> assembler;
+  double relTol{1e-13};
+  int maxIt{-1};
+  mutable int lastIterations{0};
+  template <typename R, typename K>
+  auto operator()(const R& rx, const K&) const {
+    return assembler->solve(assembler->dBCOption(), rx, relTol, maxIt, &lastIterations);
+  }
+};
+
+} // namespace Ikarus::B200

@@ -1,0 +1,153 @@
+// Standalone C++ test of the header-only drop-in wrapper over the C-ABI.
+//   build: g++ -std=c++20 -I include tests/cpp/test_deviceflatassembler.cpp -L ikarus_b200 -likb200 -Wl,-rpath,...
+// Mode "compile" (no GPU): checks the error path of ikb_create through the wrapper.
+// Mode "run" (GPU): 2x2x2 Hex8 NeoHooke cantilever: bind, matrix/vector/scalar in the three DBC modes, invariants
+// of tests/src/testassembler.cpp:122-201 of the reference, Newton with the device PCG callable.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include <ikarus_b200/deviceflatassembler.hh>
+
+using namespace Ikarus::B200;
+
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      std::printf("CHECK failed at line %d: %s\n", __LINE__, #cond);       \
+      return 1;                                                            \
+    }                                                                      \
+  } while (0)
+
+static std::vector<HostFE> makeMesh(int nx, int ny, int nz, double h, int material, int strain, int easM) {
+  std::vector<HostFE> fes;
+  const double E = 1000, nu = 0.3;
+  const double lam = E * nu / ((1 + nu) * (1 - 2 * nu)), mu = E / (2 * (1 + nu));
+  auto node = [&](int i, int j, int k) { return (std::int64_t)i + (nx + 1) * ((std::int64_t)j + (ny + 1) * (std::int64_t)k); };
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        HostFE fe;
+        fe.material = material;
+        fe.strain   = strain;
+        fe.easM     = easM;
+        fe.lambda   = lam;
+        fe.mu       = mu;
+        for (int a = 0; a < 8; ++a) {
+          const int ii = i + (a & 1), jj = j + ((a >> 1) & 1), kk = k + ((a >> 2) & 1);
+          for (int c = 0; c < 3; ++c)
+            fe.dofs.push_back(3 * node(ii, jj, kk) + c);
+          fe.corners.push_back(ii * h);
+          fe.corners.push_back(jj * h);
+          fe.corners.push_back(kk * h);
+        }
+        fes.push_back(fe);
+      }
+  return fes;
+}
+
+int main(int argc, char** argv) {
+  const bool run = argc > 1 && std::strcmp(argv[1], "run") == 0;
+  {
+    // unsupported EAS variant must surface as NotImplemented like in the reference
+    std::vector<HostFE> fes = makeMesh(1, 1, 1, 1.0, IKB_MAT_NEOHOOKE, IKB_STRAIN_GREEN_LAGRANGE, 11);
+    HostDirichletValues dv(24);
+    bool thrown = false;
+    try {
+      auto a = makeDeviceSparseFlatAssembler(fes, dv);
+    } catch (const NotImplemented&) {
+      thrown = true;
+    } catch (const InvalidState&) {
+      thrown = !run;  // without a GPU the CUDA runtime may fail first
+    }
+    CHECK(thrown);
+  }
+  if (!run) {
+    std::printf("compile-mode ok\n");
+    return 0;
+  }
+  const int nx = 4, ny = 2, nz = 2;
+  auto fes = makeMesh(nx, ny, nz, 0.5, IKB_MAT_NEOHOOKE, IKB_STRAIN_GREEN_LAGRANGE, 0);
+  const std::size_t n = 3 * (nx + 1) * (ny + 1) * (nz + 1);
+  HostDirichletValues dv(n);
+  for (int k = 0; k <= nz; ++k)
+    for (int j = 0; j <= ny; ++j)
+      for (int c = 0; c < 3; ++c)
+        dv.setSingleDOF(3 * ((nx + 1) * (j + (ny + 1) * k)) + c);
+  auto asmb = makeDeviceSparseFlatAssembler(fes, dv);
+  using A   = std::remove_cvref_t<decltype(*asmb)>;
+  CHECK(asmb->size() == n && asmb->reducedSize() == n - dv.fixedDOFsize());
+  bool unbound = false;
+  try {
+    asmb->requirement();
+  } catch (const InvalidState&) {
+    unbound = true;
+  }
+  CHECK(unbound);
+
+  HostRequirement req;
+  req.d.assign(n, 0.0);
+  for (std::size_t i = 0; i < n; ++i)
+    req.d[i] = dv.isConstrained(i) ? 0.0 : 1e-3 * std::sin(0.37 * i);
+  std::vector<double> fext(n, 0.0);
+  fext[n - 1] = -1.0;
+  asmb->setExternalLoad(fext);
+  req.lambda = 0.5;
+  asmb->bind(req, elastoStatics, DBCOption::Full);
+  CHECK(asmb->bound() && &asmb->requirement() == &req);
+
+  const auto& Kraw  = asmb->matrix(DBCOption::Raw);
+  const auto& Kfull = asmb->matrix(DBCOption::Full);
+  const auto& Kred  = asmb->matrix(DBCOption::Reduced);
+  const auto& Rfull = asmb->vector(DBCOption::Full);
+  const auto& Rred  = asmb->vector(DBCOption::Reduced);
+  CHECK(Kraw.rows() == (std::int64_t)n && Kred.rows() == (std::int64_t)asmb->reducedSize());
+  CHECK(Kraw.nonZeros() == Kfull.nonZeros());
+  for (std::size_t i = 0; i < n; ++i) {
+    if (!dv.isConstrained(i))
+      continue;
+    CHECK(Kfull.coeff(i, i) == 1.0 && Rfull[i] == 0.0);
+    for (std::int64_t p = Kfull.outer[i]; p < Kfull.outer[i + 1]; ++p)
+      CHECK(Kfull.inner[p] == (std::int32_t)i || Kfull.values[p] == 0.0);
+  }
+  // Reduced == Raw with fixed rows/cols removed (testassembler.cpp:185-201)
+  for (std::size_t c = 0; c < n; ++c) {
+    if (dv.isConstrained(c))
+      continue;
+    for (std::int64_t p = Kraw.outer[c]; p < Kraw.outer[c + 1]; ++p) {
+      const std::size_t r = Kraw.inner[p];
+      if (dv.isConstrained(r))
+        continue;
+      CHECK(Kred.coeff(r - asmb->constraintsBelow(r), c - asmb->constraintsBelow(c)) == Kraw.values[p]);
+    }
+  }
+  auto full = asmb->createFullVector(Rred);
+  auto back = asmb->createReducedVector(full);
+  CHECK(back == Rred);
+  const double E0 = asmb->scalar();
+  CHECK(std::isfinite(E0));
+
+  // Newton iteration with the device PCG callable, as NewtonRaphson::solve does (newtonraphson.hh:196-257)
+  DevicePCG<A> ls{asmb, 1e-13};
+  double rnorm = 0;
+  int iter = 0;
+  for (; iter < 20; ++iter) {
+    const auto& rx = asmb->vector();
+    const auto& Ax = asmb->matrix();
+    rnorm          = 0;
+    for (double v : rx)
+      rnorm += v * v;
+    rnorm = std::sqrt(rnorm);
+    if (rnorm <= 1e-10)
+      break;
+    auto corr = ls(rx, Ax);
+    CHECK(ls.lastIterations > 0);
+    for (std::size_t i = 0; i < n; ++i)
+      req.d[i] -= corr[i];
+  }
+  CHECK(rnorm <= 1e-10 && iter > 1 && iter < 10);
+  std::printf("run-mode ok: Newton converged in %d iterations, |R| = %.3e\n", iter, rnorm);
+  return 0;
+}
