@@ -54,6 +54,8 @@ SYMBOLS = {
     "ikb_set_row_ownership": [C.c_void_p, C.c_int64, C.c_int64],
     "ikb_nccl_unique_id": [C.c_void_p],
     "ikb_comm_init": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+    "ikb_halo_intervals": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "ikb_halo_exchange": [C.c_void_p, C.c_char_p],
     "ikb_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
     "ikb_sync": [C.c_void_p],
     "ikb_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "ikb_dist.cuh"
 #include "ikb_elem_eas.cuh"
 #include "ikb_elem_q1.cuh"
 #include "ikb_elem_q2.cuh"
@@ -259,6 +260,112 @@ int launchSpmv(Handle* h, int dbc, const double* x, double* y) {
   return IKB_OK;
 }
 
+int haloExchange(Handle* h, double* v) {
+  if (!h->comm || h->nranks == 1) return IKB_OK;
+  const int D = h->dim;
+  const int64_t* me = h->peerRanges.data() + 4 * h->rank;
+  int rc = nccl().groupStart();
+  for (int s = 0; s < h->nranks && rc == 0; ++s) {
+    if (s == h->rank) continue;
+    const int64_t* pr = h->peerRanges.data() + 4 * s;
+    int64_t sb, se, rb, re;
+    haloIntervals(me[0], me[1], me[2], me[3], pr[0], pr[1], pr[2], pr[3], sb, se, rb, re);
+    if (se > sb) rc = nccl().send(v + D * sb, (size_t)D * (se - sb), NCCL_FLOAT64, s, h->comm, h->stream);
+    if (rc == 0 && re > rb) rc = nccl().recv(v + D * rb, (size_t)D * (re - rb), NCCL_FLOAT64, s, h->comm, h->stream);
+  }
+  const int rc2 = nccl().groupEnd();
+  if (rc != 0 || rc2 != 0) return fail(h, IKB_ENCCL, std::string("halo exchange: ") + nccl().errorString(rc ? rc : rc2));
+  h->launches++;
+  return IKB_OK;
+}
+
+int allReduceSum(Handle* h, double* devScalars, int count) {
+  if (!h->comm || h->nranks == 1) return IKB_OK;
+  const int rc = nccl().allReduce(devScalars, devScalars, (size_t)count, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+  if (rc != 0) return fail(h, IKB_ENCCL, std::string("ncclAllReduce: ") + nccl().errorString(rc));
+  h->launches++;
+  return IKB_OK;
+}
+
+// Jacobi-PCG over row blocks: halo exchange of the search direction before every SpMV, one all-reduce
+// for p.q and one for (r.z, r.r) per iteration.  Full mode only.
+int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int maxIt, int* itersOut,
+            double* relResOut) {
+  const int dbc = IKB_DBC_FULL;
+  const int64_t n = h->nRowsLocal();
+  const int64_t off = h->rowBegin * h->dim;
+  const int tpb = 256;
+  for (auto* b : {&h->cgR, &h->cgZ, &h->cgQ, &h->cgX, &h->cgDinv})
+    if (b->n < (size_t)std::max<int64_t>(n, 1)) IKB_CUDA(h, b->alloc((size_t)std::max<int64_t>(n, 1)));
+  if (h->cgPglob.n < (size_t)h->nDof) {
+    IKB_CUDA(h, h->cgPglob.alloc((size_t)h->nDof));
+    IKB_CUDA(h, cudaMemsetAsync(h->cgPglob.p, 0, h->cgPglob.bytes(), h->stream));
+  }
+  if (h->Corr.n < (size_t)h->nDof) IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
+  IKB_CUDA(h, cudaMemsetAsync(h->Corr.p, 0, h->Corr.bytes(), h->stream));
+  double* p = h->cgPglob.p + off;
+  int rc;
+  if (rhsHost) {
+    IKB_CUDA(h, cudaMemcpyAsync(h->cgR.p, rhsHost, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "resident residual not assembled");
+    vec_scale_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, -1.0, h->vec[dbc].p, h->cgR.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  IKB_CUDA(h, cudaMemsetAsync(h->cgX.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), h->stream));
+  if (h->nBlocks) {
+    if (h->dim == 3)
+      diag_inv_block_kernel<3><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+    else
+      diag_inv_block_kernel<2><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  double* scal = h->cgScal.p;
+  vec_mul_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, h->cgDinv.p, h->cgR.p, h->cgZ.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, cudaMemcpyAsync(p, h->cgZ.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = deviceDot(h, 1, h->cgR.p, h->cgZ.p, n, scal + 0, 1.0, nullptr))) return rc;
+  if ((rc = deviceDot(h, 2, h->cgR.p, nullptr, n, scal + 4, 1.0, nullptr))) return rc;
+  if ((rc = allReduceSum(h, scal + 0, 1))) return rc;
+  if ((rc = allReduceSum(h, scal + 4, 1))) return rc;
+  double bb = 0.0;
+  IKB_CUDA(h, cudaMemcpyAsync(&bb, scal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int it = 0;
+  double rr = bb;
+  const double threshold = std::max(relTol * relTol * bb, 1e-300);
+  if (bb > 0.0) {
+    while (it < maxIt && rr >= threshold) {
+      if ((rc = haloExchange(h, h->cgPglob.p))) return rc;
+      if ((rc = launchSpmv(h, dbc, h->cgPglob.p, h->cgQ.p))) return rc;
+      if ((rc = deviceDot(h, 1, p, h->cgQ.p, n, scal + 1, 1.0, nullptr))) return rc;
+      if ((rc = allReduceSum(h, scal + 1, 1))) return rc;
+      cg_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, p, h->cgQ.p, h->cgDinv.p, h->cgX.p, h->cgR.p,
+                                                          h->cgZ.p, h->scratch.p + 2 * RED_BLOCKS);
+      IKB_LAUNCH_CHECK(h);
+      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(h->scratch.p + 2 * RED_BLOCKS, RED_BLOCKS, scal, nullptr);
+      IKB_LAUNCH_CHECK(h);
+      if ((rc = allReduceSum(h, scal + 2, 2))) return rc;
+      IKB_CUDA(h, cudaMemcpyAsync(h->hostScal, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      cg_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgZ.p, p);
+      IKB_LAUNCH_CHECK(h);
+      cg_shift_kernel<<<1, 1, 0, h->stream>>>(scal);
+      IKB_LAUNCH_CHECK(h);
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      rr = h->hostScal[0];
+      ++it;
+      if (!(rr == rr)) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
+    }
+  }
+  if (itersOut) *itersOut = it;
+  if (relResOut) *relResOut = bb > 0.0 ? std::sqrt(rr / bb) : 0.0;
+  IKB_CUDA(h, cudaMemcpyAsync(h->Corr.p + off, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = haloExchange(h, h->Corr.p))) return rc;
+  if (xHost) IKB_CUDA(h, cudaMemcpyAsync(xHost, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -351,6 +458,9 @@ int ikb_destroy(ikb_handle hh) {
   h->redInner.release();
   h->redOuter.release();
   h->errFlag.release();
+  if (h->comm) nccl().commDestroy(h->comm);
+  h->cgPglob.release();
+  h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->stream2);
@@ -409,6 +519,15 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
       en[(size_t)a * ne + e] = (int32_t)node;
     }
   if (!ok) return fail(h, IKB_EINVAL, "inconsistent element dof indices");
+  {
+    int32_t mn = INT32_MAX, mx = -1;
+    for (int32_t v : en) {
+      mn = std::min(mn, v);
+      mx = std::max(mx, v);
+    }
+    h->colBegin = mn;
+    h->colEnd = (int64_t)mx + 1;
+  }
   std::vector<double> xs((size_t)nc * D * ne);
   for (int64_t e = 0; e < ne; ++e)
     for (int q = 0; q < nc * D; ++q) xs[(size_t)q * ne + e] = corner[(size_t)e * nc * D + q];
@@ -803,7 +922,23 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
       if ((rc = deviceDot(h, 1, h->Fext.p, h->U.p, h->nDof, lDev, -(h->fextScales ? h->lambda : 1.0), nullptr)))
         return rc;
     }
-    if ((rc = deviceDot(h, 0, h->Est.p, nullptr, h->nElem, eDev, 1.0, h->hasFext ? lDev : nullptr))) return rc;
+    const bool partitioned = h->rowBegin != 0 || h->rowEnd != h->nNodes;
+    if (partitioned && h->nElem) {
+      mask_unowned_energy_kernel<<<gridFor(h->nElem, 256), 256, 0, h->stream>>>(h->elemNode.p, h->nElem, h->rowBegin,
+                                                                                h->rowEnd, h->Est.p);
+      IKB_LAUNCH_CHECK(h);
+      h->stagedWhat &= ~IKB_SCALAR;  // Est was modified in place
+    }
+    // with a communicator every rank holds the full d and fext, so the load term is added once, after the reduction
+    if ((rc = deviceDot(h, 0, h->Est.p, nullptr, h->nElem, eDev, 1.0, (h->hasFext && !h->comm) ? lDev : nullptr)))
+      return rc;
+    if (h->comm) {
+      if ((rc = allReduceSum(h, eDev, 1))) return rc;
+      if (h->hasFext) {
+        vec_axpy_kernel<<<1, 1, 0, h->stream>>>(1, 1.0, lDev, eDev);
+        IKB_LAUNCH_CHECK(h);
+      }
+    }
     h->energyVersion = h->stateVersion;
   }
   return IKB_OK;
@@ -890,6 +1025,7 @@ int ikb_vector_norm(ikb_handle hh, int dbc, double* norm) {
   const int64_t n = rowsOf(h, dbc);
   int rc = deviceDot(h, 2, h->vec[dbc].p, nullptr, n, h->cgScal.p + 10, 1.0, nullptr);
   if (rc) return rc;
+  if ((rc = allReduceSum(h, h->cgScal.p + 10, 1))) return rc;
   double s = 0.0;
   IKB_CUDA(h, cudaMemcpyAsync(&s, h->cgScal.p + 10, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   rc = checkMaterialError(h);
@@ -958,7 +1094,11 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
   if (checkHandle(h)) return IKB_EINVAL;
   if (dbc != IKB_DBC_FULL && dbc != IKB_DBC_REDUCED) return fail(h, IKB_EINVAL, "PCG needs the Full or Reduced matrix");
   if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
-  if (h->rowBegin != 0 || h->rowEnd != h->nNodes) return fail(h, IKB_ENOTIMPL, "partitioned PCG: use the distributed driver");
+  if (h->rowBegin != 0 || h->rowEnd != h->nNodes || h->comm) {
+    if (!h->comm) return fail(h, IKB_ESTATE, "partitioned handle: call ikb_comm_init before solving");
+    if (dbc != IKB_DBC_FULL) return fail(h, IKB_ENOTIMPL, "distributed PCG supports DBCOption::Full");
+    return distPcg(h, rhs, x, relTol, maxIt, itersOut, relResOut);
+  }
   const int64_t n = rowsOf(h, dbc);
   if (itersOut) *itersOut = 0;
   if (relResOut) *relResOut = 0.0;
@@ -1066,8 +1206,68 @@ int ikb_update_solution(ikb_handle hh, int dbc, const double* correction) {
   return IKB_OK;
 }
 
-int ikb_nccl_unique_id(void*) { return IKB_ENOTIMPL; }
-int ikb_comm_init(ikb_handle hh, const void*, int, int) { return fail(H(hh), IKB_ENOTIMPL, "NCCL layer not built yet"); }
+int ikb_nccl_unique_id(void* id128) {
+  if (!id128) return IKB_EINVAL;
+  std::string err;
+  if (!nccl().load(err)) return IKB_ENCCL;
+  NcclId id;
+  if (nccl().getUniqueId(&id) != 0) return IKB_ENCCL;
+  std::memcpy(id128, id.internal, 128);
+  return IKB_OK;
+}
+
+int ikb_comm_init(ikb_handle hh, const void* id128, int rank, int nranks) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!id128 || rank < 0 || rank >= nranks) return fail(h, IKB_EINVAL, "bad communicator arguments");
+  if (!h->meshUploaded) return fail(h, IKB_ESTATE, "upload the mesh and set the row ownership first");
+  if (h->layout != LAYOUT_INTERLEAVED) return fail(h, IKB_ENOTIMPL, "row partitioning needs FlatInterleaved dofs");
+  std::string err;
+  if (!nccl().load(err)) return fail(h, IKB_ENCCL, err);
+  NcclId id;
+  std::memcpy(id.internal, id128, 128);
+  int rc = nccl().commInitRank(&h->comm, nranks, id, rank);
+  if (rc != 0) return fail(h, IKB_ENCCL, std::string("ncclCommInitRank: ") + nccl().errorString(rc));
+  h->rank = rank;
+  h->nranks = nranks;
+  // everybody learns everybody's owned rows and touched columns
+  DevBuf<int64_t> mine, all;
+  IKB_CUDA(h, mine.alloc(4));
+  IKB_CUDA(h, all.alloc((size_t)4 * nranks));
+  const int64_t r4[4] = {h->rowBegin, h->rowEnd, h->colBegin, h->colEnd};
+  IKB_CUDA(h, cudaMemcpyAsync(mine.p, r4, sizeof(r4), cudaMemcpyHostToDevice, h->stream));
+  rc = nccl().allGather(mine.p, all.p, 4, NCCL_INT64, h->comm, h->stream);
+  if (rc != 0) return fail(h, IKB_ENCCL, std::string("ncclAllGather: ") + nccl().errorString(rc));
+  h->peerRanges.assign((size_t)4 * nranks, 0);
+  IKB_CUDA(h, cudaMemcpyAsync(h->peerRanges.data(), all.p, all.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  mine.release();
+  all.release();
+  return IKB_OK;
+}
+
+int ikb_halo_intervals(const int64_t* mine4, const int64_t* peer4, int64_t* out4) {
+  if (!mine4 || !peer4 || !out4) return IKB_EINVAL;
+  haloIntervals(mine4[0], mine4[1], mine4[2], mine4[3], peer4[0], peer4[1], peer4[2], peer4[3], out4[0], out4[1], out4[2],
+                out4[3]);
+  return IKB_OK;
+}
+
+int ikb_halo_exchange(ikb_handle hh, const char* what) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!what) return fail(h, IKB_EINVAL, "null array name");
+  const std::string w(what);
+  double* v = nullptr;
+  if (w == "solution")
+    v = h->U.p;
+  else if (w == "correction")
+    v = h->Corr.p;
+  else
+    return fail(h, IKB_EINVAL, "unknown array");
+  if (!v) return fail(h, IKB_ESTATE, "array not allocated");
+  return haloExchange(h, v);
+}
 
 int ikb_stream(ikb_handle hh, void** s) {
   Handle* h = H(hh);

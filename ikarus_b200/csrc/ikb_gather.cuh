@@ -168,6 +168,13 @@ __global__ void __launch_bounds__(256) reduce_stage2(const double* __restrict__ 
   if (threadIdx.x == 0) out[0] = scale * sh[0] + (addend ? addend[0] : 0.0);
 }
 
+// element-partitioned runs: an element's energy counts on the rank that owns its first node
+__global__ void mask_unowned_energy_kernel(const int32_t* __restrict__ elemNode0, int64_t nElem, int64_t rowBegin,
+                                           int64_t rowEnd, double* Est) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nElem && (elemNode0[e] < rowBegin || elemNode0[e] >= rowEnd)) Est[e] = 0.0;
+}
+
 // dense mirror of a CSR matrix (DenseFlatAssembler, simpleassemblers.inl:301-375), column-major
 __global__ void csr_to_dense_kernel(const int64_t* __restrict__ outer, const int32_t* __restrict__ inner,
                                     const double* __restrict__ vals, int64_t rows, double* dense) {

@@ -126,9 +126,12 @@ struct Handle {
   DevBuf<double> cgScal;       // device scalars
   double* hostScal = nullptr;  // pinned
 
-  // NCCL
+  // NCCL (element-partitioned runs)
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  int64_t colBegin = 0, colEnd = 0;          // node range touched by the uploaded elements (owned + ghost)
+  std::vector<int64_t> peerRanges;           // [nranks][4] = ownBegin, ownEnd, needBegin, needEnd (nodes)
+  DevBuf<double> cgPglob;                    // search direction, global length (owned + halo filled)
 
   PatternView view() const {
     PatternView P;

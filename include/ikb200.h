@@ -150,6 +150,11 @@ int ikb_spmv(ikb_handle h, int dbc, const double* x, double* y);
 int ikb_set_row_ownership(ikb_handle h, int64_t node_begin, int64_t node_end);
 int ikb_nccl_unique_id(void* id128 /* 128 bytes */);
 int ikb_comm_init(ikb_handle h, const void* id128, int rank, int nranks);
+/* Pure host helper (no GPU needed): node intervals exchanged between two ranks of a contiguous row-block
+ * partition.  mine4/peer4 = {ownBegin, ownEnd, needBegin, needEnd}; out4 = {sendBegin, sendEnd, recvBegin, recvEnd}. */
+int ikb_halo_intervals(const int64_t* mine4, const int64_t* peer4, int64_t* out4);
+/* exchange the interface node layers of a global-length resident array ("solution" | "correction") */
+int ikb_halo_exchange(ikb_handle h, const char* what);
 
 /* ---- introspection for benchmarks ------------------------------------------------ */
 int ikb_stream(ikb_handle h, void** cuda_stream);
