@@ -251,10 +251,11 @@ int launchSpmv(Handle* h, int dbc, const double* x, double* y) {
     const PatternView P = h->view();
     const int64_t rows = P.nRowNodes * h->dim;
     if (rows == 0) return IKB_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>((P.nRowNodes + 7) / 8, 148 * 16);
     if (h->dim == 3)
-      spmv_block_kernel<3, 8><<<gridFor(rows * 8, tpb), tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y);
+      spmv_node_dot_kernel<3><<<grid, tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y, nullptr, nullptr, nullptr);
     else
-      spmv_block_kernel<2, 4><<<gridFor(rows * 4, tpb), tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y);
+      spmv_node_dot_kernel<2><<<grid, tpb, 0, h->stream>>>(P, h->vals[dbc].p, x, y, nullptr, nullptr, nullptr);
   }
   IKB_LAUNCH_CHECK(h);
   return IKB_OK;
@@ -460,6 +461,7 @@ int ikb_destroy(ikb_handle hh) {
   h->errFlag.release();
   if (h->comm) nccl().commDestroy(h->comm);
   h->cgPglob.release();
+  h->cgState.release();
   h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
   cudaStreamDestroy(h->stream);
@@ -1140,7 +1142,41 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
   double rr = bb;
   // Eigen's criterion: stop when |r|^2 < tol^2 |b|^2 (ConjugateGradient.h), x = 0 for b = 0
   const double threshold = std::max(relTol * relTol * bb, 1e-300);
-  if (bb > 0.0) {
+  if (bb > 0.0 && dbc == IKB_DBC_FULL) {
+    // sync-free path: 3 kernels per iteration, convergence decided on the device, the host looks at the state
+    // once per batch of iterations
+    if (!h->cgState.p) IKB_CUDA(h, h->cgState.alloc(128));
+    CgState* st = reinterpret_cast<CgState*>(h->cgState.p);
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(h->cgState.p + 96);
+    cg2_init_kernel<<<1, 1, 0, h->stream>>>(st, scal + 0, scal + 4, relTol, maxIt, arrive);
+    IKB_LAUNCH_CHECK(h);
+    const PatternView P = h->view();
+    double* pqPartial = h->scratch.p;
+    double* rzPartial = h->scratch.p + 2 * RED_BLOCKS;
+    CgState* hs = reinterpret_cast<CgState*>(h->hostScal);
+    const int batch = 32;
+    while (true) {
+      for (int b = 0; b < batch; ++b) {
+        if (h->dim == 3)
+          spmv_node_dot_kernel<3><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                     pqPartial, st);
+        else
+          spmv_node_dot_kernel<2><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                     pqPartial, st);
+        cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, pqPartial, RED_BLOCKS, h->cgP.p, h->cgQ.p,
+                                                             h->cgDinv.p, h->cgX.p, h->cgR.p, h->cgZ.p, rzPartial);
+        cg2_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, rzPartial, RED_BLOCKS, h->cgZ.p, h->cgP.p, arrive);
+        h->launches += 3;
+      }
+      IKB_CUDA(h, cudaGetLastError());
+      IKB_CUDA(h, cudaMemcpyAsync(hs, st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (hs->done || hs->iter >= maxIt) break;
+    }
+    it = hs->iter;
+    rr = hs->rr;
+    if (hs->done == 2) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
+  } else if (bb > 0.0) {
     while (it < maxIt && rr >= threshold) {
       if ((rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p))) return rc;
       if ((rc = deviceDot(h, 1, h->cgP.p, h->cgQ.p, n, scal + 1, 1.0, nullptr))) return rc;

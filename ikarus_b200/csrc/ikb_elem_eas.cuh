@@ -441,11 +441,11 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       }
     }
     // park the uncondensed blocks in the staging array (this thread re-reads them after the solve)
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * DD;
+    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
-      double* dst = Ke + (size_t)(k * N + a) * DD;
+      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
 #pragma unroll
       for (int q = 0; q < DD; ++q) dst[q] = acc[k][q];
     }
@@ -607,13 +607,13 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   // ------------------------------------------------------------------ condensation
   // K_ab -= L_a^T Z_b ; R_a -= L_a^T (D^-1 Rt)   (enhancedassumedstrains.hh:292-296, 341-345)
   if (A.what & IKB_MATRIX) {
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * DD;
+    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll 1
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
       const int b = (a + k) & (N - 1);
       double blk[DD];
-      double* dst = Ke + (size_t)(k * N + a) * DD;
+      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
 #pragma unroll
       for (int q = 0; q < DD; ++q) blk[q] = dst[q];
 #pragma unroll

@@ -89,7 +89,8 @@ struct Q1Cfg {
   static constexpr int VEC = NV * D * N;
   static constexpr int GPS0 = VEC + NS;
   static constexpr int GPS = GPS0 + ((5 - GPS0 % 4) % 4);   // == 1 (mod 4): conflict-free phase-1 stores
-  static constexpr int S0 = N * GPS;
+  static constexpr int BS = blockStride(D);
+  static constexpr int S0 = (N * GPS > NPAIR * BS) ? N * GPS : NPAIR * BS;  // also holds the packed K_e for write-out
   static constexpr int S = S0 + ((N % 16) - (S0 % 16) + 16) % 16;  // == N (mod 16): conflict-free phase-2 loads
   static constexpr int SMEM_BUDGET = 110 * 1024;
   static constexpr int EPW = 32 / N;                               // elements per warp
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   const int64_t e = (int64_t)blockIdx.x * C::EPC + el;
   const bool active = e < A.nElem;
   double* rec = smem + (size_t)el * C::S;
+  const unsigned grpMask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << ((threadIdx.x & 31u) / N * N));
 
   // ------------------------------------------------------------------ phase 1
   if (active) {
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   for (int i = 0; i < D; ++i) Ra[i] = 0.0;
 
   const int a = t;
-#pragma unroll 1
+#pragma unroll 2
   for (int g = 0; g < N; ++g) {
     const double* gp = rec + g * C::GPS;
     const double* vM = gp;
@@ -406,31 +408,38 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   }
 
   // ------------------------------------------------------------------ write-out
-  if (A.what & IKB_MATRIX) {
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * DD;
-#pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      if (k == C::KMAX && a >= N / 2) break;
-      double* dst = Ke + (size_t)(k * N + a) * DD;
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          // diagonal block: mirror the upper triangle so K_e is exactly symmetric
-          const double v = (k == 0 && i > j) ? acc[0][j * D + i] : acc[k][i * D + j];
-          dst[i * D + j] = v;
-        }
-    }
-  }
-  if (A.what & IKB_VECTOR) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) A.Rst[(size_t)e * (N * D) + a * D + i] = Ra[i];
-  }
+  // E_e first (it reads the records), then the record area is recycled to transpose K_e so that the element's
+  // N lanes store 16-byte vectors to consecutive addresses (full 32-byte sectors instead of 8-byte pieces).
   if ((A.what & IKB_SCALAR) && a == 0) {
     double s = 0.0;
 #pragma unroll
     for (int g = 0; g < N; ++g) s += rec[g * C::GPS + C::VEC + C::O_PSI];
     A.Est[e] = s;
+  }
+  if (A.what & IKB_MATRIX) {
+    __syncwarp(grpMask);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if (k == C::KMAX && a >= N / 2) break;
+      double* dst = rec + (k * N + a) * C::BS;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          // diagonal block: mirror the upper triangle so K_e is exactly symmetric
+          dst[i * D + j] = (k == 0 && i > j) ? acc[0][j * D + i] : acc[k][i * D + j];
+        }
+    }
+    __syncwarp(grpMask);
+    constexpr int NV2 = C::NPAIR * C::BS / 2;
+    const double2* src2 = reinterpret_cast<const double2*>(rec);
+    double2* dst2 = reinterpret_cast<double2*>(A.Kst + (size_t)e * C::NPAIR * C::BS);
+#pragma unroll 4
+    for (int idx = a; idx < NV2; idx += N) dst2[idx] = src2[idx];
+  }
+  if (A.what & IKB_VECTOR) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) A.Rst[(size_t)e * (N * D) + a * D + i] = Ra[i];
   }
 }
 

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
   double Ra[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) Ra[i] = 0.0;
-  double* Ke = A.Kst + (size_t)e * C::NPAIR * DD;
+  double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll 1
   for (int pass = 0; pass < C::NPASS; ++pass) {
     const int k0 = pass * C::KPASS;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
       for (int k = 0; k < C::KPASS; ++k) {
         const int kk = k0 + k;
         if (kk > C::KMAX) break;
-        double* dst = Ke + (size_t)(kk * N + a) * DD;
+        double* dst = Ke + (size_t)(kk * N + a) * blockStride(D);
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll

@@ -16,6 +16,8 @@ enum Layout { LAYOUT_INTERLEAVED = 0, LAYOUT_LEXICOGRAPHIC = 1 };
 
 constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
 constexpr uint32_t SRC_MASK = 0x7fffffffu;
+// doubles per staged K_e block
+__host__ __device__ constexpr int blockStride(int dim) { return dim * dim; }
 
 template <typename T>
 struct DevBuf {
@@ -125,6 +127,7 @@ struct Handle {
   DevBuf<double> cgR, cgZ, cgP, cgQ, cgX, cgDinv, cgB;
   DevBuf<double> cgScal;       // device scalars
   double* hostScal = nullptr;  // pinned
+  DevBuf<uint8_t> cgState;     // CgState + arrival counter of the sync-free PCG
 
   // NCCL (element-partitioned runs)
   void* comm = nullptr;

@@ -47,6 +47,178 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(PatternView P, const do
   if (row < nRows && lane == 0) y[outRow] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sync-free PCG building blocks (single GPU).  One warp per node-row: the D scalar rows of a node share
+// their column set, so x is gathered once per column and used for D rows; consecutive lanes read consecutive
+// values of each row (coalesced).  The p.q partial sums are produced by the same kernel.  All folds of
+// per-block partials are done redundantly by every block of the consumer kernel in the same fixed order,
+// so no separate reduction kernels and no host round trip are needed per iteration; a device-side `done`
+// flag turns the remaining launches of a batch into no-ops once |r|^2 < threshold.
+struct CgState {
+  double rz[2];      // r.z ping-pong by iteration parity
+  double rr;         // |r|^2 of the last completed iteration
+  double threshold;  // tol^2 |b|^2
+  int iter;          // completed iterations
+  int done;          // 1 converged, 2 NaN
+  int maxIter;
+  int pad;
+};
+
+__global__ void cg2_init_kernel(CgState* st, const double* rzDev, const double* bbDev, double relTol, int maxIter,
+                                unsigned int* arrive) {
+  st->rz[0] = rzDev[0];
+  st->rz[1] = 0.0;
+  st->rr = bbDev[0];
+  const double thr = relTol * relTol * bbDev[0];
+  st->threshold = thr > 1e-300 ? thr : 1e-300;
+  st->iter = 0;
+  st->done = (bbDev[0] > 0.0 && bbDev[0] >= st->threshold) ? 0 : 1;
+  st->maxIter = maxIter;
+  *arrive = 0u;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) spmv_node_dot_kernel(PatternView P, const double* __restrict__ vals,
+                                                            const double* __restrict__ x, double* __restrict__ y,
+                                                            const double* __restrict__ pLocal, double* partial,
+                                                            const CgState* st) {
+  if (st && (st->done || st->iter >= st->maxIter)) return;
+  __shared__ double sh[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warpsTotal = (int64_t)gridDim.x * 8;
+  double dot = 0.0;
+  for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < P.nRowNodes; g += warpsTotal) {
+    const int32_t b0 = P.nbrPtr[g];
+    const int nnb = P.nbrPtr[g + 1] - b0;
+    const int len = nnb * D;
+    double s[D];
+    int64_t start[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      s[i] = 0.0;
+      start[i] = rawRowStart(P, g, i, nnb);
+    }
+    for (int j = lane; j < len; j += 32) {
+      int slot, k;
+      if (P.layout == LAYOUT_INTERLEAVED) {
+        slot = j / D;
+        k = j - slot * D;
+      } else {
+        k = j / nnb;
+        slot = j - k * nnb;
+      }
+      const double xv = x[dofOf(P.layout, D, P.nNodes, P.nbrIdx[b0 + slot], k)];
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = fma(vals[start[i] + j], xv, s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], w);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t r = localRowOf(P, g, i);
+        y[r] = s[i];
+        if (pLocal) dot = fma(pLocal[r], s[i], dot);
+      }
+    }
+  }
+  if (partial) {
+    if (lane == 0) sh[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += sh[w];
+      partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// deterministic fold of np partials by one whole block (every block computes the same value)
+__device__ __forceinline__ double blockFold(const double* __restrict__ partial, int np, double* sh) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// x += alpha p ; r -= alpha q ; z = dinv r ; block partials of r.z and r.r.  alpha = rz / fold(pq partials).
+__global__ void __launch_bounds__(256) cg2_update_kernel(int64_t n, const CgState* st, const double* __restrict__ pqPartial,
+                                                         int npq, const double* __restrict__ p,
+                                                         const double* __restrict__ q, const double* __restrict__ dinv,
+                                                         double* x, double* r, double* z, double* partial) {
+  if (st->done || st->iter >= st->maxIter) return;
+  __shared__ double sh[256];
+  __shared__ double sh1[256];
+  const double pq = blockFold(pqPartial, npq, sh);
+  const double rz = st->rz[st->iter & 1];
+  const double alpha = pq != 0.0 ? rz / pq : 0.0;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    const double zi = dinv[i] * ri;
+    z[i] = zi;
+    s0 = fma(ri, zi, s0);
+    s1 = fma(ri, ri, s1);
+  }
+  sh[threadIdx.x] = s0;
+  sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      sh[threadIdx.x] += sh[threadIdx.x + w];
+      sh1[threadIdx.x] += sh1[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    partial[gridDim.x + blockIdx.x] = sh1[0];
+  }
+}
+
+// p = z + beta p, beta = rz_new / rz ; the LAST block to finish publishes rz_new, rr, iter+1 and the done flag
+// (all blocks must have read the old state first, hence the arrival counter).
+__global__ void __launch_bounds__(256) cg2_direction_kernel(int64_t n, CgState* st, const double* __restrict__ partial,
+                                                            int np, const double* __restrict__ z, double* p,
+                                                            unsigned int* arrive) {
+  if (st->done || st->iter >= st->maxIter) return;
+  __shared__ double sh[256];
+  const double rzNew = blockFold(partial, np, sh);
+  const double rr = blockFold(partial + np, np, sh);
+  const int it = st->iter;
+  const double rz = st->rz[it & 1];
+  const double beta = rz != 0.0 ? rzNew / rz : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(arrive, 1u);
+    if (ticket == gridDim.x - 1) {
+      *arrive = 0u;
+      st->rz[(it + 1) & 1] = rzNew;
+      st->rr = rr;
+      if (!(rr == rr))
+        st->done = 2;
+      else if (rr < st->threshold)
+        st->done = 1;
+      __threadfence();
+      st->iter = it + 1;
+    }
+  }
+}
+
 template <int LANES>
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const int64_t* __restrict__ outer,
                                                        const int32_t* __restrict__ inner,
