@@ -184,8 +184,9 @@ int64_t nnzOf(Handle* h, int dbc) { return dbc == IKB_DBC_REDUCED ? h->nnzRed : 
 int launchGather(Handle* h, unsigned what, int dbc) {
   GatherArgs G;
   G.P = h->view();
-  G.cptr = h->cptr.p;
-  G.csrc = h->csrc.p;
+  G.adjPtr = h->adjPtr.p;
+  G.adjCode = h->adjCode.p;
+  G.slotTab = h->slotTab.p;
   G.Kst = h->Kst.p;
   G.Rst = h->Rst.p;
   G.fext = h->hasFext ? h->Fext.p : nullptr;
@@ -195,18 +196,31 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   G.vec = (what & IKB_VECTOR) ? h->vec[dbc].p : nullptr;
   G.dbc = dbc;
   G.npair = h->npair;
-  G.nn = h->nn;
+  // tile rows are padded to a stride == D (mod 16) doubles
+  G.maxOut = h->dim * (h->dim * std::max(h->maxNbr, 1) + 16);
   G.freeCnt = h->freeCnt.p;
   G.freeTot = h->freeTot.p;
   G.redRowStart = h->redRowStart.p;
   G.cbelow = h->cbelow.p;
   G.redVecOffset = 0;
-  const int tpb = 256;
-  if (h->nBlocks == 0) return IKB_OK;
-  if (h->dim == 3)
-    gather_kernel<3><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(G);
-  else
-    gather_kernel<2><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(G);
+  const int64_t nRowNodes = h->rowEnd - h->rowBegin;
+  if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
+  // one warp per node-row; fewer warps per CTA when the output tile is large (Hex27)
+  const int warps = (size_t)G.maxOut * 8 * 8 <= 64 * 1024 ? 8 : 4;
+  const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
+  const unsigned grid = gridFor(nRowNodes, warps);
+  cudaError_t e = cudaErrorInvalidValue;
+#define IKB_GATHER(DIM, NN)                                                                                         \
+  if (h->dim == DIM && h->nn == NN) {                                                                               \
+    e = cudaFuncSetAttribute(gather_kernel<DIM, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (e == cudaSuccess) gather_kernel<DIM, NN><<<grid, warps * 32, smem, h->stream>>>(G);                         \
+  }
+  IKB_GATHER(3, 8)
+  IKB_GATHER(3, 27)
+  IKB_GATHER(2, 4)
+  IKB_GATHER(2, 9)
+#undef IKB_GATHER
+  if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("gather launch: ") + cudaGetErrorString(e));
   IKB_LAUNCH_CHECK(h);
   return IKB_OK;
 }
@@ -452,6 +466,9 @@ int ikb_destroy(ikb_handle hh) {
   h->nbrRow.release();
   h->cptr.release();
   h->csrc.release();
+  h->adjPtr.release();
+  h->adjCode.release();
+  h->slotTab.release();
   h->cbelow.release();
   h->freeCnt.release();
   h->freeTot.release();
@@ -731,8 +748,48 @@ int ikb_build_pattern(ikb_handle hh) {
   ukeys.p = nullptr;  // aliased keys.p
   keys.release();
   keysOut.release();
-  counts.release();
   nRuns.release();
+  counts.release();
+  // node -> (element, local node) adjacency in element order + slot tables: the map of the warp-per-node gather
+  {
+    const PatternView P = h->view();
+    DevBuf<int32_t> adjCount, rowLen, maxLen;
+    IKB_CUDA(h, adjCount.alloc((size_t)nRowNodes + 1));
+    IKB_CUDA(h, rowLen.alloc((size_t)std::max<int64_t>(nRowNodes, 1)));
+    IKB_CUDA(h, maxLen.alloc(1));
+    IKB_CUDA(h, cudaMemsetAsync(adjCount.p, 0, adjCount.bytes(), h->stream));
+    adj_count_kernel<<<gridFor(nRowNodes, tpb), tpb, 0, h->stream>>>(P, h->cptr.p, adjCount.p, rowLen.p);
+    IKB_LAUNCH_CHECK(h);
+    IKB_CUDA(h, h->adjPtr.alloc((size_t)nRowNodes + 1));
+    tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, adjCount.p, h->adjPtr.p, nRowNodes + 1, h->stream);
+    IKB_CUDA(h, tmp.alloc(tmpBytes));
+    IKB_CUDA(h, cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, adjCount.p, h->adjPtr.p, nRowNodes + 1, h->stream));
+    h->launches++;
+    tmpBytes = 0;
+    cub::DeviceReduce::Max(nullptr, tmpBytes, rowLen.p, maxLen.p, nRowNodes, h->stream);
+    IKB_CUDA(h, tmp.alloc(tmpBytes));
+    IKB_CUDA(h, cub::DeviceReduce::Max(tmp.p, tmpBytes, rowLen.p, maxLen.p, nRowNodes, h->stream));
+    h->launches++;
+    int32_t nAdj = 0, mx = 0;
+    IKB_CUDA(h, cudaMemcpyAsync(&nAdj, h->adjPtr.p + nRowNodes, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    IKB_CUDA(h, cudaMemcpyAsync(&mx, maxLen.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->maxNbr = mx;
+    if (mx > 255) return fail(h, IKB_ENOTIMPL, "pattern rows with more than 255 neighbour nodes are not supported");
+    IKB_CUDA(h, h->adjCode.alloc((size_t)std::max(nAdj, 1)));
+    IKB_CUDA(h, h->slotTab.alloc((size_t)std::max(nAdj, 1) * nn));
+    adj_fill_kernel<<<gridFor(nRowNodes, tpb), tpb, 0, h->stream>>>(P, h->cptr.p, h->csrc.p, h->adjPtr.p, h->elemNode.p,
+                                                                    h->nElem, nn, h->npair, h->adjCode.p, h->slotTab.p);
+    IKB_LAUNCH_CHECK(h);
+    IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+    adjCount.release();
+    rowLen.release();
+    maxLen.release();
+    // the per-block contribution lists were only needed to derive the adjacency
+    h->csrc.release();
+    h->cptr.release();
+  }
   tmp.release();
   h->patternBuilt = true;
   h->reducedBuilt = false;

@@ -14,8 +14,9 @@ namespace ikb {
 
 struct GatherArgs {
   PatternView P;
-  const int32_t* cptr;
-  const uint32_t* csrc;
+  const int32_t* adjPtr;    // [nRowNodes+1]
+  const uint32_t* adjCode;  // [nAdj] e*N + la, ascending element order per node
+  const uint8_t* slotTab;   // [nAdj][N] slot of element node lb in the pattern row of the node
   const double* Kst;
   const double* Rst;
   const double* fext;   // may be null
@@ -25,7 +26,7 @@ struct GatherArgs {
   double* vec;          // output vector for mode dbc (null: skip vector)
   int dbc;
   int npair;
-  int nn;               // nodes per element
+  int maxOut;           // doubles of shared memory per warp
   // reduced mode
   const uint16_t* freeCnt;
   const uint16_t* freeTot;
@@ -34,97 +35,143 @@ struct GatherArgs {
   int64_t redVecOffset;  // index of the first local free row in the reduced vector
 };
 
-template <int D>
+// One warp per node-row.  For every element touching the node (ascending element order, as the reference's
+// serial loop visits them, ikarus/assembler/simpleassemblers.inl:126-136) the warp streams the N staged blocks
+// K_e[la][0..N-1] -- consecutive lanes on consecutive doubles of a block -- and adds them into the node's
+// D x (D*nnb) output tile in shared memory.  The positions written for one element are distinct, so there are
+// no atomics and no ordering issue inside an element; a __syncwarp orders successive elements, which keeps the
+// reference's summation order per entry.  The finished tile (contiguous in Eigen's value order for
+// FlatInterleaved dofs) is written once, coalesced, with the Dirichlet mode applied.
+// The inner loop is table driven: offTab[la][idx] is the offset of value idx of chunk la inside the
+// symmetric-packed staged K_e (transposition folded in), slots come from one byte load per element node.
+template <int D, int N>
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   constexpr int DD = D * D;
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= G.P.nBlocks) return;
-  const PatternView& P = G.P;
-  const int64_t g = P.nbrRow[b];
-  const int64_t gb = P.nbrIdx[b];
-  const int32_t c0 = G.cptr[b], c1 = G.cptr[b + 1];
-  const bool diag = (g + P.rowBegin) == gb;
-
-  bool rowFixed[D], colFixed[D];
-  int64_t rowDof[D], colDof[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    rowDof[i] = dofOf(P.layout, D, P.nNodes, g + P.rowBegin, i);
-    colDof[i] = dofOf(P.layout, D, P.nNodes, gb, i);
-    rowFixed[i] = G.flags ? (G.flags[rowDof[i]] != 0) : false;
-    colFixed[i] = G.flags ? (G.flags[colDof[i]] != 0) : false;
+  constexpr int CHUNK = N * DD;
+  constexpr int NIT = (CHUNK + 31) / 32;
+  constexpr int HALF = N / 2;
+  extern __shared__ double gsm[];
+  __shared__ int16_t offTab[N * CHUNK];
+  for (int t = threadIdx.x; t < N * CHUNK; t += blockDim.x) {
+    const int la = t / CHUNK, idx = t - la * CHUNK;
+    const int lb = idx / DD, q = idx - lb * DD;
+    const int i = q / D, k = q - i * D;
+    int k1 = lb - la;
+    if (k1 < 0) k1 += N;
+    const bool direct = (N & 1) ? (k1 <= HALF) : (k1 < HALF || (k1 == HALF && la < HALF));
+    offTab[t] = (int16_t)(direct ? (k1 * N + la) * DD + q : ((N - k1) * N + lb) * DD + k * D + i);
   }
+  __syncthreads();
+  const PatternView& P = G.P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= P.nRowNodes) return;
+  double* out = gsm + (size_t)warp * G.maxOut;
+  const int32_t b0 = P.nbrPtr[g];
+  const int nnb = P.nbrPtr[g + 1] - b0;
+  const int rowLen = D * nnb;
+  // padded row stride of the tile: (i*stride + k) distinct mod 16 for i,k < D -> conflict-free accumulation
+  const int rowStride = rowLen + ((D - (rowLen & 15)) + 16) % 16;
+  const int32_t a0 = G.adjPtr[g], a1 = G.adjPtr[g + 1];
 
   if (G.vals) {
-    double acc[DD];
+    for (int idx = lane; idx < D * rowStride; idx += 32) out[idx] = 0.0;
+    // element-independent lane constants
+    int lbOf[NIT], outBase[NIT];
+    bool valid[NIT];
 #pragma unroll
-    for (int q = 0; q < DD; ++q) acc[q] = 0.0;
-    for (int32_t c = c0; c < c1; ++c) {
-      const uint32_t s = G.csrc[c];
-      const double* p = G.Kst + (size_t)(s & SRC_MASK) * DD;
-      if (s & SRC_TRANSPOSE) {
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int k = 0; k < D; ++k) acc[i * D + k] += p[k * D + i];
-      } else {
-#pragma unroll
-        for (int q = 0; q < DD; ++q) acc[q] += p[q];
-      }
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = lane + 32 * it;
+      valid[it] = idx < CHUNK;
+      const int lb = valid[it] ? idx / DD : 0;
+      const int q = idx - lb * DD;
+      const int i = q / D, k = q - i * D;
+      lbOf[it] = lb;
+      outBase[it] = i * rowStride + k;
     }
-    const int nnb = P.nbrPtr[g + 1] - P.nbrPtr[g];
-    const int slot = (int)(b - P.nbrPtr[g]);
-    if (G.dbc == IKB_DBC_REDUCED) {
+    __syncwarp();
+    const int elemStride = G.npair * DD;
+    for (int32_t base = a0; base < a1; base += 32) {
+      const int cnt = (a1 - base) < 32 ? (a1 - base) : 32;
+      const uint32_t myCode = lane < cnt ? G.adjCode[base + lane] : 0u;
+      // UB elements in flight: their index, slot and value loads are independent of each other; the tile
+      // updates below still run element by element in ascending order
+      constexpr int UB = 4;
+      for (int j0 = 0; j0 < cnt; j0 += UB) {
+        double v[UB][NIT];
+        int mySlot[UB];
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        if (rowFixed[i]) continue;
-        const int64_t start = G.redRowStart[localRowOf(P, g, i)];
+        for (int u = 0; u < UB; ++u) {
+          const int j = j0 + u;
+          const uint32_t code = __shfl_sync(0xffffffffu, myCode, j & 31);
+          const bool on = j < cnt;
+          const uint32_t e = code / (uint32_t)N;
+          const int la = (int)(code - e * (uint32_t)N);
+          const double* Ke = G.Kst + (size_t)e * elemStride;
+          const int16_t* tab = offTab + la * CHUNK + lane;
+          mySlot[u] = (on && lane < N) ? (int)G.slotTab[(size_t)(base + j) * N + lane] : 0;
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          if (colFixed[k]) continue;
-          G.vals[start + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b, gb, k)] = acc[i * D + k];
+          for (int it = 0; it < NIT; ++it) v[u][it] = (on && valid[it]) ? Ke[tab[32 * it]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          if (j0 + u < cnt) {  // warp-uniform
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+              const int s = __shfl_sync(0xffffffffu, mySlot[u], lbOf[it]);
+              if (valid[it]) out[outBase[it] + D * s] += v[u][it];
+            }
+            __syncwarp();
+          }
         }
       }
-    } else {
-      const bool full = G.dbc == IKB_DBC_FULL;
+    }
+    const bool full = G.dbc == IKB_DBC_FULL;
+    const int64_t gGlobal = g + P.rowBegin;
+    bool rowFixed[D];
+    int64_t rowStart[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      rowFixed[i] = G.flags ? (G.flags[dofOf(P.layout, D, P.nNodes, gGlobal, i)] != 0) : false;
+      rowStart[i] = rawRowStart(P, g, i, nnb);
+    }
+    for (int idx2 = lane; idx2 < rowLen; idx2 += 32) {
+      const int s = idx2 / D, k = idx2 - s * D;
+      const int64_t gb = P.nbrIdx[b0 + s];
+      const bool colFixed = G.flags ? (G.flags[dofOf(P.layout, D, P.nNodes, gb, k)] != 0) : false;
+      const int64_t offs = rawEntryOffset(P, s, k, nnb);
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const int64_t start = rawRowStart(P, g, i, nnb);
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-          double v = acc[i * D + k];
+        double v = out[i * rowStride + idx2];
+        if (G.dbc == IKB_DBC_REDUCED) {
+          if (!rowFixed[i] && !colFixed)
+            G.vals[G.redRowStart[localRowOf(P, g, i)] + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b0 + s, gb, k)] = v;
+        } else {
           // Full: zero constrained rows and columns, unit diagonal (simpleassemblers.inl:159-167)
-          if (full && (rowFixed[i] || colFixed[k])) v = (diag && i == k) ? 1.0 : 0.0;
-          G.vals[start + rawEntryOffset(P, slot, k, nnb)] = v;
+          if (full && (rowFixed[i] || colFixed)) v = (gb == gGlobal && i == k) ? 1.0 : 0.0;
+          G.vals[rowStart[i] + offs] = v;
         }
       }
     }
   }
 
-  if (G.vec && diag) {
-    // the diagonal block's contributions are exactly (element, la == lb) for every element
-    // touching this node, in element order: reuse them for R
-    double r[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) r[i] = 0.0;
-    for (int32_t c = c0; c < c1; ++c) {
-      const uint32_t s = G.csrc[c] & SRC_MASK;  // = e*npair + la   (k = 0)
-      const int64_t e = s / G.npair;
-      const int la = (int)(s - e * G.npair);
-      const double* p = G.Rst + (size_t)e * (G.nn * D) + la * D;
-#pragma unroll
-      for (int i = 0; i < D; ++i) r[i] += p[i];
+  if (G.vec && lane < D) {
+    const int i = lane;
+    double r = 0.0;
+    for (int32_t j = a0; j < a1; ++j) {
+      const uint32_t code = G.adjCode[j];
+      const uint32_t e = code / (uint32_t)N;
+      const int la = (int)(code - e * (uint32_t)N);
+      r += G.Rst[(size_t)e * (N * D) + la * D + i];
     }
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      double v = r[i];
-      if (G.fext) v -= G.fextScale * G.fext[rowDof[i]];
-      if (G.dbc == IKB_DBC_REDUCED) {
-        if (!rowFixed[i]) G.vec[rowDof[i] - G.cbelow[rowDof[i]] - G.redVecOffset] = v;
-      } else {
-        if (G.dbc == IKB_DBC_FULL && rowFixed[i]) v = 0.0;  // simpleassemblers.inl:90-92
-        G.vec[localRowOf(P, g, i)] = v;
-      }
+    const int64_t rowDof = dofOf(P.layout, D, P.nNodes, g + P.rowBegin, i);
+    const bool rowFixed = G.flags ? (G.flags[rowDof] != 0) : false;
+    if (G.fext) r -= G.fextScale * G.fext[rowDof];
+    if (G.dbc == IKB_DBC_REDUCED) {
+      if (!rowFixed) G.vec[rowDof - G.cbelow[rowDof] - G.redVecOffset] = r;
+    } else {
+      if (G.dbc == IKB_DBC_FULL && rowFixed) r = 0.0;  // simpleassemblers.inl:90-92
+      G.vec[localRowOf(P, g, i)] = r;
     }
   }
 }

@@ -98,6 +98,12 @@ struct Handle {
   int64_t nBlocks = 0;
   DevBuf<int32_t> nbrPtr, nbrIdx, nbrRow, cptr;
   DevBuf<uint32_t> csrc;
+  // node -> adjacent (element, local node) list in ascending element order, and for each of them the slot of
+  // every element node in the node's pattern row (gather map of the warp-per-node gather)
+  DevBuf<int32_t> adjPtr;       // [nRowNodes+1]
+  DevBuf<uint32_t> adjCode;     // [nAdj]  e*n + la
+  DevBuf<uint8_t> slotTab;      // [nAdj][n]
+  int maxNbr = 0;               // longest pattern row in nodes
   // reduced-mode structures
   bool reducedBuilt = false;
   int64_t nRed = 0, nnzRed = 0;

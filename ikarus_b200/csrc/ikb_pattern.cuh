@@ -82,6 +82,59 @@ __global__ void row_ptr_kernel(const int32_t* __restrict__ nbrRow, int64_t nBloc
   nbrPtr[g] = (int32_t)lo;
 }
 
+// ---------------------------------------------------------------------------- node -> element adjacency
+// The diagonal block (g,g) of row g lists exactly the (element, la) pairs touching node g, in element order.
+__device__ __forceinline__ int32_t diagBlockOf(const PatternView& P, int64_t g) {
+  int32_t lo = P.nbrPtr[g], hi = P.nbrPtr[g + 1];
+  const int32_t target = (int32_t)(g + P.rowBegin);
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (P.nbrIdx[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__global__ void adj_count_kernel(PatternView P, const int32_t* __restrict__ cptr, int32_t* adjCount, int32_t* rowLen) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.nRowNodes) return;
+  const int32_t b = diagBlockOf(P, g);
+  adjCount[g] = cptr[b + 1] - cptr[b];
+  rowLen[g] = P.nbrPtr[g + 1] - P.nbrPtr[g];
+}
+
+__global__ void adj_fill_kernel(PatternView P, const int32_t* __restrict__ cptr, const uint32_t* __restrict__ csrc,
+                                const int32_t* __restrict__ adjPtr, const int32_t* __restrict__ elemNode,
+                                int64_t nElem, int n, int npair, uint32_t* adjCode, uint8_t* slotTab) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.nRowNodes) return;
+  const int32_t b0 = P.nbrPtr[g], b1 = P.nbrPtr[g + 1];
+  const int32_t bd = diagBlockOf(P, g);
+  const int32_t c0 = cptr[bd];
+  const int32_t cnt = cptr[bd + 1] - c0;
+  const int32_t a0 = adjPtr[g];
+  for (int32_t j = 0; j < cnt; ++j) {
+    const uint32_t s = csrc[c0 + j] & SRC_MASK;  // diagonal pair: e*npair + la
+    const int64_t e = s / (uint32_t)npair;
+    const int la = (int)(s - e * npair);
+    adjCode[a0 + j] = (uint32_t)(e * n + la);
+    for (int lb = 0; lb < n; ++lb) {
+      const int32_t nb = elemNode[(size_t)lb * nElem + e];
+      int32_t l2 = b0, h2 = b1;
+      while (l2 < h2) {
+        const int32_t mid = (l2 + h2) >> 1;
+        if (P.nbrIdx[mid] < nb)
+          l2 = mid + 1;
+        else
+          h2 = mid;
+      }
+      slotTab[(size_t)(a0 + j) * n + lb] = (uint8_t)(l2 - b0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- reduced mode
 __global__ void flags_to_int_kernel(const uint8_t* flags, int64_t n, int32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
