@@ -210,15 +210,33 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
   const unsigned grid = gridFor(nRowNodes, warps);
   cudaError_t e = cudaErrorInvalidValue;
-#define IKB_GATHER(DIM, NN)                                                                                         \
-  if (h->dim == DIM && h->nn == NN) {                                                                               \
-    e = cudaFuncSetAttribute(gather_kernel<DIM, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    if (e == cudaSuccess) gather_kernel<DIM, NN><<<grid, warps * 32, smem, h->stream>>>(G);                         \
+#define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
+  {                                                                                                                  \
+    e = cudaFuncSetAttribute(gather_kernel<DIM, NN, MODE, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                             (int)smem);                                                                             \
+    if (e == cudaSuccess) gather_kernel<DIM, NN, MODE, IL><<<grid, warps * 32, smem, h->stream>>>(G);                \
+  }
+#define IKB_GATHER2(DIM, NN, MODE)                    \
+  if (h->layout == LAYOUT_INTERLEAVED)                \
+    IKB_GATHER3(DIM, NN, MODE, true)                  \
+  else                                                \
+    IKB_GATHER3(DIM, NN, MODE, false)
+#define IKB_GATHER(DIM, NN)                           \
+  if (h->dim == DIM && h->nn == NN) {                 \
+    if (dbc == IKB_DBC_RAW) {                         \
+      IKB_GATHER2(DIM, NN, IKB_DBC_RAW)               \
+    } else if (dbc == IKB_DBC_FULL) {                 \
+      IKB_GATHER2(DIM, NN, IKB_DBC_FULL)              \
+    } else {                                          \
+      IKB_GATHER2(DIM, NN, IKB_DBC_REDUCED)           \
+    }                                                 \
   }
   IKB_GATHER(3, 8)
   IKB_GATHER(3, 27)
   IKB_GATHER(2, 4)
   IKB_GATHER(2, 9)
+#undef IKB_GATHER2
+#undef IKB_GATHER3
 #undef IKB_GATHER
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("gather launch: ") + cudaGetErrorString(e));
   IKB_LAUNCH_CHECK(h);

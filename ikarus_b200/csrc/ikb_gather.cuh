@@ -44,12 +44,13 @@ struct GatherArgs {
 // FlatInterleaved dofs) is written once, coalesced, with the Dirichlet mode applied.
 // The inner loop is table driven: offTab[la][idx] is the offset of value idx of chunk la inside the
 // symmetric-packed staged K_e (transposition folded in), slots come from one byte load per element node.
-template <int D, int N>
+template <int D, int N, int DBC, bool INTERLEAVED>
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   constexpr int DD = D * D;
   constexpr int CHUNK = N * DD;
   constexpr int NIT = (CHUNK + 31) / 32;
   constexpr int HALF = N / 2;
+  constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
   extern __shared__ double gsm[];
   __shared__ int16_t offTab[N * CHUNK];
   for (int t = threadIdx.x; t < N * CHUNK; t += blockDim.x) {
@@ -76,79 +77,87 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
 
   if (G.vals) {
     for (int idx = lane; idx < D * rowStride; idx += 32) out[idx] = 0.0;
-    // element-independent lane constants
+    // element-independent lane constants: value idx = lane + 32*it of a chunk belongs to element node lbOf[it]
     int lbOf[NIT], outBase[NIT];
-    bool valid[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int idx = lane + 32 * it;
-      valid[it] = idx < CHUNK;
-      const int lb = valid[it] ? idx / DD : 0;
-      const int q = idx - lb * DD;
+      const int idc = idx < CHUNK ? idx : 0;
+      const int lb = idc / DD;
+      const int q = idc - lb * DD;
       const int i = q / D, k = q - i * D;
       lbOf[it] = lb;
       outBase[it] = i * rowStride + k;
     }
     __syncwarp();
     const int elemStride = G.npair * DD;
-    for (int32_t base = a0; base < a1; base += 32) {
-      const int cnt = (a1 - base) < 32 ? (a1 - base) : 32;
-      const uint32_t myCode = lane < cnt ? G.adjCode[base + lane] : 0u;
-      // UB elements in flight: their index, slot and value loads are independent of each other; the tile
-      // updates below still run element by element in ascending order
-      constexpr int UB = 4;
-      for (int j0 = 0; j0 < cnt; j0 += UB) {
-        double v[UB][NIT];
-        int mySlot[UB];
+    // software pipeline, depth PD: the loads of elements j+1..j+PD are in flight while element j is added to the tile
+    constexpr int PD = 1;
+    double vq[PD][NIT];
+    int sq[PD][NIT];
+    auto fetch = [&](int32_t j, int slotIdx) {
+      const uint32_t code = G.adjCode[j];
+      const uint32_t e = code / (uint32_t)N;
+      const int la = (int)(code - e * (uint32_t)N);
+      const double* Ke = G.Kst + (size_t)e * elemStride;
+      const int16_t* tab = offTab + la * CHUNK + lane;
+      const uint8_t* st = G.slotTab + (size_t)j * N;
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          const int j = j0 + u;
-          const uint32_t code = __shfl_sync(0xffffffffu, myCode, j & 31);
-          const bool on = j < cnt;
-          const uint32_t e = code / (uint32_t)N;
-          const int la = (int)(code - e * (uint32_t)N);
-          const double* Ke = G.Kst + (size_t)e * elemStride;
-          const int16_t* tab = offTab + la * CHUNK + lane;
-          mySlot[u] = (on && lane < N) ? (int)G.slotTab[(size_t)(base + j) * N + lane] : 0;
-#pragma unroll
-          for (int it = 0; it < NIT; ++it) v[u][it] = (on && valid[it]) ? Ke[tab[32 * it]] : 0.0;
+      for (int it = 0; it < NIT; ++it) {
+        if (it < NIT - 1 || lane + 32 * it < CHUNK) {
+          vq[slotIdx][it] = Ke[tab[32 * it]];
+          sq[slotIdx][it] = st[lbOf[it]];
         }
+      }
+    };
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-          if (j0 + u < cnt) {  // warp-uniform
+    for (int u = 0; u < PD; ++u)
+      if (a0 + u < a1) fetch(a0 + u, u);
+    for (int32_t j0 = a0; j0 < a1; j0 += PD) {
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-              const int s = __shfl_sync(0xffffffffu, mySlot[u], lbOf[it]);
-              if (valid[it]) out[outBase[it] + D * s] += v[u][it];
-            }
-            __syncwarp();
+      for (int u = 0; u < PD; ++u) {
+        const int32_t j = j0 + u;
+        if (j < a1) {  // warp-uniform
+          double v[NIT];
+          int sl[NIT];
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            v[it] = vq[u][it];
+            sl[it] = sq[u][it];
           }
+          if (j + PD < a1) fetch(j + PD, u);
+#pragma unroll
+          for (int it = 0; it < NIT; ++it)
+            if (it < NIT - 1 || lane + 32 * it < CHUNK) out[outBase[it] + D * sl[it]] += v[it];
+          __syncwarp();
         }
       }
     }
-    const bool full = G.dbc == IKB_DBC_FULL;
     const int64_t gGlobal = g + P.rowBegin;
     bool rowFixed[D];
     int64_t rowStart[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      rowFixed[i] = G.flags ? (G.flags[dofOf(P.layout, D, P.nNodes, gGlobal, i)] != 0) : false;
-      rowStart[i] = rawRowStart(P, g, i, nnb);
+      rowFixed[i] = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gGlobal, i)] != 0) : false;
+      if (INTERLEAVED)
+        rowStart[i] = (int64_t)DD * b0 + (int64_t)i * rowLen;
+      else
+        rowStart[i] = (int64_t)i * D * P.nBlocks + (int64_t)D * b0;
     }
     for (int idx2 = lane; idx2 < rowLen; idx2 += 32) {
       const int s = idx2 / D, k = idx2 - s * D;
       const int64_t gb = P.nbrIdx[b0 + s];
-      const bool colFixed = G.flags ? (G.flags[dofOf(P.layout, D, P.nNodes, gb, k)] != 0) : false;
-      const int64_t offs = rawEntryOffset(P, s, k, nnb);
+      const bool colFixed = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gb, k)] != 0) : false;
+      const int64_t offs = INTERLEAVED ? (int64_t)idx2 : (int64_t)k * nnb + s;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double v = out[i * rowStride + idx2];
-        if (G.dbc == IKB_DBC_REDUCED) {
+        if (DBC == IKB_DBC_REDUCED) {
           if (!rowFixed[i] && !colFixed)
             G.vals[G.redRowStart[localRowOf(P, g, i)] + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b0 + s, gb, k)] = v;
         } else {
           // Full: zero constrained rows and columns, unit diagonal (simpleassemblers.inl:159-167)
-          if (full && (rowFixed[i] || colFixed)) v = (gb == gGlobal && i == k) ? 1.0 : 0.0;
+          if (DBC == IKB_DBC_FULL && (rowFixed[i] || colFixed)) v = (gb == gGlobal && i == k) ? 1.0 : 0.0;
           G.vals[rowStart[i] + offs] = v;
         }
       }
@@ -164,13 +173,13 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       const int la = (int)(code - e * (uint32_t)N);
       r += G.Rst[(size_t)e * (N * D) + la * D + i];
     }
-    const int64_t rowDof = dofOf(P.layout, D, P.nNodes, g + P.rowBegin, i);
-    const bool rowFixed = G.flags ? (G.flags[rowDof] != 0) : false;
+    const int64_t rowDof = dofOf(LAYOUT, D, P.nNodes, g + P.rowBegin, i);
+    const bool rowFixed = (DBC != IKB_DBC_RAW) ? (G.flags[rowDof] != 0) : false;
     if (G.fext) r -= G.fextScale * G.fext[rowDof];
-    if (G.dbc == IKB_DBC_REDUCED) {
+    if (DBC == IKB_DBC_REDUCED) {
       if (!rowFixed) G.vec[rowDof - G.cbelow[rowDof] - G.redVecOffset] = r;
     } else {
-      if (G.dbc == IKB_DBC_FULL && rowFixed) r = 0.0;  // simpleassemblers.inl:90-92
+      if (DBC == IKB_DBC_FULL && rowFixed) r = 0.0;  // simpleassemblers.inl:90-92
       G.vec[localRowOf(P, g, i)] = r;
     }
   }
