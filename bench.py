@@ -256,8 +256,13 @@ def run_ours(args):
             # element kernel: u, corner coordinates, connectivity read once
             dom, t_dom = "elem_q1_kernel", t_el
             dom_bytes = 8.0 * slab.n_dof + 8.0 * 24 * len(fes) + 4.0 * 8 * len(fes)
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(dom)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (t_dom * 1e-3) / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": dom_bytes / (t_dom * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": dom_bytes / (t_dom * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": t_dom}
         t_peak = asm.timePhase("dfma_peak", DBC, 3)
         fp64_peak = 148 * 16 * 256 * 2048 * 16 / (t_peak * 1e-3) / 1e12
