@@ -208,12 +208,19 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   // one warp per node-row; fewer warps per CTA when the output tile is large (Hex27)
   const int warps = (size_t)G.maxOut * 8 * 8 <= 64 * 1024 ? 8 : 4;
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
-  const unsigned grid = gridFor(nRowNodes, warps);
+  // persistent grid sized from the real occupancy: every SM full, each CTA loops over node-rows
+  const int64_t wantBlocks = gridFor(nRowNodes, warps);
   cudaError_t e = cudaErrorInvalidValue;
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \
     e = cudaFuncSetAttribute(gather_kernel<DIM, NN, MODE, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                              (int)smem);                                                                             \
+    int occ = 1;                                                                                                     \
+    if (e == cudaSuccess)                                                                                            \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_kernel<DIM, NN, MODE, IL>, warps * 32, smem);   \
+    const bool persist = NN * NN * DIM * DIM > 2048;                                                                 \
+    const unsigned grid = (unsigned)(persist ? std::min<int64_t>(wantBlocks, (int64_t)148 * std::max(occ, 1) * 4)   \
+                                             : wantBlocks);                                                          \
     if (e == cudaSuccess) gather_kernel<DIM, NN, MODE, IL><<<grid, warps * 32, smem, h->stream>>>(G);                \
   }
 #define IKB_GATHER2(DIM, NN, MODE)                    \

@@ -65,9 +65,15 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   __syncthreads();
   const PatternView& P = G.P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (g >= P.nRowNodes) return;
   double* out = gsm + (size_t)warp * G.maxOut;
+  // persistent CTAs: the offset table is built once per CTA and reused for many node-rows
+  // (only for the large Q2 tables; for Q1 one node-row per warp keeps the register count and latency lower)
+  constexpr bool PERSIST = (N * CHUNK > 2048);
+  const int64_t warpsTotal = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= P.nRowNodes) return;
+  do {
+  __syncwarp();
   const int32_t b0 = P.nbrPtr[g];
   const int nnb = P.nbrPtr[g + 1] - b0;
   const int rowLen = D * nnb;
@@ -183,6 +189,8 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       G.vec[localRowOf(P, g, i)] = r;
     }
   }
+    g += warpsTotal;
+  } while (PERSIST && g < P.nRowNodes);
 }
 
 // ------------------------------------------------------------------ deterministic reductions
