@@ -34,6 +34,7 @@ SYMBOLS = {
     "ikb_get_constraints_below": [C.c_void_p, C.c_void_p],
     "ikb_element_linear_indices": [C.c_void_p, C.c_int64, C.c_void_p],
     "ikb_set_solution": [C.c_void_p, C.c_void_p],
+    "ikb_set_solution_range": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64],
     "ikb_set_parameter": [C.c_void_p, C.c_double],
     "ikb_set_external_load": [C.c_void_p, C.c_void_p, C.c_int],
     "ikb_assemble": [C.c_void_p, C.c_uint, C.c_int],

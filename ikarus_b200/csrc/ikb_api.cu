@@ -928,6 +928,18 @@ int ikb_set_solution(ikb_handle hh, const double* d) {
   return IKB_OK;
 }
 
+int ikb_set_solution_range(ikb_handle hh, const double* d, int64_t dofBegin, int64_t count) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!d || dofBegin < 0 || count < 0 || dofBegin + count > h->nDof) return fail(h, IKB_EINVAL, "bad dof range");
+  int rc = ensureSolution(h);
+  if (rc) return rc;
+  if (count)
+    IKB_CUDA(h, cudaMemcpyAsync(h->U.p + dofBegin, d, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->stateVersion++;
+  return IKB_OK;
+}
+
 int ikb_get_solution(ikb_handle hh, double* d) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;

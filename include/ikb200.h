@@ -97,6 +97,9 @@ int ikb_element_linear_indices(ikb_handle h, int64_t elem, int64_t* out);
 /* ---- per-solve state ------------------------------------------------------------ */
 /* FERequirements::globalSolution()/parameter() (finiteelements/ferequirements.hh:222-407) */
 int ikb_set_solution(ikb_handle h, const double* d);
+/* Partial upload: d[0..count) -> resident solution[dof_begin .. dof_begin+count).  An element-partitioned rank only
+ * needs the dofs of its owned + ghost node layers. */
+int ikb_set_solution_range(ikb_handle h, const double* d, int64_t dof_begin, int64_t count);
 int ikb_set_parameter(ikb_handle h, double lambda);
 /* Host-sampled volume/Neumann/point loads (mechanics/loads/volume.hh:67-106,
  * loads/traction.hh:70-138): R = F_int - s*fext, E -= s*fext.d with s = lambda when
