@@ -79,8 +79,8 @@ struct EasCfg {
   static constexpr int GPS0 = O_TS + S;
   static constexpr int GPS = GPS0 + ((5 - GPS0 % 4) % 4);
   static constexpr int REC0 = N * GPS;
-  // D [M][M] lives behind the records; L/Z [M][ND], Rt [M], partial [N][M] reuse the record area
-  static constexpr int SCR = M * ND + M + N * M;
+  // D [M][M] lives behind the records; the condensation scratch reuses the record area
+  static constexpr int SCR = M * ND + M + N * M + M;  // Y [M][ND], Rt [M], partial [N][M], reciprocal pivots [M]
   static constexpr int ES0 = (REC0 > SCR ? REC0 : SCR) + M * M;
   static constexpr int ES = ES0 + ((N % 16) - (ES0 % 16) + 16) % 16;
   static constexpr int EPW = 32 / N;
@@ -136,12 +136,12 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   const int tid = threadIdx.x;
   const int el = tid / N;
   const int t = tid % N;
-  const int64_t e = (int64_t)blockIdx.x * C::EPC + el;
-  const bool active = e < A.nElem;
+  const int64_t eRaw = (int64_t)blockIdx.x * C::EPC + el;
+  // lane groups past the last element recompute the last element (their global writes are suppressed) so that
+  // every warp-level barrier below can be a plain full-warp __syncwarp()
+  const bool active = eRaw < A.nElem;
+  const int64_t e = active ? eRaw : A.nElem - 1;
   double* rec = smem + (size_t)el * C::ES;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned grpMask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (lane / N * N));
-  if (!active) return;  // whole N-lane groups leave together; group syncs below use grpMask
 
   // ------------------------------------------------------------------ phase 1: Gauss point t
   {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       gp[C::O_TS + r] = w * s;
     }
   }
-  __syncwarp(grpMask);
+  __syncwarp();
 
   const int a = t;
   constexpr int NK = C::KMAX + 1;
@@ -446,8 +446,10 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
       double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
+      if (active) {
 #pragma unroll
-      for (int q = 0; q < DD; ++q) dst[q] = acc[k][q];
+        for (int q = 0; q < DD; ++q) dst[q] = acc[k][q];
+      }
     }
   }
 
@@ -518,10 +520,10 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
       for (int c = 0; c < D; ++c) Lr[j][c] = fma(sm[T::mono(j)], QB[T::row(j)][c], Lr[j][c]);
   }
-  __syncwarp(grpMask);  // all passes done: the record area becomes condensation scratch
+  __syncwarp();  // all passes done: the record area becomes condensation scratch
 
-  double* Lm = rec;                 // [M][ND]  -> Z = D^-1 L in place
-  double* Rm = Lm + M * ND;         // [M]      -> D^-1 Rt in place
+  double* Lm = rec;                 // [M][ND]  L, overwritten by Y = Lf^-1 L (D = Lf diag(d) Lf^T)
+  double* Rm = Lm + M * ND;         // [M]      Rt -> Lf^-1 Rt (assembly) / D^-1 (Rt + L du) (update)
   double* Pm = Rm + M;              // [N][M]   partial sums of L du (update mode)
 #pragma unroll
   for (int jj = 0; jj < C::ROWS; ++jj) {
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       Pm[a * M + j] = s;
     }
   }
-  __syncwarp(grpMask);
+  __syncwarp();
   if (EA.updateMode) {
     // Rt_j + (L du)_j, node contributions added in node order
 #pragma unroll
@@ -558,54 +560,90 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
         Rm[j] = s;
       }
     }
-    __syncwarp(grpMask);
+    __syncwarp();
   }
 
   // ------------------------------------------------------------------ cooperative LDL^T (lower triangle, in place)
+  // The reciprocal of pivot k+1 is computed by the owner of row k+1 while the others scale column k, so no
+  // thread waits on a division inside the elimination, and the solves below need no divisions at all.
+  double* invd = Pm + N * M;  // [M]
+  if (a == 0) invd[0] = 1.0 / Dm[0];
+  __syncwarp();
 #pragma unroll 1
   for (int k = 0; k < M; ++k) {
-    const double idk = 1.0 / Dm[k * M + k];
+    const double idk = invd[k];
     for (int i = k + 1 + a; i < M; i += N) {
       const double lik = Dm[i * M + k] * idk;
+#pragma unroll 4
       for (int j = k + 1; j <= i; ++j) Dm[i * M + j] = fma(-lik, Dm[j * M + k], Dm[i * M + j]);
     }
-    __syncwarp(grpMask);
+    __syncwarp();
     for (int i = k + 1 + a; i < M; i += N) Dm[i * M + k] *= idk;
-    __syncwarp(grpMask);
+    if (k + 1 < M && ((k + 1) % N) == a) invd[k + 1] = 1.0 / Dm[(k + 1) * M + k + 1];
+    __syncwarp();
   }
-  // ------------------------------------------------------------------ solves: thread a owns the columns of node a; thread N-1 also Rt
-  auto solveColumn = [&](double* col, int stride) {
-    for (int i = 1; i < M; ++i) {
-      double s = col[i * stride];
-      for (int j = 0; j < i; ++j) s = fma(-Dm[i * M + j], col[j * stride], s);
-      col[i * stride] = s;
-    }
-    for (int i = 0; i < M; ++i) col[i * stride] /= Dm[i * M + i];
-    for (int i = M - 2; i >= 0; --i) {
-      double s = col[i * stride];
-      for (int j = i + 1; j < M; ++j) s = fma(-Dm[j * M + i], col[j * stride], s);
-      col[i * stride] = s;
-    }
-  };
+  // ------------------------------------------------------------------ solves
+  // With D = Lf diag(d) Lf^T:  L^T D^-1 L = Y^T diag(1/d) Y  and  L^T D^-1 Rt = Y^T diag(1/d) y_R  with
+  // Y = Lf^-1 L, y_R = Lf^-1 Rt, so the assembly only needs FORWARD substitutions.  Thread a does the D columns
+  // of node a together, fully unrolled in registers (each factor entry is loaded once for D columns).
+  double z[M][D];
   if (!EA.updateMode) {
-#pragma unroll 1
-    for (int c = 0; c < D; ++c) solveColumn(Lm + a * D + c, ND);
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) z[i][c] = Lr[i][c];
+#pragma unroll
+    for (int i = 1; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        const double l = Dm[i * M + j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) z[i][c] = fma(-l, z[j][c], z[i][c]);
+      }
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) Lm[i * ND + a * D + c] = z[i][c];
   }
-  if (a == N - 1) solveColumn(Rm, 1);
-  __syncwarp(grpMask);
+  if (a == N - 1) {
+    double zr[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) zr[i] = Rm[i];
+#pragma unroll
+    for (int i = 1; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < i; ++j) zr[i] = fma(-Dm[i * M + j], zr[j], zr[i]);
+    if (EA.updateMode) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) zr[i] *= invd[i];
+#pragma unroll
+      for (int i = M - 2; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) zr[i] = fma(-Dm[j * M + i], zr[j], zr[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) Rm[i] = zr[i];
+  }
+  __syncwarp();
 
   if (EA.updateMode) {
     // alpha -= D^-1 (Rt + L du)     (enhancedassumedstrains.hh:243)
 #pragma unroll
     for (int jj = 0; jj < C::ROWS; ++jj) {
       const int j = a + jj * N;
-      if (j < M) EA.alpha[(size_t)e * M + j] -= Rm[j];
+      if (j < M && active) EA.alpha[(size_t)e * M + j] -= Rm[j];
     }
     return;
   }
 
   // ------------------------------------------------------------------ condensation
-  // K_ab -= L_a^T Z_b ; R_a -= L_a^T (D^-1 Rt)   (enhancedassumedstrains.hh:292-296, 341-345)
+  // K_ab -= Y_a^T diag(1/d) Y_b ; R_a -= Y_a^T diag(1/d) y_R   (enhancedassumedstrains.hh:292-296, 341-345)
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const double id = invd[j];
+#pragma unroll
+    for (int c = 0; c < D; ++c) z[j][c] *= id;
+  }
   if (A.what & IKB_MATRIX) {
     double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll 1
@@ -624,20 +662,22 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-          for (int c = 0; c < D; ++c) blk[i * D + c] = fma(-Lr[j][i], zb[c], blk[i * D + c]);
+          for (int c = 0; c < D; ++c) blk[i * D + c] = fma(-z[j][i], zb[c], blk[i * D + c]);
       }
+      if (active) {
 #pragma unroll
-      for (int i = 0; i < D; ++i)
+        for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) dst[i * D + j] = (k == 0 && i > j) ? blk[j * D + i] : blk[i * D + j];
+          for (int j = 0; j < D; ++j) dst[i * D + j] = (k == 0 && i > j) ? blk[j * D + i] : blk[i * D + j];
+      }
     }
   }
-  if (A.what & IKB_VECTOR) {
+  if ((A.what & IKB_VECTOR) && active) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      const double z = Rm[j];
+      const double zR = Rm[j];
 #pragma unroll
-      for (int i = 0; i < D; ++i) Ra[i] = fma(-Lr[j][i], z, Ra[i]);
+      for (int i = 0; i < D; ++i) Ra[i] = fma(-z[j][i], zR, Ra[i]);
     }
 #pragma unroll
     for (int i = 0; i < D; ++i) A.Rst[(size_t)e * ND + a * D + i] = Ra[i];
