@@ -5,8 +5,8 @@ Host-side mirror of the reference's assembler interface over the C-ABI in includ
 from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, DeviceMatrix, FERequirements,  # noqa: F401
                         MatrixAffordance, ScalarAffordance, SparseFlatAssembler, VectorAffordance, elastoStatics,
                         makeDenseFlatAssembler, makeSparseFlatAssembler)
-from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, nonLinearElastic,  # noqa: F401
-                 planeStrain, skills, toLamesFirstParameterAndShearModulus)
+from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, neumannBoundaryLoad,  # noqa: F401
+                 nonLinearElastic, planeStrain, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
 from .solvers import (ControlInformation, DeviceLinearSolver, LoadControl, LoadControlConfig, NewtonRaphson,  # noqa: F401
                       NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings)
 

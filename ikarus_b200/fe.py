@@ -79,6 +79,12 @@ class _VolumeLoad:
     fn: Callable  # f(x[dim], lambda) -> force density [dim]
 
 
+@dataclass(frozen=True)
+class _NeumannLoad:
+    fn: Callable  # t(x[dim], lambda) -> traction [dim]
+    faces: tuple  # ((element index, face id), ...); DUNE cube faces: 2k -> xi_k = 0, 2k+1 -> xi_k = 1
+
+
 def linearElastic(mat):
     """mechanics/linearelastic.hh linearElastic(mat): small strains; needs a linear-strain material."""
     if mat.strain != capi.STRAIN_LINEAR:
@@ -103,6 +109,12 @@ def eas(numberOfInternalVariables=0, enhanced="GreenLagrangeStrain"):
 def volumeLoad(fn):
     """mechanics/loads/volume.hh volumeLoad<dim>(f): f(x, lambda) sampled on the host."""
     return _VolumeLoad(fn)
+
+
+def neumannBoundaryLoad(faces, fn):
+    """mechanics/loads/traction.hh neumannBoundaryLoad(&patch, t): t(x, lambda) on the boundary faces of the patch,
+    given here as (element, face) pairs; sampled on the host with the face rule of order = basis order (:122)."""
+    return _NeumannLoad(fn, tuple((int(e), int(f)) for e, f in faces))
 
 
 def skills(*s):
@@ -167,6 +179,9 @@ class FEContainer:
     def sample_external_load(self, lam=1.0):
         """R_e -= N_i f(x_gp, lambda) detJ w summed over elements (loads/volume.hh:86-106) -> fext[n_dof]."""
         fext = np.zeros(self.n_dof)
+        for s in self.loads:
+            if isinstance(s, _NeumannLoad):
+                self._sample_traction(s, lam, fext)
         vl = [s for s in self.loads if isinstance(s, _VolumeLoad)]
         if not vl:
             return fext
@@ -191,6 +206,49 @@ class FEContainer:
         return fext
 
 
+def _face_points(dim, order, face):
+    """Quadrature points (in element reference coordinates), weights and the in-face directions of a cube face for the
+    Gauss rule of polynomial order `order` (1 -> midpoint, 2 -> 2 points per direction)."""
+    import itertools
+    k, side = face // 2, face % 2
+    x1, w1 = _gauss01(order // 2 + 1)
+    dirs = [j for j in range(dim) if j != k]
+    pts = []
+    for idx in itertools.product(range(len(x1)), repeat=dim - 1):
+        xi = np.zeros(dim)
+        xi[k] = float(side)
+        w = 1.0
+        for j, i in zip(dirs, idx):
+            xi[j] = x1[i]
+            w *= w1[i]
+        pts.append((xi, w))
+    return pts, dirs
+
+
+def _sample_traction_impl(self, load, lam, fext):
+    """R_e -= N_i t(x, lambda) w detJ_face over the listed faces (loads/traction.hh:107-138)."""
+    d, order = self.dim, self.order
+    for e, face in load.faces:
+        X = self.corner_coords[e]
+        pts, dirs = _face_points(d, order, face)
+        for xi, w in pts:
+            N = _shape(d, order, xi)
+            Ng = _shape(d, 1, xi)
+            dNg = _dshape_q1(d, xi)
+            Jt = np.einsum("ci,cj->ij", dNg, X)  # Jt[i][j] = dx_j/dxi_i
+            if d == 2:
+                area = np.linalg.norm(Jt[dirs[0]])
+            else:
+                area = np.linalg.norm(np.cross(Jt[dirs[0]], Jt[dirs[1]]))
+            x = Ng @ X
+            t = np.asarray(load.fn(x, lam), float)
+            contrib = (N[:, None] * t[None, :] * (w * area)).reshape(-1)
+            np.add.at(fext, self.elem_dofs[e], contrib)
+
+
+FEContainer._sample_traction = _sample_traction_impl
+
+
 def makeFE(basis, sk, corner_coords=None, elem_dofs=None):
     """makeFE(basisHandler, skills(...)) (finiteelements/fefactory.hh:67-72) followed by bind over all
     grid elements.  `basis` is a dict/obj with dim, order, n_dof."""
@@ -199,7 +257,7 @@ def makeFE(basis, sk, corner_coords=None, elem_dofs=None):
     if len(solid) != 1:
         raise TypeError("exactly one solid skill (linearElastic / nonLinearElastic) is required")
     e = [s for s in sk if isinstance(s, _EAS)]
-    loads = tuple(s for s in sk if isinstance(s, _VolumeLoad))
+    loads = tuple(s for s in sk if isinstance(s, (_VolumeLoad, _NeumannLoad)))
     mat = solid[0].material
     if dim == 2 and not mat.reduced:
         raise TypeError("2D elements need a reduced material (planeStrain)")
