@@ -97,47 +97,47 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
     }
     __syncwarp();
     const int elemStride = G.npair * DD;
-    // software pipeline, depth PD: the loads of elements j+1..j+PD are in flight while element j is added to the tile
-    constexpr int PD = 1;
-    double vq[PD][NIT];
-    int sq[PD][NIT];
-    auto fetch = [&](int32_t j, int slotIdx) {
-      const uint32_t code = G.adjCode[j];
+    // Two-stage software pipeline with explicit ping-pong buffers (no register copies): while element j is added
+    // to the tile, the staged values and the slot bytes of element j+1 are already in flight.  The N slot bytes of
+    // an element are fetched by lanes 0..N-1 with one load and distributed with shuffles.
+    int shiftOf[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) shiftOf[it] = lbOf[it];
+    const int16_t* tabLane = offTab + lane;
+    const double* __restrict__ Kst = G.Kst;
+    const uint8_t* __restrict__ slotTab = G.slotTab;
+    const uint32_t* __restrict__ adjCode = G.adjCode;
+    auto fetch = [&](int32_t j, double (&v)[NIT], int& slotByte) {
+      const uint32_t code = adjCode[j];
       const uint32_t e = code / (uint32_t)N;
-      const int la = (int)(code - e * (uint32_t)N);
-      const double* Ke = G.Kst + (size_t)e * elemStride;
-      const int16_t* tab = offTab + la * CHUNK + lane;
-      const uint8_t* st = G.slotTab + (size_t)j * N;
+      const uint32_t la = code - e * (uint32_t)N;
+      const double* Ke = Kst + (size_t)e * (unsigned)elemStride;
+      const int16_t* tab = tabLane + la * CHUNK;
+      slotByte = lane < N ? (int)slotTab[(size_t)j * N + lane] : 0;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        if (it < NIT - 1 || lane + 32 * it < CHUNK) v[it] = Ke[tab[32 * it]];
+    };
+    auto accumulate = [&](const double (&v)[NIT], int slotByte) {
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
-        if (it < NIT - 1 || lane + 32 * it < CHUNK) {
-          vq[slotIdx][it] = Ke[tab[32 * it]];
-          sq[slotIdx][it] = st[lbOf[it]];
-        }
+        const int sl = __shfl_sync(0xffffffffu, slotByte, shiftOf[it]);
+        if (it < NIT - 1 || lane + 32 * it < CHUNK) out[outBase[it] + D * sl] += v[it];
       }
+      __syncwarp();
     };
-#pragma unroll
-    for (int u = 0; u < PD; ++u)
-      if (a0 + u < a1) fetch(a0 + u, u);
-    for (int32_t j0 = a0; j0 < a1; j0 += PD) {
-#pragma unroll
-      for (int u = 0; u < PD; ++u) {
-        const int32_t j = j0 + u;
-        if (j < a1) {  // warp-uniform
-          double v[NIT];
-          int sl[NIT];
-#pragma unroll
-          for (int it = 0; it < NIT; ++it) {
-            v[it] = vq[u][it];
-            sl[it] = sq[u][it];
-          }
-          if (j + PD < a1) fetch(j + PD, u);
-#pragma unroll
-          for (int it = 0; it < NIT; ++it)
-            if (it < NIT - 1 || lane + 32 * it < CHUNK) out[outBase[it] + D * sl[it]] += v[it];
-          __syncwarp();
-        }
-      }
+    double vA[NIT], vB[NIT];
+    int sA = 0, sB = 0;
+    int32_t j = a0;
+    if (j < a1) fetch(j, vA, sA);
+    while (j < a1) {
+      if (j + 1 < a1) fetch(j + 1, vB, sB);
+      accumulate(vA, sA);
+      ++j;
+      if (j >= a1) break;
+      if (j + 1 < a1) fetch(j + 1, vA, sA);
+      accumulate(vB, sB);
+      ++j;
     }
     const int64_t gGlobal = g + P.rowBegin;
     bool rowFixed[D];
