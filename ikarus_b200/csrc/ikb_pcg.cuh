@@ -107,9 +107,13 @@ __global__ void __launch_bounds__(256) spmv_node_dot_kernel(PatternView P, const
         k = j / nnb;
         slot = j - k * nnb;
       }
-      const double xv = x[dofOf(P.layout, D, P.nNodes, P.nbrIdx[b0 + slot], k)];
+      // the matrix is streamed exactly once: keep it out of L1 (__ldcs) so the gathered x stays resident there
+      double av[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) s[i] = fma(vals[start[i] + j], xv, s[i]);
+      for (int i = 0; i < D; ++i) av[i] = __ldcs(vals + start[i] + j);
+      const double xv = __ldg(x + dofOf(P.layout, D, P.nNodes, __ldg(P.nbrIdx + b0 + slot), k));
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = fma(av[i], xv, s[i]);
     }
 #pragma unroll
     for (int i = 0; i < D; ++i)
