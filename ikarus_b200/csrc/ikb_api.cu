@@ -504,6 +504,7 @@ int ikb_destroy(ikb_handle hh) {
   if (h->comm) nccl().commDestroy(h->comm);
   h->cgPglob.release();
   h->cgState.release();
+  if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
   h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
   cudaStreamDestroy(h->stream);
@@ -1249,7 +1250,7 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
     double* rzPartial = h->scratch.p + 2 * RED_BLOCKS;
     CgState* hs = reinterpret_cast<CgState*>(h->hostScal);
     const int batch = 32;
-    while (true) {
+    auto enqueueBatch = [&]() {
       for (int b = 0; b < batch; ++b) {
         if (h->dim == 3)
           spmv_node_dot_kernel<3><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
@@ -1260,8 +1261,33 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
         cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, pqPartial, RED_BLOCKS, h->cgP.p, h->cgQ.p,
                                                              h->cgDinv.p, h->cgX.p, h->cgR.p, h->cgZ.p, rzPartial);
         cg2_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, rzPartial, RED_BLOCKS, h->cgZ.p, h->cgP.p, arrive);
-        h->launches += 3;
       }
+    };
+    // a batch is captured once into a CUDA graph (all arguments are resident pointers) and replayed
+    if (!h->cgGraph || h->cgGraphKey[0] != h->vals[dbc].p || h->cgGraphKey[1] != h->cgP.p ||
+        h->cgGraphKey[2] != h->nbrIdx.p) {
+      if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
+      h->cgGraph = nullptr;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueueBatch();
+        if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
+          if (cudaGraphInstantiate(&h->cgGraph, graph, 0) != cudaSuccess) h->cgGraph = nullptr;
+          cudaGraphDestroy(graph);
+        }
+      }
+      cudaGetLastError();
+      h->cgGraphKey[0] = h->vals[dbc].p;
+      h->cgGraphKey[1] = h->cgP.p;
+      h->cgGraphKey[2] = h->nbrIdx.p;
+    }
+    while (true) {
+      if (h->cgGraph) {
+        IKB_CUDA(h, cudaGraphLaunch(h->cgGraph, h->stream));
+      } else {
+        enqueueBatch();
+      }
+      h->launches += 3 * batch;
       IKB_CUDA(h, cudaGetLastError());
       IKB_CUDA(h, cudaMemcpyAsync(hs, st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
       IKB_CUDA(h, cudaStreamSynchronize(h->stream));

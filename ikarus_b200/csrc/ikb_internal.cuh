@@ -134,6 +134,8 @@ struct Handle {
   DevBuf<double> cgScal;       // device scalars
   double* hostScal = nullptr;  // pinned
   DevBuf<uint8_t> cgState;     // CgState + arrival counter of the sync-free PCG
+  cudaGraphExec_t cgGraph = nullptr;  // one captured batch of PCG iterations
+  const void* cgGraphKey[3] = {nullptr, nullptr, nullptr};
 
   // NCCL (element-partitioned runs)
   void* comm = nullptr;
