@@ -57,6 +57,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   A.Rst = h->Rst.p;
   A.Est = h->Est.p;
   A.errFlag = h->errFlag.p;
+  A.Lap = h->Lap.p;
   A.nElem = h->nElem;
   A.nNodes = h->nNodes;
   A.layout = h->layout;
@@ -477,6 +478,7 @@ int ikb_destroy(ikb_handle hh) {
   if (!h) return IKB_EINVAL;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  h->Lap.release();
   for (auto* b : {&h->X, &h->U, &h->Fext, &h->Corr, &h->Kst, &h->Rst, &h->Est, &h->scratch, &h->alpha, &h->cgR, &h->cgZ,
                   &h->cgP, &h->cgQ, &h->cgX, &h->cgDinv, &h->cgB, &h->cgScal})
     b->release();
@@ -586,6 +588,15 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->patternBuilt = false;
   h->reducedBuilt = false;
   h->stateVersion++;
+  h->Lap.release();
+  if (h->order == 1 && h->easM == 0 && h->form != FORM_SVK) {
+    IKB_CUDA(h, h->Lap.alloc((size_t)h->npair * ne));
+    if (D == 3)
+      lap_q1_kernel<3><<<gridFor(ne, 128), 128, 0, h->stream>>>(h->X.p, ne, h->Lap.p);
+    else
+      lap_q1_kernel<2><<<gridFor(ne, 128), 128, 0, h->stream>>>(h->X.p, ne, h->Lap.p);
+    IKB_LAUNCH_CHECK(h);
+  }
   if (h->easM) {
     IKB_CUDA(h, h->alpha.alloc((size_t)ne * h->easM));
     IKB_CUDA(h, cudaMemsetAsync(h->alpha.p, 0, h->alpha.bytes(), h->stream));  // initializeState (:373-376)

@@ -34,6 +34,7 @@ struct ElemArgs {
   double* Kst;             // [nElem][NPAIR][D*D]
   double* Rst;             // [nElem][N*D]
   double* Est;             // [nElem]
+  const double* Lap;       // [NPAIR][nElem] sum_g w_g grad N_a . grad N_b (reference geometry only), may be null
   int32_t* errFlag;
   int64_t nElem;
   int64_t nNodes;
@@ -112,7 +113,7 @@ __device__ __forceinline__ constexpr int symIdx(int i, int j) {
   return i * D - i * (i - 1) / 2 + (j - i);
 }
 
-template <int D, int FORM>
+template <int D, int FORM, bool USELAP>
 __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 56 * 1024) ? 2 : 4)
     elem_q1_kernel(ElemArgs A) {
   using C = Q1Cfg<D, FORM>;
@@ -354,7 +355,9 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
       for (int j = 0; j < D; ++j) Ra[i] = fma(sc[C::O_WP + i * D + j], ga[j], Ra[i]);
 
     double hs[D], sg[D];  // third/fourth-term helpers of node a
-    if constexpr (FORM == FORM_LE) {
+    if constexpr (USELAP) {
+      // mu * sum_g w_g (g_a.g_b) does not depend on the displacements: it comes from the precomputed table
+    } else if constexpr (FORM == FORM_LE) {
 #pragma unroll
       for (int i = 0; i < D; ++i) hs[i] = c2 * ga[i];
     } else if constexpr (FORM == FORM_NH) {
@@ -376,14 +379,15 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
       double mb[D], gb[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        gb[i] = vG[i * N + b];
+        if constexpr (!USELAP || FORM == FORM_LE) gb[i] = vG[i * N + b];
         mb[i] = (FORM == FORM_LE) ? gb[i] : vM[i * N + b];
       }
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < D; ++j) acc[k][i * D + j] = fma(p1[i], mb[j], fma(mb[i], p2[j], acc[k][i * D + j]));
-      if constexpr (FORM == FORM_SVK) {
+      if constexpr (USELAP) {
+      } else if constexpr (FORM == FORM_SVK) {
         double cab = 0.0, sab = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -404,6 +408,17 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
 #pragma unroll
         for (int i = 0; i < D; ++i) acc[k][i * D + i] += dab;
       }
+    }
+  }
+
+  if constexpr (USELAP) {
+    const double mu = A.mu;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if (k == C::KMAX && a >= N / 2) break;
+      const double lap = mu * __ldg(A.Lap + (size_t)(k * N + a) * A.nElem + e);
+#pragma unroll
+      for (int i = 0; i < D; ++i) acc[k][i * D + i] += lap;
     }
   }
 
@@ -443,20 +458,104 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   }
 }
 
-template <int D, int FORM>
-cudaError_t launchElemQ1(const ElemArgs& A, cudaStream_t st) {
+template <int D, int FORM, bool USELAP>
+cudaError_t launchElemQ1Impl(const ElemArgs& A, cudaStream_t st) {
   using C = Q1Cfg<D, FORM>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(elem_q1_kernel<D, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(elem_q1_kernel<D, FORM, USELAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const unsigned grid = (unsigned)((A.nElem + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
-  elem_q1_kernel<D, FORM><<<grid, C::TPB, C::SMEM, st>>>(A);
+  elem_q1_kernel<D, FORM, USELAP><<<grid, C::TPB, C::SMEM, st>>>(A);
   return cudaGetLastError();
+}
+
+template <int D, int FORM>
+cudaError_t launchElemQ1(const ElemArgs& A, cudaStream_t st) {
+  if constexpr (FORM != FORM_SVK) {
+    if (A.Lap) return launchElemQ1Impl<D, FORM, true>(A, st);
+  }
+  return launchElemQ1Impl<D, FORM, false>(A, st);
+}
+
+// One-time table for the displacement-independent part of the tangent of Q1 elements:
+//   Lap[p][e] = sum_g w_g detJ_g  grad N_a . grad N_b,   p = k*N + a, b = (a+k) mod N
+// (the mu (grad N_a . grad N_b) I term of NeoHooke / LinearElasticity, see the header comment).
+template <int D>
+__global__ void __launch_bounds__(128) lap_q1_kernel(const double* __restrict__ X, int64_t nElem, double* Lap) {
+  constexpr int N = 1 << D;
+  constexpr int KMAX = N / 2;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nElem) return;
+  double x[N][D];
+#pragma unroll
+  for (int c = 0; c < N; ++c)
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[c][k] = X[(size_t)(c * D + k) * nElem + e];
+  double lap[KMAX + 1][N];
+#pragma unroll
+  for (int k = 0; k <= KMAX; ++k)
+#pragma unroll
+    for (int a = 0; a < N; ++a) lap[k][a] = 0.0;
+  const double lo = 0.5 - 0.28867513459481287, hi = 0.5 + 0.28867513459481287;
+#pragma unroll 1
+  for (int g = 0; g < N; ++g) {
+    double xi[D], om[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      xi[k] = ((g >> k) & 1) ? hi : lo;
+      om[k] = 1.0 - xi[k];
+    }
+    double dN[N][D], Jt[D][D], Ji[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) Jt[i][k] = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double v = ((c >> i) & 1) ? 1.0 : -1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+          if (k != i) v *= ((c >> k) & 1) ? xi[k] : om[k];
+        dN[c][i] = v;
+#pragma unroll
+        for (int k = 0; k < D; ++k) Jt[i][k] = fma(v, x[c][k], Jt[i][k]);
+      }
+    double w = fabs(invSmall<D>(Jt, Ji));
+#pragma unroll
+    for (int k = 0; k < D; ++k) w *= 0.5;
+    double gr[N][D];
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) s = fma(Ji[j][i], dN[a][i], s);
+        gr[a][j] = s;
+      }
+#pragma unroll
+    for (int k = 0; k <= KMAX; ++k)
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        const int b = (a + k) & (N - 1);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) s = fma(gr[a][i], gr[b][i], s);
+        lap[k][a] = fma(w, s, lap[k][a]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k <= KMAX; ++k)
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+      if (!(k == KMAX && a >= N / 2)) Lap[(size_t)(k * N + a) * nElem + e] = lap[k][a];
 }
 
 }  // namespace ikb

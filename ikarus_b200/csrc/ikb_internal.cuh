@@ -79,6 +79,7 @@ struct Handle {
   // mesh
   DevBuf<double> X;         // [nc*dim][nElem]  corner coordinates, element fastest
   DevBuf<int32_t> elemNode; // [nn][nElem]      global node ids, element fastest
+  DevBuf<double> Lap;       // [npair][nElem] displacement-independent Laplacian table of Q1 elements
   bool meshUploaded = false;
 
   // row ownership (multi-GPU); defaults to all nodes
