@@ -197,8 +197,9 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   G.vec = (what & IKB_VECTOR) ? h->vec[dbc].p : nullptr;
   G.dbc = dbc;
   G.npair = h->npair;
-  // tile rows are padded to a stride == D (mod 16) doubles
-  G.maxOut = h->dim * (h->dim * std::max(h->maxNbr, 1) + 16);
+  // tile rows are padded to a stride == D (mod 16) doubles; Q2 kinds gather one scalar row per warp (GatherCfg)
+  const int rs = h->nn > 8 ? 1 : h->dim;
+  G.maxOut = rs * (h->dim * std::max(h->maxNbr, 1) + 16);
   G.freeCnt = h->freeCnt.p;
   G.freeTot = h->freeTot.p;
   G.redRowStart = h->redRowStart.p;
@@ -206,11 +207,10 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   G.redVecOffset = 0;
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
-  // one warp per node-row; fewer warps per CTA when the output tile is large (Hex27)
-  const int warps = (size_t)G.maxOut * 8 * 8 <= 64 * 1024 ? 8 : 4;
+  const int warps = 8;
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
-  // persistent grid sized from the real occupancy: every SM full, each CTA loops over node-rows
-  const int64_t wantBlocks = gridFor(nRowNodes, warps);
+  // one warp per work unit (node-row, or scalar row for Q2)
+  const int64_t wantBlocks = gridFor(nRowNodes * (h->dim / rs), warps);
   cudaError_t e = cudaErrorInvalidValue;
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \

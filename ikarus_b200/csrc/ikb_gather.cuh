@@ -44,36 +44,52 @@ struct GatherArgs {
 // FlatInterleaved dofs) is written once, coalesced, with the Dirichlet mode applied.
 // The inner loop is table driven: offTab[la][idx] is the offset of value idx of chunk la inside the
 // symmetric-packed staged K_e (transposition folded in), slots come from one byte load per element node.
+// RS = scalar rows handled per warp: D for Q1 (the whole node-row), 1 for Q2 (one scalar row per warp: the Hex27
+// tile of a whole node-row is 9 KB and would limit the occupancy to 16 warps per SM).
+template <int D, int N>
+struct GatherCfg {
+  static constexpr int RS = (N > 8) ? 1 : D;
+  static constexpr int NU = D / RS;            // work units per node-row
+  static constexpr int CHUNK = N * RS * D;     // values of one element that go into one unit
+  static constexpr int NIT = (CHUNK + 31) / 32;
+  static constexpr bool PERSIST = (N * CHUNK > 2048);
+};
+
 template <int D, int N, int DBC, bool INTERLEAVED>
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
+  using Cfg = GatherCfg<D, N>;
   constexpr int DD = D * D;
-  constexpr int CHUNK = N * DD;
-  constexpr int NIT = (CHUNK + 31) / 32;
+  constexpr int RS = Cfg::RS, NU = Cfg::NU, CHUNK = Cfg::CHUNK, NIT = Cfg::NIT;
   constexpr int HALF = N / 2;
   constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
   extern __shared__ double gsm[];
+  // offTab[la][idx]: offset of value idx = (lb, ii, k) of chunk la inside the symmetric-packed staged K_e for
+  // ii = row 0 of the unit, plus bit 14 = "stored directly" (then a further row i0 adds i0*D, else i0)
   __shared__ int16_t offTab[N * CHUNK];
   for (int t = threadIdx.x; t < N * CHUNK; t += blockDim.x) {
     const int la = t / CHUNK, idx = t - la * CHUNK;
-    const int lb = idx / DD, q = idx - lb * DD;
+    const int lb = idx / (RS * D), q = idx - lb * (RS * D);
     const int i = q / D, k = q - i * D;
     int k1 = lb - la;
     if (k1 < 0) k1 += N;
     const bool direct = (N & 1) ? (k1 <= HALF) : (k1 < HALF || (k1 == HALF && la < HALF));
-    offTab[t] = (int16_t)(direct ? (k1 * N + la) * DD + q : ((N - k1) * N + lb) * DD + k * D + i);
+    const int off = direct ? (k1 * N + la) * DD + i * D + k : ((N - k1) * N + lb) * DD + k * D + i;
+    offTab[t] = (int16_t)(off | (direct ? 0x4000 : 0));
   }
   __syncthreads();
   const PatternView& P = G.P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* out = gsm + (size_t)warp * G.maxOut;
-  // persistent CTAs: the offset table is built once per CTA and reused for many node-rows
-  // (only for the large Q2 tables; for Q1 one node-row per warp keeps the register count and latency lower)
-  constexpr bool PERSIST = (N * CHUNK > 2048);
+  // persistent CTAs for the large Q2 tables: the offset table is built once per CTA and reused for many units
+  constexpr bool PERSIST = Cfg::PERSIST;
   const int64_t warpsTotal = (int64_t)gridDim.x * (blockDim.x >> 5);
-  int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (g >= P.nRowNodes) return;
+  const int64_t nUnits = P.nRowNodes * NU;
+  int64_t unit = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (unit >= nUnits) return;
   do {
   __syncwarp();
+  const int64_t g = unit / NU;
+  const int i0 = (int)(unit - g * NU) * RS;
   const int32_t b0 = P.nbrPtr[g];
   const int nnb = P.nbrPtr[g + 1] - b0;
   const int rowLen = D * nnb;
@@ -82,15 +98,15 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   const int32_t a0 = G.adjPtr[g], a1 = G.adjPtr[g + 1];
 
   if (G.vals) {
-    for (int idx = lane; idx < D * rowStride; idx += 32) out[idx] = 0.0;
+    for (int idx = lane; idx < RS * rowStride; idx += 32) out[idx] = 0.0;
     // element-independent lane constants: value idx = lane + 32*it of a chunk belongs to element node lbOf[it]
     int lbOf[NIT], outBase[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int idx = lane + 32 * it;
       const int idc = idx < CHUNK ? idx : 0;
-      const int lb = idc / DD;
-      const int q = idc - lb * DD;
+      const int lb = idc / (RS * D);
+      const int q = idc - lb * (RS * D);
       const int i = q / D, k = q - i * D;
       lbOf[it] = lb;
       outBase[it] = i * rowStride + k;
@@ -100,9 +116,6 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
     // Two-stage software pipeline with explicit ping-pong buffers (no register copies): while element j is added
     // to the tile, the staged values and the slot bytes of element j+1 are already in flight.  The N slot bytes of
     // an element are fetched by lanes 0..N-1 with one load and distributed with shuffles.
-    int shiftOf[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) shiftOf[it] = lbOf[it];
     const int16_t* tabLane = offTab + lane;
     const double* __restrict__ Kst = G.Kst;
     const uint8_t* __restrict__ slotTab = G.slotTab;
@@ -116,12 +129,16 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       slotByte = lane < N ? (int)slotTab[(size_t)j * N + lane] : 0;
 #pragma unroll
       for (int it = 0; it < NIT; ++it)
-        if (it < NIT - 1 || lane + 32 * it < CHUNK) v[it] = Ke[tab[32 * it]];
+        if (it < NIT - 1 || lane + 32 * it < CHUNK) {
+          const int tv = tab[32 * it];
+          const int off = (RS == D) ? (tv & 0x3fff) : (tv & 0x3fff) + ((tv & 0x4000) ? i0 * D : i0);
+          v[it] = Ke[off];
+        }
     };
     auto accumulate = [&](const double (&v)[NIT], int slotByte) {
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
-        const int sl = __shfl_sync(0xffffffffu, slotByte, shiftOf[it]);
+        const int sl = __shfl_sync(0xffffffffu, slotByte, lbOf[it]);
         if (it < NIT - 1 || lane + 32 * it < CHUNK) out[outBase[it] + D * sl] += v[it];
       }
       __syncwarp();
@@ -140,15 +157,16 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       ++j;
     }
     const int64_t gGlobal = g + P.rowBegin;
-    bool rowFixed[D];
-    int64_t rowStart[D];
+    bool rowFixed[RS];
+    int64_t rowStart[RS];
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      rowFixed[i] = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gGlobal, i)] != 0) : false;
+    for (int ii = 0; ii < RS; ++ii) {
+      const int i = i0 + ii;
+      rowFixed[ii] = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gGlobal, i)] != 0) : false;
       if (INTERLEAVED)
-        rowStart[i] = (int64_t)DD * b0 + (int64_t)i * rowLen;
+        rowStart[ii] = (int64_t)DD * b0 + (int64_t)i * rowLen;
       else
-        rowStart[i] = (int64_t)i * D * P.nBlocks + (int64_t)D * b0;
+        rowStart[ii] = (int64_t)i * D * P.nBlocks + (int64_t)D * b0;
     }
     for (int idx2 = lane; idx2 < rowLen; idx2 += 32) {
       const int s = idx2 / D, k = idx2 - s * D;
@@ -156,22 +174,23 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       const bool colFixed = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gb, k)] != 0) : false;
       const int64_t offs = INTERLEAVED ? (int64_t)idx2 : (int64_t)k * nnb + s;
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double v = out[i * rowStride + idx2];
+      for (int ii = 0; ii < RS; ++ii) {
+        const int i = i0 + ii;
+        double v = out[ii * rowStride + idx2];
         if (DBC == IKB_DBC_REDUCED) {
-          if (!rowFixed[i] && !colFixed)
+          if (!rowFixed[ii] && !colFixed)
             G.vals[G.redRowStart[localRowOf(P, g, i)] + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b0 + s, gb, k)] = v;
         } else {
           // Full: zero constrained rows and columns, unit diagonal (simpleassemblers.inl:159-167)
-          if (DBC == IKB_DBC_FULL && (rowFixed[i] || colFixed)) v = (gb == gGlobal && i == k) ? 1.0 : 0.0;
-          G.vals[rowStart[i] + offs] = v;
+          if (DBC == IKB_DBC_FULL && (rowFixed[ii] || colFixed)) v = (gb == gGlobal && i == k) ? 1.0 : 0.0;
+          G.vals[rowStart[ii] + offs] = v;
         }
       }
     }
   }
 
-  if (G.vec && lane < D) {
-    const int i = lane;
+  if (G.vec && lane < RS) {
+    const int i = i0 + lane;
     double r = 0.0;
     for (int32_t j = a0; j < a1; ++j) {
       const uint32_t code = G.adjCode[j];
@@ -189,8 +208,8 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
       G.vec[localRowOf(P, g, i)] = r;
     }
   }
-    g += warpsTotal;
-  } while (PERSIST && g < P.nRowNodes);
+    unit += warpsTotal;
+  } while (PERSIST && unit < nUnits);
 }
 
 // ------------------------------------------------------------------ deterministic reductions
