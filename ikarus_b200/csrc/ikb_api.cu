@@ -375,28 +375,55 @@ int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int 
   int it = 0;
   double rr = bb;
   const double threshold = std::max(relTol * relTol * bb, 1e-300);
+  (void)threshold;
   if (bb > 0.0) {
-    while (it < maxIt && rr >= threshold) {
-      if ((rc = haloExchange(h, h->cgPglob.p))) return rc;
-      if ((rc = launchSpmv(h, dbc, h->cgPglob.p, h->cgQ.p))) return rc;
-      if ((rc = deviceDot(h, 1, p, h->cgQ.p, n, scal + 1, 1.0, nullptr))) return rc;
-      if ((rc = allReduceSum(h, scal + 1, 1))) return rc;
-      cg_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, p, h->cgQ.p, h->cgDinv.p, h->cgX.p, h->cgR.p,
-                                                          h->cgZ.p, h->scratch.p + 2 * RED_BLOCKS);
-      IKB_LAUNCH_CHECK(h);
-      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(h->scratch.p + 2 * RED_BLOCKS, RED_BLOCKS, scal, nullptr);
-      IKB_LAUNCH_CHECK(h);
-      if ((rc = allReduceSum(h, scal + 2, 2))) return rc;
-      IKB_CUDA(h, cudaMemcpyAsync(h->hostScal, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      cg_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgZ.p, p);
-      IKB_LAUNCH_CHECK(h);
-      cg_shift_kernel<<<1, 1, 0, h->stream>>>(scal);
-      IKB_LAUNCH_CHECK(h);
+    // No host round trip per iteration: convergence is decided on the device from the all-reduced |r|^2 (identical
+    // on every rank, so all ranks stop at the same iteration); NCCL calls are stream ordered.  The host looks at the
+    // 48-byte state once per batch; iterations enqueued after convergence are no-ops apart from the (harmless)
+    // collectives.
+    if (!h->cgState.p) IKB_CUDA(h, h->cgState.alloc(128));
+    CgState* st = reinterpret_cast<CgState*>(h->cgState.p);
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(h->cgState.p + 96);
+    cg2_init_kernel<<<1, 1, 0, h->stream>>>(st, scal + 0, scal + 4, relTol, maxIt, arrive);
+    IKB_LAUNCH_CHECK(h);
+    const PatternView P = h->view();
+    double* pqPartial = h->scratch.p;
+    double* rzPartial = h->scratch.p + 2 * RED_BLOCKS;
+    CgState* hs = reinterpret_cast<CgState*>(h->hostScal);
+    const int batch = 16;
+    auto enqueueBatch = [&]() -> int {
+      for (int b = 0; b < batch; ++b) {
+        int r2;
+        if ((r2 = haloExchange(h, h->cgPglob.p))) return r2;
+        if (h->dim == 3)
+          spmv_node_dot_kernel<3><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
+                                                                     pqPartial, st);
+        else
+          spmv_node_dot_kernel<2><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
+                                                                     pqPartial, st);
+        reduce_stage2<<<1, tpb, 0, h->stream>>>(pqPartial, RED_BLOCKS, scal + 1, 1.0, nullptr);
+        if ((r2 = allReduceSum(h, scal + 1, 1))) return r2;
+        // the all-reduced scalars are passed as one-entry "partial" arrays
+        cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, scal + 1, 1, p, h->cgQ.p, h->cgDinv.p, h->cgX.p,
+                                                             h->cgR.p, h->cgZ.p, rzPartial);
+        cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(rzPartial, RED_BLOCKS, scal, nullptr);
+        if ((r2 = allReduceSum(h, scal + 2, 2))) return r2;
+        cg2_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, scal + 2, 1, h->cgZ.p, p, arrive);
+      }
+      return IKB_OK;
+    };
+    // (capturing the NCCL operations of a batch into a CUDA graph hung on the 2-GPU box and is not used)
+    while (true) {
+      if ((rc = enqueueBatch())) return rc;
+      h->launches += 8 * batch;
+      IKB_CUDA(h, cudaGetLastError());
+      IKB_CUDA(h, cudaMemcpyAsync(hs, st, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
       IKB_CUDA(h, cudaStreamSynchronize(h->stream));
-      rr = h->hostScal[0];
-      ++it;
-      if (!(rr == rr)) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
+      if (hs->done || hs->iter >= maxIt) break;
     }
+    it = hs->iter;
+    rr = hs->rr;
+    if (hs->done == 2) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
   }
   if (itersOut) *itersOut = it;
   if (relResOut) *relResOut = bb > 0.0 ? std::sqrt(rr / bb) : 0.0;
