@@ -325,6 +325,21 @@ public:
   const MatrixType& matrix(DBCOption dbc) { return matrix(requirement(), affordanceCollection().matrixAffordance(), dbc); }
   const MatrixType& matrix() { return matrix(dBCOption()); }
 
+  // ---- DenseFlatAssembler view (assembler/simpleassemblers.hh:188-231, simpleassemblers.inl:301-375) --------
+  /** Column-major rows x rows copy of the assembled matrix (Eigen::MatrixXd layout); small problems only. */
+  const std::vector<double>& denseMatrix(const FERequirement& req, HostTraits::MatrixAffordance aff,
+                                         DBCOption dbc = DBCOption::Full) {
+    if (aff != HostTraits::MatrixAffordance::stiffness)
+      IKB_THROW(NotImplemented, "MatrixAffordance not implemented");
+    push(req);
+    const int d = toCode(dbc);
+    check(ikb_assemble(h_, IKB_MATRIX, d));
+    const std::size_t n = dbc == DBCOption::Reduced ? reducedSize() : size();
+    dense_.assign(n * n, 0.0);
+    check(ikb_get_dense_matrix(h_, d, dense_.data()));
+    return dense_;
+  }
+
   // ---- resident mode ---------------------------------------------------------------------------------
   /** Assemble on the device and return a handle instead of mirroring K to the host. */
   DeviceMatrixHandle deviceMatrix(const FERequirement& req, DBCOption dbc = DBCOption::Full) {
@@ -405,6 +420,7 @@ private:
   VectorType vec_[3];
   MatrixType mat_[3];
   bool patternReady_[3]{false, false, false};
+  std::vector<double> dense_;
 };
 
 /** makeSparseFlatAssembler analogue (assembler/simpleassemblers.hh:174-177). */

@@ -123,6 +123,18 @@ int main(int argc, char** argv) {
       CHECK(Kred.coeff(r - asmb->constraintsBelow(r), c - asmb->constraintsBelow(c)) == Kraw.values[p]);
     }
   }
+  // Sparse == Dense (tests/src/testassembler.cpp:31-38, 122-183)
+  {
+    const auto& dense = asmb->denseMatrix(req, MatrixAffordance::stiffness, DBCOption::Full);
+    CHECK(dense.size() == n * n);
+    for (std::size_t c = 0; c < n; ++c)
+      for (std::int64_t p = Kfull.outer[c]; p < Kfull.outer[c + 1]; ++p)
+        CHECK(dense[c * n + Kfull.inner[p]] == Kfull.values[p]);
+    double sumDense = 0, sumSparse = 0;
+    for (double v : dense) sumDense += std::fabs(v);
+    for (double v : Kfull.values) sumSparse += std::fabs(v);
+    CHECK(sumDense == sumSparse);
+  }
   auto full = asmb->createFullVector(Rred);
   auto back = asmb->createReducedVector(full);
   CHECK(back == Rred);
