@@ -225,7 +225,7 @@ def run_ours(args):
     for _ in range(args.steps):
         asm._check(lib.ikb_set_solution_range(h, C.c_void_p(d_ptr), need_lo, need_hi - need_lo))
         asm._check(lib.ikb_assemble(h, WHAT, DBC))
-        asm._check(lib.ikb_get_vector(h, DBC, C.c_void_p(r_host.data_ptr())))  # syncs
+        asm._check(lib.ikb_get_vector(h, DBC, C.c_void_p(r_host.data_ptr())))  # waits for R only; K gather overlaps
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None

@@ -48,6 +48,15 @@ cudaError_t launchEas(Handle* h, const EasArgs& EA) {
   return cudaErrorInvalidValue;
 }
 
+void markSolutionUse(Handle* h) { cudaEventRecord(h->evUse, h->stream); }
+
+// Orders the main stream behind a pipelined solution upload that no element kernel has consumed yet.
+void joinSolution(Handle* h) {
+  if (!h->piecesPending) return;
+  cudaStreamWaitEvent(h->stream, h->evPiece[Handle::SOL_CHUNKS - 1], 0);
+  h->piecesPending = false;
+}
+
 int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   ElemArgs A;
   A.X = h->X.p;
@@ -59,6 +68,8 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   A.errFlag = h->errFlag.p;
   A.Lap = h->Lap.p;
   A.nElem = h->nElem;
+  A.elemBegin = 0;
+  A.elemEnd = h->nElem;
   A.nNodes = h->nNodes;
   A.layout = h->layout;
   A.lambda = h->desc.lambda;
@@ -66,15 +77,27 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   A.what = what;
   cudaError_t e = cudaErrorInvalidValue;
   if (h->order == 1 && h->easM == 0) {
-    if (h->dim == 3) {
-      if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
-      if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
-      if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
-    } else {
-      if (h->form == FORM_LE) e = launchElemQ1<2, FORM_LE>(A, h->stream);
-      if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
-      if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
+    // a pipelined solution upload is consumed chunk by chunk: chunk c waits for piece c of d only
+    const int nch = h->piecesPending ? Handle::SOL_CHUNKS : 1;
+    for (int c = 0; c < nch; ++c) {
+      if (h->piecesPending) {
+        cudaStreamWaitEvent(h->stream, h->evPiece[c], 0);
+        A.elemBegin = c ? h->chunkElemEnd[c - 1] : 0;
+        A.elemEnd = h->chunkElemEnd[c];
+        if (c) h->launches++;
+      }
+      if (h->dim == 3) {
+        if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
+        if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
+        if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
+      } else {
+        if (h->form == FORM_LE) e = launchElemQ1<2, FORM_LE>(A, h->stream);
+        if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
+        if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
+      }
+      if (e != cudaSuccess) break;
     }
+    h->piecesPending = false;
   } else if (h->order == 1) {
     EasArgs EA;
     EA.E = A;
@@ -97,6 +120,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
     return fail(h, IKB_ENOTIMPL, "EAS is only supported for Q1 and H1 elements");
   }
   h->launches++;
+  markSolutionUse(h);
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("element kernel: ") + cudaGetErrorString(e));
   return IKB_OK;
 }
@@ -113,6 +137,7 @@ int ensureSolution(Handle* h) {
   if (!h->U.p) {
     IKB_CUDA(h, h->U.alloc((size_t)h->nDof));
     IKB_CUDA(h, cudaMemsetAsync(h->U.p, 0, h->U.bytes(), h->stream));
+    markSolutionUse(h);
   }
   return IKB_OK;
 }
@@ -211,18 +236,33 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
   // one warp per work unit (node-row, or scalar row for Q2)
   const int64_t wantBlocks = gridFor(nRowNodes * (h->dim / rs), warps);
-  cudaError_t e = cudaErrorInvalidValue;
+  cudaError_t e = cudaSuccess;
+  const unsigned vecGrid = gridFor(nRowNodes * h->dim, 256);
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \
-    e = cudaFuncSetAttribute(gather_kernel<DIM, NN, MODE, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                             (int)smem);                                                                             \
-    int occ = 1;                                                                                                     \
-    if (e == cudaSuccess)                                                                                            \
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_kernel<DIM, NN, MODE, IL>, warps * 32, smem);   \
-    const bool persist = NN * NN * DIM * DIM > 2048;                                                                 \
-    const unsigned grid = (unsigned)(persist ? std::min<int64_t>(wantBlocks, (int64_t)148 * std::max(occ, 1) * 4)   \
-                                             : wantBlocks);                                                          \
-    if (e == cudaSuccess) gather_kernel<DIM, NN, MODE, IL><<<grid, warps * 32, smem, h->stream>>>(G);                \
+    if (G.vec) {                                                                                                     \
+      /* with a matrix gather following, the residual kernel forks onto the side stream and runs beside it */       \
+      cudaStream_t vs = G.vals ? h->stream2 : h->stream;                                                             \
+      if (G.vals) {                                                                                                  \
+        cudaEventRecord(h->evFork, h->stream);                                                                       \
+        cudaStreamWaitEvent(h->stream2, h->evFork, 0);                                                               \
+      }                                                                                                              \
+      gather_vec_kernel<DIM, NN, MODE, IL><<<vecGrid, 256, 0, vs>>>(G);                                              \
+      h->launches++;                                                                                                 \
+      cudaEventRecord(h->evVec, vs);                                                                                 \
+    }                                                                                                                \
+    if (G.vals) {                                                                                                    \
+      e = cudaFuncSetAttribute(gather_kernel<DIM, NN, MODE, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                               (int)smem);                                                                           \
+      int occ = 1;                                                                                                   \
+      if (e == cudaSuccess)                                                                                          \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_kernel<DIM, NN, MODE, IL>, warps * 32, smem); \
+      const bool persist = GatherCfg<DIM, NN>::PERSIST;                                                              \
+      const unsigned grid = (unsigned)(persist ? std::min<int64_t>(wantBlocks, (int64_t)148 * std::max(occ, 1) * 4) \
+                                               : wantBlocks);                                                        \
+      if (e == cudaSuccess) gather_kernel<DIM, NN, MODE, IL><<<grid, warps * 32, smem, h->stream>>>(G);              \
+      if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
+    }                                                                                                                \
   }
 #define IKB_GATHER2(DIM, NN, MODE)                    \
   if (h->layout == LAYOUT_INTERLEAVED)                \
@@ -243,10 +283,11 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   IKB_GATHER(3, 27)
   IKB_GATHER(2, 4)
   IKB_GATHER(2, 9)
+#undef IKB_GATHER
 #undef IKB_GATHER2
 #undef IKB_GATHER3
-#undef IKB_GATHER
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("gather launch: ") + cudaGetErrorString(e));
+  if (!G.vals) h->launches--;  // only the residual kernel was launched (already counted)
   IKB_LAUNCH_CHECK(h);
   return IKB_OK;
 }
@@ -486,8 +527,17 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     delete h;
     return IKB_EINVAL;
   }
+  int prioLo = 0, prioHi = 0;
+  cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prioHi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evVec, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evUse, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evPiece[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evPiece[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evPiece[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->evPiece[3], cudaEventDisableTiming) != cudaSuccess ||
       h->errFlag.alloc(1) != cudaSuccess || h->scratch.alloc(4 * RED_BLOCKS + 16) != cudaSuccess ||
       h->cgScal.alloc(16) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&h->hostScal), 16 * sizeof(double)) != cudaSuccess) {
     delete h;
@@ -536,6 +586,11 @@ int ikb_destroy(ikb_handle hh) {
   if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
   h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
+  if (h->evVec) cudaEventDestroy(h->evVec);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evUse) cudaEventDestroy(h->evUse);
+  for (cudaEvent_t ev : h->evPiece)
+    if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->stream2);
   delete h;
@@ -601,6 +656,21 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
     }
     h->colBegin = mn;
     h->colEnd = (int64_t)mx + 1;
+  }
+  // chunk table for the pipelined solution upload (Q1, interleaved dofs, enough elements to be worth it)
+  h->chunkElemEnd.clear();
+  h->chunkDofEnd.clear();
+  h->piecesPending = false;
+  if (h->order == 1 && h->easM == 0 && layout == LAYOUT_INTERLEAVED && ne >= (int64_t)Handle::SOL_CHUNKS * 8192) {
+    int32_t runMax = -1;
+    int64_t e = 0;
+    for (int c = 0; c < Handle::SOL_CHUNKS; ++c) {
+      int64_t end = c + 1 == Handle::SOL_CHUNKS ? ne : std::min<int64_t>(ne, ((ne * (c + 1) / Handle::SOL_CHUNKS) + 255) / 256 * 256);
+      for (; e < end; ++e)
+        for (int a = 0; a < nn; ++a) runMax = std::max(runMax, en[(size_t)a * ne + e]);
+      h->chunkElemEnd.push_back(end);
+      h->chunkDofEnd.push_back(((int64_t)runMax + 1) * D);
+    }
   }
   std::vector<double> xs((size_t)nc * D * ne);
   for (int64_t e = 0; e < ne; ++e)
@@ -962,7 +1032,9 @@ int ikb_set_solution(ikb_handle hh, const double* d) {
   if (checkHandle(h)) return IKB_EINVAL;
   if (!d) return fail(h, IKB_EINVAL, "null solution");
   if (!h->U.p) IKB_CUDA(h, h->U.alloc((size_t)h->nDof));
+  joinSolution(h);
   IKB_CUDA(h, cudaMemcpyAsync(h->U.p, d, h->U.bytes(), cudaMemcpyHostToDevice, h->stream));
+  markSolutionUse(h);
   h->stateVersion++;
   return IKB_OK;
 }
@@ -973,8 +1045,29 @@ int ikb_set_solution_range(ikb_handle hh, const double* d, int64_t dofBegin, int
   if (!d || dofBegin < 0 || count < 0 || dofBegin + count > h->nDof) return fail(h, IKB_EINVAL, "bad dof range");
   int rc = ensureSolution(h);
   if (rc) return rc;
-  if (count)
+  if (count && !h->chunkDofEnd.empty() && count >= (int64_t)1 << 16) {
+    // pieces on the side stream, one event each; launchElements() waits per chunk
+    // The copy only has to wait for the latest consumer of U on the main stream (evUse), not for work queued behind it
+    // (a matrix gather still running does not read U), so back-to-back steps overlap upload and gather.
+    joinSolution(h);
+    if (h->solutionShared) markSolutionUse(h);
+    IKB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->evUse, 0));
+    const int64_t end = dofBegin + count;
+    int64_t lo = dofBegin;
+    for (int c = 0; c < Handle::SOL_CHUNKS; ++c) {
+      const int64_t hi = c + 1 == Handle::SOL_CHUNKS ? end : std::min(end, std::max(lo, h->chunkDofEnd[c]));
+      if (hi > lo)
+        IKB_CUDA(h, cudaMemcpyAsync(h->U.p + lo, d + (lo - dofBegin), (size_t)(hi - lo) * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->stream2));
+      IKB_CUDA(h, cudaEventRecord(h->evPiece[c], h->stream2));
+      lo = hi;
+    }
+    h->piecesPending = true;
+  } else if (count) {
+    joinSolution(h);
     IKB_CUDA(h, cudaMemcpyAsync(h->U.p + dofBegin, d, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    markSolutionUse(h);
+  }
   h->stateVersion++;
   return IKB_OK;
 }
@@ -984,6 +1077,7 @@ int ikb_get_solution(ikb_handle hh, double* d) {
   if (checkHandle(h)) return IKB_EINVAL;
   int rc = ensureSolution(h);
   if (rc) return rc;
+  joinSolution(h);
   IKB_CUDA(h, cudaMemcpyAsync(d, h->U.p, h->U.bytes(), cudaMemcpyDeviceToHost, h->stream));
   IKB_CUDA(h, cudaStreamSynchronize(h->stream));
   return IKB_OK;
@@ -1056,6 +1150,7 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
       // E -= s * fext . d   (loads/volume.hh:67-84, traction.hh:70-105)
       if ((rc = deviceDot(h, 1, h->Fext.p, h->U.p, h->nDof, lDev, -(h->fextScales ? h->lambda : 1.0), nullptr)))
         return rc;
+      markSolutionUse(h);
     }
     const bool partitioned = h->rowBegin != 0 || h->rowEnd != h->nNodes;
     if (partitioned && h->nElem) {
@@ -1092,8 +1187,15 @@ int ikb_get_vector(ikb_handle hh, int dbc, double* out) {
   if (!dbcValid(dbc) || !out) return fail(h, IKB_EINVAL, "bad arguments");
   if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "vector not assembled for the current state");
   const int64_t n = rowsOf(h, dbc);
-  if (n) IKB_CUDA(h, cudaMemcpyAsync(out, h->vec[dbc].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  return checkMaterialError(h);
+  // R is complete once the residual gather has run (evVec); it is copied on the side stream so that a matrix gather
+  // still running on the main stream is not waited for.  The material error flag is final by then as well.
+  IKB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->evVec, 0));
+  int32_t flag = INT_MAX;
+  if (n) IKB_CUDA(h, cudaMemcpyAsync(out, h->vec[dbc].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream2));
+  IKB_CUDA(h, cudaMemcpyAsync(&flag, h->errFlag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream2));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream2));
+  if (flag != INT_MAX) return checkMaterialError(h);
+  return IKB_OK;
 }
 
 int ikb_get_scalar(ikb_handle hh, double* e) {
@@ -1394,8 +1496,10 @@ int ikb_update_solution(ikb_handle hh, int dbc, const double* correction) {
                                   h->stream));
     }
   }
+  joinSolution(h);
   vec_axpy_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(h->nDof, 1.0, h->Corr.p, h->U.p);
   IKB_LAUNCH_CHECK(h);
+  markSolutionUse(h);
   h->stateVersion++;
   return IKB_OK;
 }
@@ -1453,14 +1557,17 @@ int ikb_halo_exchange(ikb_handle hh, const char* what) {
   if (!what) return fail(h, IKB_EINVAL, "null array name");
   const std::string w(what);
   double* v = nullptr;
-  if (w == "solution")
+  if (w == "solution") {
+    joinSolution(h);
     v = h->U.p;
-  else if (w == "correction")
+  } else if (w == "correction")
     v = h->Corr.p;
   else
     return fail(h, IKB_EINVAL, "unknown array");
   if (!v) return fail(h, IKB_ESTATE, "array not allocated");
-  return haloExchange(h, v);
+  const int rc = haloExchange(h, v);
+  if (v == h->U.p) markSolutionUse(h);
+  return rc;
 }
 
 int ikb_stream(ikb_handle hh, void** s) {
@@ -1472,6 +1579,7 @@ int ikb_stream(ikb_handle hh, void** s) {
 int ikb_sync(ikb_handle hh) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream2));
   return checkMaterialError(h);
 }
 int ikb_launch_count(ikb_handle hh, int64_t* n) {
@@ -1484,9 +1592,11 @@ int ikb_device_ptr(ikb_handle hh, const char* what, int dbc, void** ptr) {
   Handle* h = H(hh);
   if (!h || !what || !ptr || !dbcValid(dbc)) return IKB_EINVAL;
   const std::string w(what);
-  if (w == "solution")
+  if (w == "solution") {
+    joinSolution(h);
+    h->solutionShared = true;  // the caller may use U on the main stream behind our back
     *ptr = h->U.p;
-  else if (w == "residual")
+  } else if (w == "residual")
     *ptr = h->vec[dbc].p;
   else if (w == "values")
     *ptr = h->vals[dbc].p;

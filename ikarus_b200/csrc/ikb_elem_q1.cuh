@@ -37,6 +37,7 @@ struct ElemArgs {
   const double* Lap;       // [NPAIR][nElem] sum_g w_g grad N_a . grad N_b (reference geometry only), may be null
   int32_t* errFlag;
   int64_t nElem;
+  int64_t elemBegin, elemEnd;  // element range of this launch (Q1 kernels; the others always run [0, nElem))
   int64_t nNodes;
   int layout;
   double lambda, mu;
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   const int tid = threadIdx.x;
   const int el = tid / N;     // element within CTA
   const int t = tid % N;      // Gauss point (phase 1) / row node (phase 2)
-  const int64_t e = (int64_t)blockIdx.x * C::EPC + el;
-  const bool active = e < A.nElem;
+  const int64_t e = A.elemBegin + (int64_t)blockIdx.x * C::EPC + el;
+  const bool active = e < A.elemEnd;
   double* rec = smem + (size_t)el * C::S;
   const unsigned grpMask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << ((threadIdx.x & 31u) / N * N));
 
@@ -468,7 +469,7 @@ cudaError_t launchElemQ1Impl(const ElemArgs& A, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const unsigned grid = (unsigned)((A.nElem + C::EPC - 1) / C::EPC);
+  const unsigned grid = (unsigned)((A.elemEnd - A.elemBegin + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
   elem_q1_kernel<D, FORM, USELAP><<<grid, C::TPB, C::SMEM, st>>>(A);
   return cudaGetLastError();

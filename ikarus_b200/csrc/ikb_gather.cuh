@@ -189,27 +189,39 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
     }
   }
 
-  if (G.vec && lane < RS) {
-    const int i = i0 + lane;
-    double r = 0.0;
-    for (int32_t j = a0; j < a1; ++j) {
-      const uint32_t code = G.adjCode[j];
-      const uint32_t e = code / (uint32_t)N;
-      const int la = (int)(code - e * (uint32_t)N);
-      r += G.Rst[(size_t)e * (N * D) + la * D + i];
-    }
-    const int64_t rowDof = dofOf(LAYOUT, D, P.nNodes, g + P.rowBegin, i);
-    const bool rowFixed = (DBC != IKB_DBC_RAW) ? (G.flags[rowDof] != 0) : false;
-    if (G.fext) r -= G.fextScale * G.fext[rowDof];
-    if (DBC == IKB_DBC_REDUCED) {
-      if (!rowFixed) G.vec[rowDof - G.cbelow[rowDof] - G.redVecOffset] = r;
-    } else {
-      if (DBC == IKB_DBC_FULL && rowFixed) r = 0.0;  // simpleassemblers.inl:90-92
-      G.vec[localRowOf(P, g, i)] = r;
-    }
-  }
     unit += warpsTotal;
   } while (PERSIST && unit < nUnits);
+}
+
+// Residual gather: one thread per (node-row, component).  The node's (element, local node) adjacency is walked in
+// ascending element order (VectorFlatAssembler::get*VectorImpl, ikarus/assembler/simpleassemblers.inl:59-118);
+// external load and Dirichlet mode are applied on the fly.  A separate, tiny kernel so that the host can fetch R
+// while the matrix gather is still running.
+template <int D, int N, int DBC, bool INTERLEAVED>
+__global__ void __launch_bounds__(256) gather_vec_kernel(GatherArgs G) {
+  constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
+  const PatternView& P = G.P;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nRowNodes * D) return;
+  const int64_t g = t / D;
+  const int i = (int)(t - g * D);
+  const int32_t a0 = G.adjPtr[g], a1 = G.adjPtr[g + 1];
+  double r = 0.0;
+  for (int32_t j = a0; j < a1; ++j) {
+    const uint32_t code = G.adjCode[j];
+    const uint32_t e = code / (uint32_t)N;
+    const int la = (int)(code - e * (uint32_t)N);
+    r += G.Rst[(size_t)e * (N * D) + la * D + i];
+  }
+  const int64_t rowDof = dofOf(LAYOUT, D, P.nNodes, g + P.rowBegin, i);
+  const bool rowFixed = (DBC != IKB_DBC_RAW) ? (G.flags[rowDof] != 0) : false;
+  if (G.fext) r -= G.fextScale * G.fext[rowDof];
+  if (DBC == IKB_DBC_REDUCED) {
+    if (!rowFixed) G.vec[rowDof - G.cbelow[rowDof] - G.redVecOffset] = r;
+  } else {
+    if (DBC == IKB_DBC_FULL && rowFixed) r = 0.0;  // simpleassemblers.inl:90-92
+    G.vec[localRowOf(P, g, i)] = r;
+  }
 }
 
 // ------------------------------------------------------------------ deterministic reductions

@@ -72,7 +72,18 @@ struct Handle {
   int64_t nElem = 0, nDof = 0, nNodes = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: lets the host fetch R while the matrix gather still runs
+  cudaEvent_t evVec = nullptr;     // recorded after the residual gather
+  // Pipelined host->device solution upload (ikb_set_solution_range on Q1 interleaved meshes): the element list is cut
+  // into SOL_CHUNKS chunks; chunk c needs dofs < chunkDofEnd[c] only, so d is copied in pieces on the side stream and
+  // the element kernel of chunk c starts as soon as piece c has landed.
+  static constexpr int SOL_CHUNKS = 4;
+  std::vector<int64_t> chunkElemEnd, chunkDofEnd;
+  cudaEvent_t evPiece[SOL_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+  bool piecesPending = false;
+  cudaEvent_t evUse = nullptr;   // recorded on the main stream after the latest kernel/copy touching U
+  bool solutionShared = false;   // U was handed out through ikb_device_ptr: fall back to ordering behind the whole stream
+  cudaEvent_t evFork = nullptr;    // main stream -> side stream fork point (element kernel done)
   std::string lastError;
   int64_t launches = 0;
 

@@ -247,3 +247,47 @@ def test_volume_load_sampling_matches_oracle_consistent_load():
     assert np.abs(R - Rr).max() <= TOL * np.abs(Rr).max()
     E = dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
     assert abs(E - ref2.scalar(d, 1.7)) <= 1e-12 * abs(ref2.scalar(d, 1.7))
+
+
+def test_pipelined_solution_upload_is_bit_identical():
+    """ikb_set_solution_range on a large interleaved Q1 mesh copies d in pieces on the side stream and launches the
+    element kernel chunk by chunk; K, R must be bit-identical to the plain ikb_set_solution path, also for sub-ranges
+    and when another consumer of the solution (ikb_get_solution) comes between upload and assembly."""
+    import ctypes as C
+    from ikarus_b200 import _capi as capi
+    cells = (40, 32, 32)  # 40960 elements: above the pipelining threshold
+    mesh = distorted(o.structured_mesh(cells, (40.0, 32.0, 32.0), order=1), 0.1, 3)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material("neohooke", lam, mu)
+    kind = o.ElementKind(3, 1, "gl")
+    flags = o.fix_nodes(mesh, o.boundary_nodes(o.structured_mesh(cells, (40.0, 32.0, 32.0), order=1), 0, 0.0), "interleaved")
+    dev = device_assembler(mesh, kind, mat, flags, "interleaved")
+    rng = np.random.default_rng(5)
+    n = flags.shape[0]
+    d = 0.02 * rng.uniform(-1, 1, n)
+    dev.bind(ik.FERequirements(d, 0.0), ik.elastoStatics, ik.DBCOption.Full)
+    r0 = dev.vector().copy()
+    v0 = dev.matrix().data.copy()
+    lib, h = dev._lib, dev._h
+    # whole range through the pipelined path, from a different starting state
+    dev._check(lib.ikb_set_solution(h, capi.ptr(np.zeros(n))))
+    dev._check(lib.ikb_assemble(h, 6, int(ik.DBCOption.Full)))
+    dev._check(lib.ikb_set_solution_range(h, capi.ptr(d), 0, n))
+    dev._check(lib.ikb_assemble(h, 6, int(ik.DBCOption.Full)))
+    r1 = np.empty(n)
+    v1 = np.empty_like(v0)
+    dev._check(lib.ikb_get_vector(h, int(ik.DBCOption.Full), capi.ptr(r1)))
+    dev._check(lib.ikb_get_matrix_values(h, int(ik.DBCOption.Full), capi.ptr(v1)))
+    assert np.array_equal(r0, r1) and np.array_equal(v0, v1)
+    # two sub-ranges (second one pipelined again), read back before assembling
+    dev._check(lib.ikb_set_solution(h, capi.ptr(np.zeros(n))))
+    cut = 3 * 20001
+    dev._check(lib.ikb_set_solution_range(h, capi.ptr(d), 0, cut))
+    dev._check(lib.ikb_set_solution_range(h, capi.ptr(d[cut:].copy()), cut, n - cut))
+    back = np.empty(n)
+    dev._check(lib.ikb_get_solution(h, capi.ptr(back)))
+    assert np.array_equal(back, d)
+    dev._check(lib.ikb_assemble(h, 6, int(ik.DBCOption.Full)))
+    dev._check(lib.ikb_get_vector(h, int(ik.DBCOption.Full), capi.ptr(r1)))
+    dev._check(lib.ikb_get_matrix_values(h, int(ik.DBCOption.Full), capi.ptr(v1)))
+    assert np.array_equal(r0, r1) and np.array_equal(v0, v1)
