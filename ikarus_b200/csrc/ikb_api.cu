@@ -69,7 +69,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
   A.Lap = h->Lap.p;
   A.nElem = h->nElem;
   A.elemBegin = 0;
-  A.elemEnd = h->nElem;
+  A.elemCount = h->nElem;
   A.nNodes = h->nNodes;
   A.layout = h->layout;
   A.lambda = h->desc.lambda;
@@ -82,8 +82,15 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
     for (int c = 0; c < nch; ++c) {
       if (h->piecesPending) {
         cudaStreamWaitEvent(h->stream, h->evPiece[c], 0);
-        A.elemBegin = c ? h->chunkElemEnd[c - 1] : 0;
-        A.elemEnd = h->chunkElemEnd[c];
+        const int64_t b = c ? h->chunkElemEnd[c - 1] : 0;
+        A.elemBegin = b;
+        A.elemCount = h->chunkElemEnd[c] - b;
+        A.X = h->X.p + b;
+        A.elemNode = h->elemNode.p + b;
+        A.Lap = h->Lap.p ? h->Lap.p + b : nullptr;
+        A.Kst = h->Kst.p + (size_t)b * h->npair * h->dim * h->dim;
+        A.Rst = h->Rst.p + (size_t)b * h->nd;
+        A.Est = h->Est.p + b;
         if (c) h->launches++;
       }
       if (h->dim == 3) {

@@ -37,7 +37,9 @@ struct ElemArgs {
   const double* Lap;       // [NPAIR][nElem] sum_g w_g grad N_a . grad N_b (reference geometry only), may be null
   int32_t* errFlag;
   int64_t nElem;
-  int64_t elemBegin, elemEnd;  // element range of this launch (Q1 kernels; the others always run [0, nElem))
+  // Q1 kernels can run an element sub-range: the launcher shifts every per-element pointer by elemBegin and the kernel
+  // sees elements [0, elemCount) with the SoA stride nElem unchanged (elemBegin is only used to report error ids).
+  int64_t elemBegin, elemCount;
   int64_t nNodes;
   int layout;
   double lambda, mu;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
   const int tid = threadIdx.x;
   const int el = tid / N;     // element within CTA
   const int t = tid % N;      // Gauss point (phase 1) / row node (phase 2)
-  const int64_t e = A.elemBegin + (int64_t)blockIdx.x * C::EPC + el;
-  const bool active = e < A.elemEnd;
+  const int64_t e = (int64_t)blockIdx.x * C::EPC + el;
+  const bool active = e < A.elemCount;
   double* rec = smem + (size_t)el * C::S;
   const unsigned grpMask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << ((threadIdx.x & 31u) / N * N));
 
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
       } else {  // FORM_NH  (neohooke.hh:79-142 with C = 2E + I)
         double Ci[D][D];
         const double detC = invSmall<D>(Cm, Ci);
-        if (!(detC > 0.0)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+        if (!(detC > 0.0)) atomicMin(A.errFlag, (int32_t)(e + A.elemBegin < 0x7fffffff ? e + A.elemBegin : 0x7ffffffe));
         const double lnJ = 0.5 * log(detC);
         const double mup = mu - lam * lnJ;
         double trC = (D == 2) ? 1.0 : 0.0;  // plane strain: C_33 = 1
@@ -469,7 +471,7 @@ cudaError_t launchElemQ1Impl(const ElemArgs& A, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const unsigned grid = (unsigned)((A.elemEnd - A.elemBegin + C::EPC - 1) / C::EPC);
+  const unsigned grid = (unsigned)((A.elemCount + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
   elem_q1_kernel<D, FORM, USELAP><<<grid, C::TPB, C::SMEM, st>>>(A);
   return cudaGetLastError();

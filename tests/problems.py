@@ -35,3 +35,23 @@ def distorted(mesh, amp, seed):
     cidx = [sum(((a >> k) & 1) * mesh.order * n1**k for k in range(dim)) for a in range(2**dim)]
     corner_nodes = mesh.elem_nodes[:, cidx]
     return o.Mesh(mesh.dim, mesh.order, coords, mesh.elem_nodes, coords[corner_nodes], mesh.cells)
+
+
+def unstructured(mesh, seed, drop=None):
+    """Makes a structured mesh look like an unstructured (UG/ALUGrid-style) one: cells for which `drop(centre)` is
+    true are removed, the remaining elements are shuffled, unused nodes are discarded and the node numbers are
+    permuted at random.  Connectivity, valence (1..2^d elements per node) and dof numbering are then arbitrary,
+    which is what the pattern builder / gather have to cope with (tests/src/testcommon.hh:179-248 uses UGGrid)."""
+    rng = np.random.default_rng(seed)
+    keep = np.arange(mesh.n_elem)
+    if drop is not None:
+        centres = mesh.corner_coords.mean(axis=1)
+        keep = np.array([e for e in keep if not drop(centres[e])])
+    keep = rng.permutation(keep)
+    en = mesh.elem_nodes[keep]
+    used = np.unique(en)
+    new_id = np.full(mesh.n_nodes, -1, dtype=np.int64)
+    new_id[used] = rng.permutation(used.shape[0])
+    coords = np.empty((used.shape[0], mesh.dim))
+    coords[new_id[used]] = mesh.node_coords[used]
+    return o.Mesh(mesh.dim, mesh.order, coords, new_id[en], mesh.corner_coords[keep], mesh.cells)
