@@ -18,6 +18,7 @@ using namespace ikb;
 namespace {
 
 constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs; fixed so reductions are reproducible
+constexpr int MAX_SPMV_BLOCKS = 2368;  // upper bound of the PCG SpMV grid (p.q partials live in scratch[0, MAX))
 
 Handle* H(ikb_handle h) { return reinterpret_cast<Handle*>(h); }
 
@@ -436,7 +437,7 @@ int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int 
     IKB_LAUNCH_CHECK(h);
     const PatternView P = h->view();
     double* pqPartial = h->scratch.p;
-    double* rzPartial = h->scratch.p + 2 * RED_BLOCKS;
+    double* rzPartial = h->scratch.p + MAX_SPMV_BLOCKS;
     CgState* hs = reinterpret_cast<CgState*>(h->hostScal);
     const int batch = 16;
     auto enqueueBatch = [&]() -> int {
@@ -444,12 +445,12 @@ int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int 
         int r2;
         if ((r2 = haloExchange(h, h->cgPglob.p))) return r2;
         if (h->dim == 3)
-          spmv_node_dot_kernel<3><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
-                                                                     pqPartial, st);
+          spmv_node_dot_kernel<3><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
+                                                                        pqPartial, st);
         else
-          spmv_node_dot_kernel<2><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
-                                                                     pqPartial, st);
-        reduce_stage2<<<1, tpb, 0, h->stream>>>(pqPartial, RED_BLOCKS, scal + 1, 1.0, nullptr);
+          spmv_node_dot_kernel<2><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p,
+                                                                        pqPartial, st);
+        reduce_stage2<<<1, tpb, 0, h->stream>>>(pqPartial, h->spmvBlocks, scal + 1, 1.0, nullptr);
         if ((r2 = allReduceSum(h, scal + 1, 1))) return r2;
         // the all-reduced scalars are passed as one-entry "partial" arrays
         cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, scal + 1, 1, p, h->cgQ.p, h->cgDinv.p, h->cgX.p,
@@ -534,6 +535,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     delete h;
     return IKB_EINVAL;
   }
+  if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -545,7 +547,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
       cudaEventCreateWithFlags(&h->evPiece[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->evPiece[2], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->evPiece[3], cudaEventDisableTiming) != cudaSuccess ||
-      h->errFlag.alloc(1) != cudaSuccess || h->scratch.alloc(4 * RED_BLOCKS + 16) != cudaSuccess ||
+      h->errFlag.alloc(1) != cudaSuccess || h->scratch.alloc(MAX_SPMV_BLOCKS + 2 * RED_BLOCKS + 16) != cudaSuccess ||
       h->cgScal.alloc(16) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&h->hostScal), 16 * sizeof(double)) != cudaSuccess) {
     delete h;
     return IKB_ECUDA;
@@ -1394,18 +1396,18 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
     IKB_LAUNCH_CHECK(h);
     const PatternView P = h->view();
     double* pqPartial = h->scratch.p;
-    double* rzPartial = h->scratch.p + 2 * RED_BLOCKS;
+    double* rzPartial = h->scratch.p + MAX_SPMV_BLOCKS;
     CgState* hs = reinterpret_cast<CgState*>(h->hostScal);
     const int batch = 32;
     auto enqueueBatch = [&]() {
       for (int b = 0; b < batch; ++b) {
         if (h->dim == 3)
-          spmv_node_dot_kernel<3><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
-                                                                     pqPartial, st);
+          spmv_node_dot_kernel<3><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                        pqPartial, st);
         else
-          spmv_node_dot_kernel<2><<<RED_BLOCKS, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
-                                                                     pqPartial, st);
-        cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, pqPartial, RED_BLOCKS, h->cgP.p, h->cgQ.p,
+          spmv_node_dot_kernel<2><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                        pqPartial, st);
+        cg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, pqPartial, h->spmvBlocks, h->cgP.p, h->cgQ.p,
                                                              h->cgDinv.p, h->cgX.p, h->cgR.p, h->cgZ.p, rzPartial);
         cg2_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, rzPartial, RED_BLOCKS, h->cgZ.p, h->cgP.p, arrive);
       }
@@ -1448,9 +1450,9 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
       if ((rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p))) return rc;
       if ((rc = deviceDot(h, 1, h->cgP.p, h->cgQ.p, n, scal + 1, 1.0, nullptr))) return rc;
       cg_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgP.p, h->cgQ.p, h->cgDinv.p, h->cgX.p, h->cgR.p,
-                                                          h->cgZ.p, h->scratch.p + 2 * RED_BLOCKS);
+                                                          h->cgZ.p, h->scratch.p + MAX_SPMV_BLOCKS);
       IKB_LAUNCH_CHECK(h);
-      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(h->scratch.p + 2 * RED_BLOCKS, RED_BLOCKS, scal, nullptr);
+      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(h->scratch.p + MAX_SPMV_BLOCKS, RED_BLOCKS, scal, nullptr);
       IKB_LAUNCH_CHECK(h);
       IKB_CUDA(h, cudaMemcpyAsync(h->hostScal, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       cg_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, scal, h->cgZ.p, h->cgP.p);

@@ -135,6 +135,7 @@ struct Handle {
   unsigned stagedWhat = 0;
   double energy = 0.0;
   DevBuf<double> scratch;      // reductions
+  int spmvBlocks = 888;        // grid of the SpMV inside PCG: 6 resident blocks x 148 SMs (IKB_SPMV_BLOCKS overrides, for tuning)
   DevBuf<int32_t> errFlag;     // first failing element (material abort), INT_MAX if none
 
   // EAS

@@ -78,7 +78,7 @@ __global__ void cg2_init_kernel(CgState* st, const double* rzDev, const double* 
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) spmv_node_dot_kernel(PatternView P, const double* __restrict__ vals,
+__global__ void __launch_bounds__(256, 6) spmv_node_dot_kernel(PatternView P, const double* __restrict__ vals,
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             const double* __restrict__ pLocal, double* partial,
                                                             const CgState* st) {
@@ -98,23 +98,61 @@ __global__ void __launch_bounds__(256) spmv_node_dot_kernel(PatternView P, const
       s[i] = 0.0;
       start[i] = rawRowStart(P, g, i, nnb);
     }
-    for (int j = lane; j < len; j += 32) {
-      int slot, k;
-      if (P.layout == LAYOUT_INTERLEAVED) {
-        slot = j / D;
-        k = j - slot * D;
-      } else {
-        k = j / nnb;
-        slot = j - k * nnb;
+    if (nnb <= 32) {
+      // Fast path (rows of up to 96 entries: every Q1 mesh).  The column nodes of the node-row come from ONE coalesced
+      // load and are handed out by shuffle, and the lane passes are unrolled, so all matrix loads and x gathers of the
+      // node-row are in flight together instead of one dependent index -> x chain per pass.  Same per-lane summation
+      // order as the generic loop below.
+      constexpr int U = 3;
+      const int32_t myCol = lane < nnb ? __ldg(P.nbrIdx + b0 + lane) : 0;
+      double av[U][D], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = lane + 32 * u;
+        const bool valid = j < len;
+#pragma unroll
+        for (int i = 0; i < D; ++i) av[u][i] = valid ? __ldcs(vals + start[i] + j) : 0.0;
       }
-      // the matrix is streamed exactly once: keep it out of L1 (__ldcs) so the gathered x stays resident there
-      double av[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) av[i] = __ldcs(vals + start[i] + j);
-      const double xv = __ldg(x + dofOf(P.layout, D, P.nNodes, __ldg(P.nbrIdx + b0 + slot), k));
+      for (int u = 0; u < U; ++u) {
+        xv[u] = 0.0;
+        if (32 * u < len) {  // warp-uniform
+          const int j = lane + 32 * u;
+          const bool valid = j < len;
+          int slot, k;
+          if (P.layout == LAYOUT_INTERLEAVED) {
+            slot = j / D;
+            k = j - slot * D;
+          } else {
+            k = j / nnb;
+            slot = j - k * nnb;
+          }
+          const int32_t col = __shfl_sync(0xffffffffu, myCol, valid ? slot : 0);
+          if (valid) xv[u] = __ldg(x + dofOf(P.layout, D, P.nNodes, col, k));
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < D; ++i) s[i] = fma(av[i], xv, s[i]);
-    }
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < D; ++i) s[i] = fma(av[u][i], xv[u], s[i]);
+    } else
+      for (int j = lane; j < len; j += 32) {
+        int slot, k;
+        if (P.layout == LAYOUT_INTERLEAVED) {
+          slot = j / D;
+          k = j - slot * D;
+        } else {
+          k = j / nnb;
+          slot = j - k * nnb;
+        }
+        // the matrix is streamed exactly once: keep it out of L1 (__ldcs) so the gathered x stays resident there
+        double av[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) av[i] = __ldcs(vals + start[i] + j);
+        const double xv = __ldg(x + dofOf(P.layout, D, P.nNodes, __ldg(P.nbrIdx + b0 + slot), k));
+#pragma unroll
+        for (int i = 0; i < D; ++i) s[i] = fma(av[i], xv, s[i]);
+      }
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -139,23 +177,24 @@ __global__ void __launch_bounds__(256) spmv_node_dot_kernel(PatternView P, const
   }
 }
 
-// deterministic fold of np partials by one whole block (every block computes the same value)
+// deterministic fold of np partials by one whole block of 256 threads (every block computes the same value):
+// strided per-thread sums, a shuffle tree per warp, then all threads add the 8 warp sums in the same order
 __device__ __forceinline__ double blockFold(const double* __restrict__ partial, int np, double* sh) {
   double s = 0.0;
   for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
-  sh[threadIdx.x] = s;
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) s += __shfl_down_sync(0xffffffffu, s, w);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
-  for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
-    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-    __syncthreads();
-  }
-  const double r = sh[0];
+  double r = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) r += sh[w];
   __syncthreads();
   return r;
 }
 
 // x += alpha p ; r -= alpha q ; z = dinv r ; block partials of r.z and r.r.  alpha = rz / fold(pq partials).
-__global__ void __launch_bounds__(256) cg2_update_kernel(int64_t n, const CgState* st, const double* __restrict__ pqPartial,
+__global__ void __launch_bounds__(256, 4) cg2_update_kernel(int64_t n, const CgState* st, const double* __restrict__ pqPartial,
                                                          int npq, const double* __restrict__ p,
                                                          const double* __restrict__ q, const double* __restrict__ dinv,
                                                          double* x, double* r, double* z, double* partial) {
@@ -166,14 +205,34 @@ __global__ void __launch_bounds__(256) cg2_update_kernel(int64_t n, const CgStat
   const double rz = st->rz[st->iter & 1];
   const double alpha = pq != 0.0 ? rz / pq : 0.0;
   double s0 = 0.0, s1 = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] = fma(alpha, p[i], x[i]);
-    const double ri = fma(-alpha, q[i], r[i]);
-    r[i] = ri;
-    const double zi = dinv[i] * ri;
-    z[i] = zi;
-    s0 = fma(ri, zi, s0);
-    s1 = fma(ri, ri, s1);
+  // three grid strides are issued together so that the loads of a thread overlap (n is ~3 strides for the C2 mesh)
+  constexpr int UPD = 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += UPD * stride) {
+    double pv[UPD], qv[UPD], xv[UPD], rv[UPD], dv[UPD];
+#pragma unroll
+    for (int u = 0; u < UPD; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool ok = i < n;
+      pv[u] = ok ? p[i] : 0.0;
+      qv[u] = ok ? q[i] : 0.0;
+      xv[u] = ok ? x[i] : 0.0;
+      rv[u] = ok ? r[i] : 0.0;
+      dv[u] = ok ? dinv[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UPD; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        x[i] = fma(alpha, pv[u], xv[u]);
+        const double ri = fma(-alpha, qv[u], rv[u]);
+        r[i] = ri;
+        const double zi = dv[u] * ri;
+        z[i] = zi;
+        s0 = fma(ri, zi, s0);
+        s1 = fma(ri, ri, s1);
+      }
+    }
   }
   sh[threadIdx.x] = s0;
   sh1[threadIdx.x] = s1;
@@ -203,8 +262,22 @@ __global__ void __launch_bounds__(256) cg2_direction_kernel(int64_t n, CgState* 
   const int it = st->iter;
   const double rz = st->rz[it & 1];
   const double beta = rz != 0.0 ? rzNew / rz : 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = fma(beta, p[i], z[i]);
+  constexpr int UPD = 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += UPD * stride) {
+    double pv[UPD], zv[UPD];
+#pragma unroll
+    for (int u = 0; u < UPD; ++u) {
+      const int64_t i = i0 + u * stride;
+      pv[u] = i < n ? p[i] : 0.0;
+      zv[u] = i < n ? z[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UPD; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) p[i] = fma(beta, pv[u], zv[u]);
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
