@@ -181,7 +181,15 @@ __global__ void __launch_bounds__(256, 6) spmv_node_dot_kernel(PatternView P, co
 // strided per-thread sums, a shuffle tree per warp, then all threads add the 8 warp sums in the same order
 __device__ __forceinline__ double blockFold(const double* __restrict__ partial, int np, double* sh) {
   double s = 0.0;
-  for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
+  for (int i0 = threadIdx.x; i0 < np; i0 += 4 * blockDim.x) {  // four independent loads in flight
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < np ? partial[i] : 0.0;
+    }
+    s += (v[0] + v[1]) + (v[2] + v[3]);
+  }
 #pragma unroll
   for (int w = 16; w > 0; w >>= 1) s += __shfl_down_sync(0xffffffffu, s, w);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -234,19 +242,24 @@ __global__ void __launch_bounds__(256, 4) cg2_update_kernel(int64_t n, const CgS
       }
     }
   }
-  sh[threadIdx.x] = s0;
-  sh1[threadIdx.x] = s1;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if ((int)threadIdx.x < w) {
-      sh[threadIdx.x] += sh[threadIdx.x + w];
-      sh1[threadIdx.x] += sh1[threadIdx.x + w];
-    }
-    __syncthreads();
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, w);
+    s1 += __shfl_down_sync(0xffffffffu, s1, w);
   }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = s0;
+    sh1[threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    partial[blockIdx.x] = sh[0];
-    partial[gridDim.x + blockIdx.x] = sh1[0];
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t0 += sh[w];
+      t1 += sh1[w];
+    }
+    partial[blockIdx.x] = t0;
+    partial[gridDim.x + blockIdx.x] = t1;
   }
 }
 
