@@ -303,6 +303,18 @@ def run_ours(args):
             ls = ik.DeviceLinearSolver(relTol=1e-8, maxIter=20000)
             it, rel = C.c_int(), C.c_double()
             step()
+            # TrustRegion inner solve (Steihaug-Toint tCG, diagonal preconditioner) on the same K, g
+            from ikarus_b200 import _capi as capi
+            ti = capi.TcgInfo(delta=1e5, kappa=0.1, theta=1.0, mininner=1, max_iters=4, tol=0.0,
+                              precond=capi.PRECOND_DIAGONAL)
+            asm._check(lib.ikb_tcg_solve(h, DBC, None, None, C.byref(ti)))  # untimed warm-up
+            ti.max_iters = 0
+            t0 = time.perf_counter()
+            asm._check(lib.ikb_tcg_solve(h, DBC, None, None, C.byref(ti)))
+            tcg_ms = (time.perf_counter() - t0) * 1e3
+            extra["trust_region_inner"] = {"ms": tcg_ms, "iterations": int(ti.iterations), "stop_reason": int(ti.stop_reason),
+                                           "us_per_iteration": 1e3 * tcg_ms / max(int(ti.iterations), 1),
+                                           "rel_error": ti.rel_error}
             asm._check(lib.ikb_pcg_solve(h, DBC, None, None, 1e-8, 4, C.byref(it), C.byref(rel)))  # untimed warm-up
             asm._check(lib.ikb_sync(h))
             t0 = time.perf_counter()

@@ -7,7 +7,8 @@ from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, Dev
                         makeDenseFlatAssembler, makeSparseFlatAssembler)
 from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, neumannBoundaryLoad,  # noqa: F401
                  nonLinearElastic, planeStrain, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
-from .solvers import (ControlInformation, DeviceLinearSolver, LoadControl, LoadControlConfig, NewtonRaphson,  # noqa: F401
-                      NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings)
+from .solvers import (ControlInformation, DeviceLinearSolver, DeviceTruncatedCG, LoadControl,  # noqa: F401
+                      LoadControlConfig, NewtonRaphson, NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings,
+                      PreConditioner, TrustRegion, TRSettings)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

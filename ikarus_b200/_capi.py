@@ -21,6 +21,16 @@ class Desc(C.Structure):
                 ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64)]
 
 
+class TcgInfo(C.Structure):
+    """ikb_tcg_info (Eigen::TCGInfo + the model terms TrustRegion needs)."""
+    _fields_ = [("delta", C.c_double), ("kappa", C.c_double), ("theta", C.c_double), ("mininner", C.c_int64),
+                ("max_iters", C.c_int64), ("tol", C.c_double), ("precond", C.c_int32), ("stop_reason", C.c_int32),
+                ("iterations", C.c_int64), ("rel_error", C.c_double), ("eta_norm", C.c_double),
+                ("g_dot_eta", C.c_double), ("eta_h_eta", C.c_double)]
+
+
+PRECOND_IDENTITY, PRECOND_DIAGONAL = 0, 1
+
 # every symbol include/ikb200.h declares (tests check that the library exports all of them)
 SYMBOLS = {
     "ikb_create": [C.POINTER(C.c_void_p), C.POINTER(Desc)],
@@ -52,6 +62,7 @@ SYMBOLS = {
     "ikb_update_solution": [C.c_void_p, C.c_int, C.c_void_p],
     "ikb_get_solution": [C.c_void_p, C.c_void_p],
     "ikb_spmv": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "ikb_tcg_solve": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TcgInfo)],
     "ikb_set_row_ownership": [C.c_void_p, C.c_int64, C.c_int64],
     "ikb_nccl_unique_id": [C.c_void_p],
     "ikb_comm_init": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],

@@ -3,6 +3,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 #include "ikb_dist.cuh"
 #include "ikb_elem_eas.cuh"
@@ -1468,6 +1469,144 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
   if (itersOut) *itersOut = it;
   if (relResOut) *relResOut = bb > 0.0 ? std::sqrt(rr / bb) : 0.0;
   // keep the correction resident at full size for ikb_update_solution / ikb_eas_update
+  if (dbc == IKB_DBC_REDUCED) {
+    expand_reduced_kernel<<<gridFor(h->nDof, tpb), tpb, 0, h->stream>>>(h->nDof, h->flags.p, h->cbelow.p, h->cgX.p,
+                                                                        h->Corr.p);
+    IKB_LAUNCH_CHECK(h);
+  } else {
+    IKB_CUDA(h, cudaMemcpyAsync(h->Corr.p, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (x) IKB_CUDA(h, cudaMemcpyAsync(x, h->cgX.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
+int ikb_tcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, ikb_tcg_info* info) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!info) return fail(h, IKB_EINVAL, "null tcg info");
+  if (dbc != IKB_DBC_FULL && dbc != IKB_DBC_REDUCED) return fail(h, IKB_EINVAL, "tCG needs the Full or Reduced matrix");
+  if (info->precond != IKB_PRECOND_IDENTITY && info->precond != IKB_PRECOND_DIAGONAL)
+    return fail(h, IKB_ENOTIMPL, "tCG preconditioner: only Identity and Diagonal run on the device");
+  if (!(info->delta > 0.0)) return fail(h, IKB_EINVAL, "trust-region radius must be positive");
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
+  if (h->rowBegin != 0 || h->rowEnd != h->nNodes || h->comm)
+    return fail(h, IKB_ENOTIMPL, "tCG on a partitioned handle");
+  const int64_t n = rowsOf(h, dbc);
+  info->iterations = 0;
+  info->stop_reason = IKB_TCG_MAXIMUM_INNER_ITERATIONS;
+  info->rel_error = info->eta_norm = info->g_dot_eta = info->eta_h_eta = 0.0;
+  if (n == 0) return IKB_OK;
+  for (auto* b : {&h->cgR, &h->cgZ, &h->cgP, &h->cgQ, &h->cgX, &h->cgDinv, &h->cgB})
+    if (b->n < (size_t)n) IKB_CUDA(h, b->alloc((size_t)n));
+  if (h->Corr.n < (size_t)h->nDof) IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
+  const int tpb = 256;
+  int rc;
+  double* scal = h->cgScal.p;
+  double hostS[2];
+  auto fetch = [&](const double* dev, int cnt) -> int {
+    IKB_CUDA(h, cudaMemcpyAsync(hostS, dev, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return IKB_OK;
+  };
+  // b (kept for g.eta), residual = b - H*0 = b, x = 0
+  if (rhs) {
+    IKB_CUDA(h, cudaMemcpyAsync(h->cgB.p, rhs, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "resident gradient not assembled");
+    vec_scale_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, -1.0, h->vec[dbc].p, h->cgB.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  IKB_CUDA(h, cudaMemcpyAsync(h->cgR.p, h->cgB.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  IKB_CUDA(h, cudaMemsetAsync(h->cgX.p, 0, (size_t)n * sizeof(double), h->stream));
+  if (info->precond == IKB_PRECOND_DIAGONAL) {
+    if (dbc == IKB_DBC_REDUCED) {
+      if ((rc = ensureReduced(h))) return rc;
+      diag_inv_csr_kernel<<<gridFor(n, tpb), tpb, 0, h->stream>>>(h->redOuter.p, h->redInner.p, h->vals[dbc].p, n,
+                                                                  h->cgDinv.p);
+    } else if (h->dim == 3) {
+      diag_inv_block_kernel<3><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+    } else {
+      diag_inv_block_kernel<2><<<gridFor(h->nBlocks, tpb), tpb, 0, h->stream>>>(h->view(), h->vals[dbc].p, h->cgDinv.p);
+    }
+  } else {
+    vec_fill_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, 1.0, h->cgDinv.p);
+  }
+  IKB_LAUNCH_CHECK(h);
+  // p = Minv r ; absNew = r.p ; |b|^2
+  vec_mul_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, h->cgDinv.p, h->cgR.p, h->cgP.p);
+  IKB_LAUNCH_CHECK(h);
+  if ((rc = deviceDot(h, 1, h->cgR.p, h->cgP.p, n, scal + 0, 1.0, nullptr))) return rc;
+  if ((rc = deviceDot(h, 2, h->cgR.p, nullptr, n, scal + 1, 1.0, nullptr))) return rc;
+  if ((rc = fetch(scal, 2))) return rc;
+  double absNew = hostS[0];
+  const double rhsNorm = std::sqrt(hostS[1]);
+  const double tiny = std::numeric_limits<double>::min();
+  const double tol = info->tol > 0.0 ? info->tol : std::numeric_limits<double>::epsilon();
+  const int64_t maxIters = info->max_iters > 0 ? info->max_iters : 2 * n;
+  const double Delta = info->delta;
+  double resNorm = rhsNorm;
+  int64_t i = 0;
+  int stop = IKB_TCG_MAXIMUM_INNER_ITERATIONS;
+  bool solved = rhsNorm <= tiny;  // x = 0 (:87-92)
+  const double threshold = std::max(tol * tol * rhsNorm * rhsNorm, tiny);
+  if (!solved && resNorm * resNorm < threshold) solved = true;  // :94-99
+  if (!solved) {
+    double e_Pd = 0.0, e_Pe = 0.0, d_Pd = absNew;
+    double* partial = h->scratch.p + MAX_SPMV_BLOCKS;
+    i = 1;
+    while (i < maxIters) {
+      if ((rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p))) return rc;
+      if ((rc = deviceDot(h, 1, h->cgP.p, h->cgQ.p, n, scal + 0, 1.0, nullptr))) return rc;
+      if ((rc = fetch(scal, 1))) return rc;
+      const double d_Hd = hostS[0];
+      const double alpha = absNew / d_Hd;
+      const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+      if (d_Hd <= 0 || e_Pe_new >= Delta * Delta) {  // negative curvature or trust region exceeded (:122-134)
+        const double tau = (-e_Pd + std::sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd;
+        vec_axpy_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, tau, h->cgP.p, h->cgX.p);
+        IKB_LAUNCH_CHECK(h);
+        stop = d_Hd <= 0 ? IKB_TCG_NEGATIVE_CURVATURE : IKB_TCG_EXCEEDED_TRUST_REGION;
+        break;
+      }
+      e_Pe = e_Pe_new;
+      tcg_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, alpha, h->cgP.p, h->cgQ.p, h->cgDinv.p, h->cgX.p, h->cgR.p,
+                                                          h->cgZ.p, partial);
+      IKB_LAUNCH_CHECK(h);
+      cg_fold2_kernel<<<1, tpb, 0, h->stream>>>(partial, RED_BLOCKS, scal, nullptr);  // scal[2] = r.z, scal[3] = r.r
+      IKB_LAUNCH_CHECK(h);
+      if ((rc = fetch(scal + 2, 2))) return rc;
+      resNorm = std::sqrt(hostS[1]);
+      if (!(resNorm == resNorm)) return fail(h, IKB_ECUDA, "tCG produced NaN");
+      if (i >= info->mininner && resNorm <= rhsNorm * std::min(rhsNorm, info->kappa)) {  // :142-150
+        stop = info->kappa < rhsNorm ? IKB_TCG_REACHED_KAPPA_LINEAR : IKB_TCG_REACHED_THETA_SUPERLINEAR;
+        break;
+      }
+      // the reference compares the NORM with the squared-norm threshold here (:151); kept as is
+      if (resNorm < threshold) break;
+      const double absOld = absNew;
+      absNew = hostS[0];
+      const double beta = absNew / absOld;
+      e_Pd = beta * (e_Pd + alpha * d_Pd);
+      d_Pd = absNew + beta * beta * d_Pd;
+      tcg_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, beta, h->cgZ.p, h->cgP.p);
+      IKB_LAUNCH_CHECK(h);
+      ++i;
+    }
+  }
+  info->iterations = i;
+  info->stop_reason = stop;
+  info->rel_error = rhsNorm > tiny ? resNorm / rhsNorm : 0.0;
+  // model terms: |eta|, g.eta = -b.eta, eta.H eta
+  if ((rc = launchSpmv(h, dbc, h->cgX.p, h->cgQ.p))) return rc;
+  if ((rc = deviceDot(h, 2, h->cgX.p, nullptr, n, scal + 0, 1.0, nullptr))) return rc;
+  if ((rc = deviceDot(h, 1, h->cgB.p, h->cgX.p, n, scal + 1, 1.0, nullptr))) return rc;
+  if ((rc = fetch(scal, 2))) return rc;
+  info->eta_norm = std::sqrt(hostS[0]);
+  info->g_dot_eta = -hostS[1];
+  if ((rc = deviceDot(h, 1, h->cgX.p, h->cgQ.p, n, scal + 0, 1.0, nullptr))) return rc;
+  if ((rc = fetch(scal, 1))) return rc;
+  info->eta_h_eta = hostS[0];
   if (dbc == IKB_DBC_REDUCED) {
     expand_reduced_kernel<<<gridFor(h->nDof, tpb), tpb, 0, h->stream>>>(h->nDof, h->flags.p, h->cbelow.p, h->cgX.p,
                                                                         h->Corr.p);

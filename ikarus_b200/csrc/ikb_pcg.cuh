@@ -433,6 +433,52 @@ __global__ void vec_axpy_kernel(int64_t n, double a, const double* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = fma(a, x[i], y[i]);
 }
+// Truncated CG (trust-region inner solve) building blocks; the scalar recurrences live on the host
+// (linearalgebra/truncatedconjugategradient.hh:114-163), so alpha / beta arrive by value.
+//   x += alpha p ; r -= alpha q ; z = minv r ; block partials of r.z and r.r
+__global__ void __launch_bounds__(256) tcg_update_kernel(int64_t n, double alpha, const double* __restrict__ p,
+                                                         const double* __restrict__ q, const double* __restrict__ minv,
+                                                         double* x, double* r, double* z, double* partial) {
+  __shared__ double sh[8], sh1[8];
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    const double zi = minv[i] * ri;
+    z[i] = zi;
+    s0 = fma(ri, zi, s0);
+    s1 = fma(ri, ri, s1);
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, w);
+    s1 += __shfl_down_sync(0xffffffffu, s1, w);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = s0;
+    sh1[threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t0 += sh[w];
+      t1 += sh1[w];
+    }
+    partial[blockIdx.x] = t0;
+    partial[gridDim.x + blockIdx.x] = t1;
+  }
+}
+// p = z + beta p
+__global__ void tcg_direction_kernel(int64_t n, double beta, const double* __restrict__ z, double* p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+__global__ void vec_fill_kernel(int64_t n, double a, double* y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = a;
+}
+
 // full <- reduced expansion / reduced <- full contraction (createFullVector / createReducedVector,
 // assembler/simpleassemblers.inl:26-57)
 __global__ void expand_reduced_kernel(int64_t n, const uint8_t* __restrict__ flags, const int32_t* __restrict__ cbelow,

@@ -4,6 +4,7 @@ the reference's own templates (solver/nonlinearsolver/newtonraphson.hh, controlr
 drive include/ikarus_b200/deviceflatassembler.hh unchanged when DUNE is available.
 """
 import ctypes as C
+import enum
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -157,4 +158,168 @@ class LoadControl:
             if not si.success:
                 return info
         info.success = True
+        return info
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TrustRegion with the truncated CG on the device
+class PreConditioner(enum.Enum):
+    """solver/nonlinearsolver/trustregion.hh:31-36"""
+    IncompleteCholesky = 0
+    IdentityPreconditioner = 1
+    DiagonalPreconditioner = 2
+
+
+@dataclass
+class TRSettings:
+    """solver/nonlinearsolver/trustregion.hh:38-52"""
+    verbosity: int = 5
+    maxtime: float = float("inf")
+    minIter: int = 3
+    maxIter: int = 1000
+    debug: int = 0
+    grad_tol: float = 1e-6
+    corr_tol: float = 1e-6
+    rho_prime: float = 0.01
+    useRand: bool = False
+    rho_reg: float = 1e6
+    Delta_bar: float = float("inf")
+    Delta0: float = 10.0
+
+
+TCG_STOP_REASON = ("negative curvature", "exceeded trust region", "reached target residual-kappa (linear)",
+                   "reached target residual-theta (superlinear)", "maximum inner iterations", "model increased")
+
+
+class DeviceTruncatedCG:
+    """Eigen::TruncatedConjugateGradient (linearalgebra/truncatedconjugategradient.hh:170-282) on the resident matrix:
+    `solveWithGuess(rhs, 0)` under the trust-region radius `Delta`.  Identity and Diagonal preconditioners."""
+
+    def __init__(self, preConditioner=PreConditioner.DiagonalPreconditioner, kappa=0.1, theta=1.0, mininner=1,
+                 maxIterations=None, tolerance=None):
+        if preConditioner == PreConditioner.IncompleteCholesky:
+            raise NotImplementedError("IncompleteCholesky is a sequential factorisation: use the Diagonal or Identity "
+                                      "preconditioner on the device, or mirror mode with the reference's own tCG")
+        self.precond = (capi.PRECOND_DIAGONAL if preConditioner == PreConditioner.DiagonalPreconditioner
+                        else capi.PRECOND_IDENTITY)
+        self.kappa, self.theta, self.mininner = kappa, theta, mininner
+        self.maxIterations, self.tolerance = maxIterations, tolerance
+        self.info = None
+
+    def solve(self, Ax, rhs, Delta, download=True):
+        if not isinstance(Ax, DeviceMatrix):
+            raise TypeError("DeviceTruncatedCG needs the assembler in resident mode (matrix() -> DeviceMatrix)")
+        asm = Ax.assembler
+        n = Ax.shape[0]
+        info = capi.TcgInfo(delta=float(Delta), kappa=self.kappa, theta=self.theta, mininner=self.mininner,
+                            max_iters=int(self.maxIterations or 0), tol=float(self.tolerance or 0.0),
+                            precond=self.precond)
+        b = None if rhs is None else capi.as_f64(rhs)
+        x = np.empty(n) if download else None
+        asm._check(asm._lib.ikb_tcg_solve(asm._h, int(Ax.dbc), capi.ptr(b), capi.ptr(x), C.byref(info)))
+        self.info = info
+        return x
+
+
+class TrustRegion:
+    """solver/nonlinearsolver/trustregion.hh:226-430 on an assembler bound with
+    AffordanceCollections.elastoStatics: energy = scalar(), gradient = vector(), Hessian = matrix() (resident),
+    inner problem by DeviceTruncatedCG.  The random correction predictor (useRand) is not mirrored."""
+
+    def __init__(self, assembler, settings: TRSettings = None, preConditioner=PreConditioner.DiagonalPreconditioner):
+        self.assembler = assembler
+        self.settings = settings or TRSettings()
+        if self.settings.useRand:
+            raise NotImplementedError("TRSettings.useRand")
+        s = self.settings
+        assert s.rho_prime < 0.25 and s.Delta_bar > 0 and 0 < s.Delta0 < s.Delta_bar  # setup() (:218-224)
+        self.tcg = DeviceTruncatedCG(preConditioner)
+        self.listeners = []
+        self.history = []
+        self.innerIterSum = 0
+
+    def _notify(self, msg, **kw):
+        for f in self.listeners:
+            f(msg, **kw)
+
+    def solve(self, req, stepSize=0.0):
+        asm, s = self.assembler, self.settings
+        eps_ = 0.0001220703125  # sqrt(sqrt(machine precision)) (:563)
+        info = NonLinearSolverInformation()
+        self.history, self.innerIterSum = [], 0
+        self._notify("INIT")
+        e = float(asm.scalar(req))
+        g = np.array(asm.vector(req))
+        h = asm.matrix(req)
+        energy, gradNorm, etaNorm, outer = e, float(np.linalg.norm(g)), 0.0, 0
+        Delta = s.Delta0
+        rejected = 0
+        stop = None
+        d = req.globalSolution()
+        dbc = asm.dBCOption()
+        while True:
+            if gradNorm < s.grad_tol and outer != 0:
+                stop = "gradientNormTolReached"
+                break
+            if etaNorm < s.corr_tol and outer != 0:
+                stop = "correctionNormTolReached"
+                break
+            if outer >= s.maxIter:
+                stop = "maximumIterationsReached"
+                break
+            self._notify("ITERATION_STARTED")
+            eta = self.tcg.solve(h, None, Delta)  # H eta = -g with the resident gradient
+            ti = self.tcg.info
+            self.innerIterSum += ti.iterations
+            etaNorm = ti.eta_norm
+            full = asm.createFullVector(eta) if dbc == DBCOption.Reduced and eta.shape[0] != d.shape[0] else eta
+            d += full
+            e = float(asm.scalar(req))
+            proposal = e
+            rhonum = energy - proposal
+            rhoden = -(ti.g_dot_eta + 0.5 * ti.eta_h_eta)
+            rhoReg = max(1.0, abs(energy)) * eps_ * s.rho_reg
+            rhonum += rhoReg
+            rhoden += rhoReg
+            modelDecreased = rhoden > 0.0
+            rho = rhonum / rhoden
+            rho = -1.0 if rho < 0.0 else rho
+            a_, b_ = energy - proposal, -1e-12  # Dune::FloatCmp::ge (:346)
+            energyDecreased = a_ > b_ or abs(a_ - b_) <= 8 * np.finfo(float).eps * max(abs(a_), abs(b_))
+            tr = "   "
+            if rho < 1e-4 or not modelDecreased or np.isnan(rho) or not energyDecreased:
+                tr = "TR-"
+                Delta /= 4.0
+            elif rho > 0.99 and ti.stop_reason in (0, 1):
+                tr = "TR+"
+                Delta = min(3.5 * Delta, s.Delta_bar)
+            if modelDecreased and rho > s.rho_prime and energyDecreased:
+                accept = True
+                rejected = 0
+            else:
+                accept = False
+                Delta = Delta / 2 if rejected >= 5 else min(Delta, etaNorm / 2.0)
+                rejected += 1
+            outer += 1
+            info.correctionNorm, info.residualNorm = etaNorm, gradNorm
+            self._notify("CORRECTION_UPDATED", correction=full)
+            self.history.append(dict(accept=accept, tr=tr, inner=int(ti.iterations), stop=int(ti.stop_reason), rho=rho,
+                                     energy=energy, proposal=proposal, Delta=Delta, eta_norm=etaNorm))
+            if accept:
+                energy = proposal
+                self._notify("SOLUTION_CHANGED")
+            else:
+                d -= full
+            e = float(asm.scalar(req))
+            g = np.array(asm.vector(req))
+            h = asm.matrix(req)
+            gradNorm = float(np.linalg.norm(g))
+            self._notify("ITERATION_ENDED")
+        info.success = stop in ("correctionNormTolReached", "gradientNormTolReached")
+        info.iterations = outer
+        info.residualNorm = gradNorm
+        self.stopReason = stop
+        self.energy = e
+        if info.success:
+            self._notify("FINISHED_SUCESSFULLY")
         return info

@@ -137,6 +137,41 @@ int ikb_eas_set_alpha(ikb_handle h, const double* alpha);
  * resident residual.  Stops at ||r|| <= rel_tol*||rhs||. */
 int ikb_pcg_solve(ikb_handle h, int dbc, const double* rhs, double* x, double rel_tol, int max_it, int* iters,
                   double* rel_res);
+/* Steihaug-Toint truncated CG on the assembled matrix of mode dbc: the inner solver of
+ * TrustRegion, Eigen::TruncatedConjugateGradient with the Identity or Diagonal preconditioner
+ * (linearalgebra/truncatedconjugategradient.hh:68-168, solver/nonlinearsolver/trustregion.hh:529-547),
+ * started from x = 0 like TrustRegion::solve does (:262).  rhs == NULL solves H eta = -g with
+ * the resident gradient g = R.  x may be NULL: eta stays resident as the correction for
+ * ikb_update_solution / ikb_eas_update.  The model terms TrustRegion needs afterwards
+ * (|eta|, g.eta, eta.H eta; trustregion.hh:268, 317, 327) are returned so that no vector
+ * has to leave the device. */
+enum { IKB_PRECOND_IDENTITY = 0, IKB_PRECOND_DIAGONAL = 1 };
+enum {
+  IKB_TCG_NEGATIVE_CURVATURE = 0,
+  IKB_TCG_EXCEEDED_TRUST_REGION = 1,
+  IKB_TCG_REACHED_KAPPA_LINEAR = 2,
+  IKB_TCG_REACHED_THETA_SUPERLINEAR = 3,
+  IKB_TCG_MAXIMUM_INNER_ITERATIONS = 4,
+  IKB_TCG_MODEL_INCREASED = 5
+}; /* Eigen::TCGStopReason, truncatedconjugategradient.hh:25-33 */
+typedef struct ikb_tcg_info {
+  /* in (TCGInfo, truncatedconjugategradient.hh:34-50) */
+  double delta;       /* trust-region radius */
+  double kappa;       /* 0.1 */
+  double theta;       /* 1.0 (unused by the reference's stopping rule, kept for layout parity) */
+  int64_t mininner;   /* 1 */
+  int64_t max_iters;  /* <= 0: 2 n (Eigen::IterativeSolverBase default) */
+  double tol;         /* <= 0: machine epsilon (Eigen default) */
+  int32_t precond;    /* IKB_PRECOND_* */
+  /* out */
+  int32_t stop_reason; /* IKB_TCG_* */
+  int64_t iterations;
+  double rel_error;   /* |r| / |rhs| */
+  double eta_norm;    /* |eta|_2 */
+  double g_dot_eta;   /* g.eta with g = -rhs */
+  double eta_h_eta;   /* eta.(H eta) */
+} ikb_tcg_info;
+int ikb_tcg_solve(ikb_handle h, int dbc, const double* rhs, double* x, ikb_tcg_info* info);
 /* x += correction on the resident solution (NonlinearSolverFactory update functor,
  * solver/nonlinearsolver/nonlinearsolverfactory.hh:33-56); correction lives on the device
  * (last PCG result) when correction == NULL. dbc selects Reduced->Full expansion. */

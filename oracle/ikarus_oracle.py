@@ -739,3 +739,159 @@ def load_control(asm: FlatAssembler, d, load_steps, t_begin, t_end, lam0=0.0, **
         ok = info["success"]
         curve.append((lam, float(np.abs(d).max())))
     return d, lam, dict(total_iterations=total, success=ok, curve=curve, per_step=per_step)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Trust region with Steihaug-Toint truncated CG.
+# Restates ikarus/linearalgebra/truncatedconjugategradient.hh:68-168 and
+# ikarus/solver/nonlinearsolver/trustregion.hh:226-430, 481-547.  Pinned by tests/src/testtrustregion.cpp:124-190
+# (11 outer iterations with the identity, 8 with the diagonal preconditioner, minimiser and energy to 1e-12).
+TCG_STOP = ("negative curvature", "exceeded trust region", "reached target residual-kappa (linear)",
+            "reached target residual-theta (superlinear)", "maximum inner iterations", "model increased")
+
+
+def diagonal_preconditioner(A):
+    """Eigen::DiagonalPreconditioner: 1/diag, 1 where the diagonal is zero."""
+    dg = np.asarray(A.diagonal(), float)
+    return np.where(dg != 0.0, 1.0 / np.where(dg != 0.0, dg, 1.0), 1.0)
+
+
+def truncated_cg(A, b, x0, minv, Delta, kappa=0.1, theta=1.0, mininner=1, max_iters=None, tol=np.finfo(float).eps):
+    """internal::truncated_conjugate_gradient (truncatedconjugategradient.hh:68-168).  `minv` is the inverse
+    diagonal (ones for the identity preconditioner).  Returns x, info(iterations, stop, rel_error)."""
+    n = b.shape[0]
+    if max_iters is None:
+        max_iters = 2 * n  # Eigen::IterativeSolverBase default
+    x = np.array(x0, float)
+    residual = b - A @ x
+    rhs_norm = np.linalg.norm(b)
+    tiny = np.finfo(float).tiny
+    if rhs_norm <= tiny:
+        return np.zeros(n), dict(iterations=0, stop=4, rel_error=0.0)
+    threshold = max(tol * tol * rhs_norm * rhs_norm, tiny)
+    res_norm = np.linalg.norm(residual)
+    if res_norm * res_norm < threshold:
+        return x, dict(iterations=0, stop=4, rel_error=res_norm / rhs_norm)
+    e_Pd = 0.0
+    e_Pe = float(x @ x)
+    p = minv * residual
+    stop = 4  # maximumInnerIterations
+    abs_new = float(residual @ p)
+    d_Pd = abs_new
+    i = 1
+    while i < max_iters:
+        tmp = A @ p
+        d_Hd = float(p @ tmp)
+        # alpha is formed before the curvature test, exactly as in the reference (inf/nan for d_Hd == 0 is harmless:
+        # the branch below is taken)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            alpha = np.float64(abs_new) / np.float64(d_Hd)
+            e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd
+        if d_Hd <= 0 or e_Pe_new >= Delta * Delta:
+            tau = (-e_Pd + np.sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd
+            x = x + tau * p
+            stop = 0 if d_Hd <= 0 else 1
+            break
+        e_Pe = e_Pe_new
+        x = x + alpha * p
+        residual = residual - alpha * tmp
+        res_norm = np.linalg.norm(residual)
+        if i >= mininner and res_norm <= rhs_norm * min(rhs_norm, kappa):
+            stop = 2 if kappa < rhs_norm else 3
+            break
+        if res_norm < threshold:
+            break
+        z = minv * residual
+        abs_old = abs_new
+        abs_new = float(residual @ z)
+        beta = abs_new / abs_old
+        e_Pd = beta * (e_Pd + alpha * d_Pd)
+        d_Pd = abs_new + beta * beta * d_Pd
+        p = z + beta * p
+        i += 1
+    return x, dict(iterations=i, stop=stop, rel_error=res_norm / rhs_norm)
+
+
+def trust_region(energy, gradient, hessian, x, update=None, precond="diagonal", min_iter=3, max_iter=1000,
+                 grad_tol=1e-6, corr_tol=1e-6, rho_prime=0.01, rho_reg=1e6, Delta_bar=np.inf, Delta0=10.0,
+                 on_correction=None):
+    """TrustRegion::solve (trustregion.hh:226-430) without the random predictor.  `update(x, eta)` returns the new
+    point (default x + eta); `on_correction(x, eta)` is the CORRECTION_UPDATED hook (EAS), called like the reference
+    after the proposal was applied and before acceptance is decided (:396)."""
+    if update is None:
+        update = lambda xx, eta: xx + eta
+    eps_ = 0.0001220703125
+    x = np.array(x, float)
+    e = energy(x)
+    g = gradient(x)
+    h = hessian(x)
+    n = g.shape[0]
+    stats = dict(energy=e, grad_norm=float(np.linalg.norm(g)), eta_norm=0.0, outer=0, inner_sum=0, rho=0.0)
+    Delta = Delta0
+    consecutive_rejected = 0
+    history = []
+    stop_reason = None
+    while True:
+        # stoppingCriterion (:481-527)
+        if stats["grad_norm"] < grad_tol and stats["outer"] != 0:
+            stop_reason = "gradient"
+            break
+        if stats["eta_norm"] < corr_tol and stats["outer"] != 0:
+            stop_reason = "correction"
+            break
+        if stats["outer"] >= max_iter:
+            stop_reason = "maxiter"
+            break
+        minv = diagonal_preconditioner(h) if precond == "diagonal" else np.ones(n)
+        eta, inner = truncated_cg(h, -g, np.zeros(n), minv, Delta)
+        stats["inner_sum"] += inner["iterations"]
+        Heta = h @ eta
+        stats["eta_norm"] = float(np.linalg.norm(eta))
+        x = update(x, eta)
+        e = energy(x)
+        proposal = e
+        rhonum = stats["energy"] - proposal
+        rhoden = -float(eta @ (g + 0.5 * Heta))
+        rho_r = max(1.0, abs(stats["energy"])) * eps_ * rho_reg
+        rhonum += rho_r
+        rhoden += rho_r
+        model_decreased = rhoden > 0.0
+        rho = rhonum / rhoden
+        rho = -1.0 if rho < 0.0 else rho
+        # Dune::FloatCmp::ge(energy - proposal, -1e-12): '>' or equal within the default relative-weak epsilon
+        a_, b_ = stats["energy"] - proposal, -1e-12
+        energy_decreased = a_ > b_ or abs(a_ - b_) <= 8 * np.finfo(float).eps * max(abs(a_), abs(b_))
+        tr = "   "
+        if rho < 1e-4 or not model_decreased or np.isnan(rho) or not energy_decreased:
+            tr = "TR-"
+            Delta /= 4.0
+        elif rho > 0.99 and inner["stop"] in (0, 1):
+            tr = "TR+"
+            Delta = min(3.5 * Delta, Delta_bar)
+        if model_decreased and rho > rho_prime and energy_decreased:
+            accept = True
+            consecutive_rejected = 0
+        else:
+            accept = False
+            if consecutive_rejected >= 5:
+                Delta /= 2
+            else:
+                Delta = min(Delta, stats["eta_norm"] / 2.0)
+            consecutive_rejected += 1
+        stats["outer"] += 1
+        stats["rho"] = rho
+        if on_correction is not None:
+            on_correction(x, eta)
+        history.append(dict(accept=accept, tr=tr, inner=inner["iterations"], stop=inner["stop"], rho=rho,
+                            energy=stats["energy"], proposal=proposal, Delta=Delta, eta_norm=stats["eta_norm"]))
+        if accept:
+            stats["energy"] = proposal
+        else:
+            x = update(x, -eta)
+        e = energy(x)
+        g = gradient(x)
+        h = hessian(x)
+        stats["grad_norm"] = float(np.linalg.norm(g))
+    success = stop_reason in ("gradient", "correction")
+    return x, dict(iterations=stats["outer"], success=success, residual_norm=stats["grad_norm"], energy=e,
+                   inner_iterations=stats["inner_sum"], stop=stop_reason, history=history)
