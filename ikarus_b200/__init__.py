@@ -9,6 +9,6 @@ from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, ma
                  nonLinearElastic, planeStrain, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
 from .solvers import (ControlInformation, DeviceLinearSolver, DeviceTruncatedCG, LoadControl,  # noqa: F401
                       LoadControlConfig, NewtonRaphson, NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings,
-                      PreConditioner, TrustRegion, TRSettings)
+                      PreConditioner, TrustRegion, TRSettings, obtainForcesDueToIDBC)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -6,6 +6,7 @@ createFullVector(), createReducedVector() with the semantics of
 ikarus/assembler/interface.hh:51-462 and simpleassemblers.inl.  All arithmetic runs in
 libikb200.so on the GPU; there is no CPU path.
 """
+import copy
 import ctypes as C
 import enum
 from dataclasses import dataclass
@@ -119,8 +120,10 @@ class _FlatAssemblerBase:
             raise ValueError(mode)
         self._lib = capi.load()
         self._fes = fes
-        self._dv = DirichletValues(dirichletValues.size())
-        self._dv.container()[:] = dirichletValues.container()  # the reference copies DirichletValues (:260)
+        self._dv = copy.copy(dirichletValues)  # the reference copies DirichletValues (:260): flags AND functions
+        self._dv._flags = np.array(dirichletValues.container(), dtype=bool)
+        if hasattr(dirichletValues, "_functions"):
+            self._dv._functions = list(dirichletValues._functions)
         self._mode = mode
         flags = self._dv.container()
         self._n = int(fes.n_dof)
@@ -237,6 +240,16 @@ class _FlatAssemblerBase:
         full = np.asarray(full, float)
         assert full.shape[0] == self._n, "The full vector you passed has the wrong dimensions."
         return full[~self._dv.container()].copy()
+
+    def obtainForcesDueToIDBC(self):
+        """utils::obtainForcesDueToIDBC (utils/functionhelper.hh:170-185) for the bound requirement and DBC option:
+        K_raw * d(d_D)/d(lambda), zeroed at constrained dofs (Full) or reduced; the SpMV runs on the device."""
+        dbc = self.dBCOption()
+        self._push(self._req)
+        inc = capi.as_f64(self._dv.evaluateInhomogeneousBoundaryConditionDerivative(1.0))
+        out = np.empty(self._n if dbc == DBCOption.Full else self._nred)
+        self._check(self._lib.ikb_idbc_forces(self._h, int(dbc), capi.ptr(inc), capi.ptr(out)))
+        return out
 
     def bind(self, req=None, affordanceCollection=None, dbcOption=None):
         """interface.hh:150-180: stores a reference to the requirement (identity is tested in

@@ -1335,6 +1335,38 @@ int ikb_spmv(ikb_handle hh, int dbc, const double* x, double* y) {
   return IKB_OK;
 }
 
+int ikb_idbc_forces(ikb_handle hh, int dbc, const double* dInc, double* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!dbcValid(dbc) || !dInc || !out) return fail(h, IKB_EINVAL, "bad arguments");
+  if (!h->hasFlags) return fail(h, IKB_ESTATE, "Dirichlet flags missing");
+  if (h->rowBegin != 0 || h->rowEnd != h->nNodes || h->comm)
+    return fail(h, IKB_ENOTIMPL, "inhomogeneous Dirichlet forces on a partitioned handle");
+  int rc;
+  if ((rc = ikb_assemble(hh, IKB_MATRIX, IKB_DBC_RAW))) return rc;  // assembler->matrix(DBCOption::Raw) (:172)
+  const int64_t n = h->nDof;
+  if (n == 0) return IKB_OK;
+  if (h->cgP.n < (size_t)n) IKB_CUDA(h, h->cgP.alloc((size_t)n));
+  if (h->cgQ.n < (size_t)n) IKB_CUDA(h, h->cgQ.alloc((size_t)n));
+  IKB_CUDA(h, cudaMemcpyAsync(h->cgP.p, dInc, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launchSpmv(h, IKB_DBC_RAW, h->cgP.p, h->cgQ.p))) return rc;
+  const int tpb = 256;
+  if (dbc == IKB_DBC_FULL) {
+    zero_flagged_kernel<<<gridFor(n, tpb), tpb, 0, h->stream>>>(n, h->flags.p, h->cgQ.p);  // setZeroAtConstrainedDofs
+    IKB_LAUNCH_CHECK(h);
+    IKB_CUDA(h, cudaMemcpyAsync(out, h->cgQ.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    if ((rc = ensureReduced(h))) return rc;
+    if (h->cgZ.n < (size_t)std::max<int64_t>(h->nRed, 1)) IKB_CUDA(h, h->cgZ.alloc((size_t)std::max<int64_t>(h->nRed, 1)));
+    contract_full_kernel<<<gridFor(n, tpb), tpb, 0, h->stream>>>(n, h->flags.p, h->cbelow.p, h->cgQ.p, h->cgZ.p);
+    IKB_LAUNCH_CHECK(h);
+    if (h->nRed)
+      IKB_CUDA(h, cudaMemcpyAsync(out, h->cgZ.p, (size_t)h->nRed * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return IKB_OK;
+}
+
 int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double relTol, int maxIt, int* itersOut,
                   double* relResOut) {
   Handle* h = H(hh);

@@ -492,6 +492,11 @@ __global__ void contract_full_kernel(int64_t n, const uint8_t* __restrict__ flag
   if (i < n && !flags[i]) red[i - cbelow[i]] = full[i];
 }
 
+__global__ void zero_flagged_kernel(int64_t n, const uint8_t* __restrict__ flags, double* v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) v[i] = 0.0;
+}
+
 // FP64 FMA peak probe: 8 independent chains per thread
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

@@ -268,10 +268,15 @@ def makeFE(basis, sk, corner_coords=None, elem_dofs=None):
 
 
 class DirichletValues:
-    """utils/dirichletvalues.hh:73-311 (flags only; inhomogeneous BC functions are SURVEY 8f 'next')."""
+    """utils/dirichletvalues.hh:73-311: the flags plus (with `nodeCoords` given) the inhomogeneous boundary functions.
+    `nodeCoords` are the positions of the Lagrange nodes in global node numbering ([nNodes, dim]); interpolation of a
+    nodal function into the power basis is point evaluation there."""
 
-    def __init__(self, n_dof):
+    def __init__(self, n_dof, nodeCoords=None, layout="interleaved"):
         self._flags = np.zeros(int(n_dof), dtype=bool)
+        self._coords = None if nodeCoords is None else np.asarray(nodeCoords, float)
+        self._layout = layout
+        self._functions = []  # (value(x, lam), derivative(x, lam))
 
     def fixDOFs(self, f):
         f(self._flags)
@@ -293,3 +298,37 @@ class DirichletValues:
 
     def container(self):
         return self._flags
+
+    # ---- inhomogeneous values (dirichletvalues.hh:214-302)
+    def storeInhomogeneousBoundaryCondition(self, f, lambda_=1.0, derivative=None):
+        """`f(globalCoord, lambda) -> dim values`.  The reference differentiates f in lambda with autodiff (:215-219);
+        here `derivative(globalCoord, lambda)` may be given, otherwise a complex step is used (exact to rounding for
+        functions built from arithmetic and numpy ufuncs)."""
+        if self._coords is None:
+            raise RuntimeError("DirichletValues needs nodeCoords to interpolate inhomogeneous boundary functions")
+        if derivative is None:
+            def derivative(x, lam, _f=f):
+                return np.imag(np.asarray(_f(x, complex(lam, 1e-30)), dtype=complex)) / 1e-30
+        self._functions.append((f, derivative))
+        inc = self.evaluateInhomogeneousBoundaryCondition(lambda_)  # setInhomogeneousBoundaryConditionFlag (:296-302)
+        self._flags[inc != 0.0] = True
+
+    def _interpolate(self, which, lam):
+        nn, dim = self._coords.shape
+        out = np.zeros(self.size())
+        for fn in self._functions:
+            vals = np.array([np.real(np.asarray(fn[which](x, lam))).astype(float) for x in self._coords])
+            out += vals.reshape(-1) if self._layout == "interleaved" else vals.T.reshape(-1)
+        return out
+
+    def evaluateInhomogeneousBoundaryCondition(self, lam):
+        return self._interpolate(0, lam)
+
+    def evaluateInhomogeneousBoundaryConditionDerivative(self, lam):
+        return self._interpolate(1, lam)
+
+    def hasInhomogeneousBoundaryConditions(self):
+        return bool(self._functions)
+
+    def setZeroAtConstrainedDofs(self, x):
+        x[self._flags] = 0.0

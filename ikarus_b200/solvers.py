@@ -25,6 +25,14 @@ class NRSettings:
 class NewtonRaphsonConfig:
     parameters: NRSettings = field(default_factory=NRSettings)
     linearSolver: object = None
+    # NonlinearSolverFactory::withIDBCForceFunction(assembler) (nonlinearsolverfactory.hh:88-104): callable
+    # `assembler -> forces due to inhomogeneous Dirichlet values`; None = utils::IDBCForceDefault (no such forces)
+    idbcForceFunction: object = None
+
+
+def obtainForcesDueToIDBC(assembler):
+    """utils/functionhelper.hh:170-185"""
+    return assembler.obtainForcesDueToIDBC()
 
 
 @dataclass
@@ -84,7 +92,15 @@ class NewtonRaphson:
         cfg = config or NewtonRaphsonConfig()
         self.settings = cfg.parameters
         self.linearSolver = cfg.linearSolver or SparseDirectSolver()
+        self.idbcForceFunction = cfg.idbcForceFunction
         self.listeners = []
+
+    def syncParameterAndGlobalSolution(self, req):
+        """Impl::updateFunctor with SyncFERequirements (nonlinearsolverfactory.hh:45-54): prescribed values of the
+        inhomogeneous Dirichlet functions at the current lambda overwrite the solution."""
+        inc = self.assembler.dirichletValues().evaluateInhomogeneousBoundaryCondition(req.parameter())
+        nz = inc != 0.0
+        req.globalSolution()[nz] = inc[nz]
 
     def _notify(self, msg, **kw):
         for f in self.listeners:
@@ -99,6 +115,9 @@ class NewtonRaphson:
         rNorm = float(np.linalg.norm(rx))
         info.residualNorm = rNorm
         it = 0
+        if self.idbcForceFunction is not None:  # newtonraphson.hh:214-217
+            rx = rx + self.idbcForceFunction(asm) * stepSize
+            rNorm = float(np.linalg.norm(rx))
         while (rNorm > s.tol and it < s.maxIter) or it < s.minIter:
             correction = -np.asarray(self.linearSolver(rx, Ax))
             info.correctionNorm = float(np.linalg.norm(correction))
@@ -111,6 +130,8 @@ class NewtonRaphson:
                 d += asm.createFullVector(correction)
             else:
                 d += correction
+            if self.idbcForceFunction is not None:  # :237-238
+                self.syncParameterAndGlobalSolution(req)
             self._notify("SOLUTION_CHANGED")
             rx = asm.vector(req)
             Ax = asm.matrix(req)
@@ -151,6 +172,8 @@ class LoadControl:
         for ls in range(self.loadSteps):
             req.setParameter(req.parameter() + self.stepSize)  # predictor (:56)
             si = self.nls.solve(req, self.stepSize)
+            if si.iterations == 0 and getattr(self.nls, "idbcForceFunction", None) is not None:
+                self.nls.syncParameterAndGlobalSolution(req)  # loadcontrol.inl:44-46
             info.solverInfos.append(si)
             info.totalIterations += si.iterations
             for f in self.listeners:

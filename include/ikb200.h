@@ -172,6 +172,11 @@ typedef struct ikb_tcg_info {
   double eta_h_eta;   /* eta.(H eta) */
 } ikb_tcg_info;
 int ikb_tcg_solve(ikb_handle h, int dbc, const double* rhs, double* x, ikb_tcg_info* info);
+/* Forces due to inhomogeneous Dirichlet boundary conditions, utils::obtainForcesDueToIDBC
+ * (utils/functionhelper.hh:170-185): F = K_raw * d_inc with d_inc = d(d_D)/d(lambda) (N entries, the caller
+ * evaluates its boundary functions), then zeroed at constrained dofs (dbc == Full, N entries out) or
+ * reduced (otherwise, N_red entries out).  The Raw matrix of the current state is assembled on demand. */
+int ikb_idbc_forces(ikb_handle h, int dbc, const double* d_inc, double* out);
 /* x += correction on the resident solution (NonlinearSolverFactory update functor,
  * solver/nonlinearsolver/nonlinearsolverfactory.hh:33-56); correction lives on the device
  * (last PCG result) when correction == NULL. dbc selects Reduced->Full expansion. */

@@ -697,7 +697,54 @@ class FlatAssembler:
 # --------------------------------------------------------------------------------------
 
 
-def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full", linear_solver=None):
+class InhomogeneousDirichlet:
+    """The inhomogeneous part of DirichletValues (utils/dirichletvalues.hh:214-281): nodal functions f(x, lambda)
+    interpolated into the flat dof vector (Lagrange nodes => point evaluation), their lambda-derivatives, and the
+    flag rule of setInhomogeneousBoundaryConditionFlag (:296-302: every dof whose value at `lambda0` is non-zero
+    becomes constrained).  `fns` = list of (value(x, lam) -> dim-vector, derivative(x, lam) -> dim-vector)."""
+
+    def __init__(self, mesh: Mesh, fns, layout="interleaved"):
+        self.mesh, self.fns, self.layout = mesh, list(fns), layout
+
+    def _interp(self, which, lam):
+        m = self.mesh
+        out = np.zeros(m.n_nodes * m.dim)
+        for f in self.fns:
+            vals = np.array([np.asarray(f[which](x, lam), float) for x in m.node_coords])  # [nNodes, dim]
+            out += vals.reshape(-1) if self.layout == "interleaved" else vals.T.reshape(-1)
+        return out
+
+    def values(self, lam):
+        return self._interp(0, lam)
+
+    def derivative(self, lam):
+        return self._interp(1, lam)
+
+    def flag(self, flags, lam0=1.0):
+        flags = np.array(flags, dtype=bool)
+        flags[self.values(lam0) != 0.0] = True
+        return flags
+
+    def sync(self, d, lam):
+        """Impl::updateFunctor, SyncFERequirements branch (nonlinearsolverfactory.hh:45-54)."""
+        inc = self.values(lam)
+        nz = inc != 0.0
+        d[nz] = inc[nz]
+        return d
+
+
+def idbc_forces(asm: "FlatAssembler", d, lam, dbc, idbc: InhomogeneousDirichlet):
+    """utils::obtainForcesDueToIDBC (utils/functionhelper.hh:170-185): K_raw * d(d_D)/d(lambda) at lambda = 1, zeroed at
+    constrained dofs (Full) or reduced (otherwise)."""
+    F = asm.matrix(d, lam, "raw") @ idbc.derivative(1.0)
+    if dbc == "full":
+        F[asm.flags] = 0.0
+        return F
+    return asm.create_reduced_vector(F)
+
+
+def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full", linear_solver=None, idbc=None,
+                   step_size=0.0):
     import scipy.sparse.linalg as spla
 
     if linear_solver is None:
@@ -705,6 +752,8 @@ def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full"
     d = np.array(d, float)
     r = asm.vector(d, lam, dbc)
     A = asm.matrix(d, lam, dbc)
+    if idbc is not None:
+        r = r + idbc_forces(asm, d, lam, dbc, idbc) * step_size  # newtonraphson.hh:214-217
     rnorm = np.linalg.norm(r)
     it = 0
     while rnorm > tol and it < max_iter:
@@ -712,6 +761,8 @@ def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full"
         full = corr if dbc != "reduced" else asm.create_full_vector(corr)
         asm.update_eas(d, full)  # CORRECTION_UPDATED before the solution update (:230-235)
         d = d + full
+        if idbc is not None:
+            d = idbc.sync(d, lam)  # x.syncParameterAndGlobalSolution (:237-238)
         r = asm.vector(d, lam, dbc)
         A = asm.matrix(d, lam, dbc)
         rnorm = np.linalg.norm(r)
@@ -720,10 +771,12 @@ def newton_raphson(asm: FlatAssembler, d, lam, tol=1e-8, max_iter=20, dbc="full"
 
 
 def load_control(asm: FlatAssembler, d, load_steps, t_begin, t_end, lam0=0.0, **nr):
-    """LoadControl::run: initial solve at the current lambda, then loadSteps increments."""
+    """LoadControl::run: initial solve at the current lambda, then loadSteps increments (with inhomogeneous Dirichlet
+    values the step size is handed to the solver and a step with 0 iterations still syncs d, loadcontrol.inl:44-46)."""
     step = (t_end - t_begin) / load_steps
     lam = lam0
     total = 0
+    idbc = nr.get("idbc")
     d, info = newton_raphson(asm, d, lam, **nr)
     total += info["iterations"]
     curve = [(lam, float(np.abs(d).max()))]
@@ -733,7 +786,9 @@ def load_control(asm: FlatAssembler, d, load_steps, t_begin, t_end, lam0=0.0, **
         if not ok:
             break
         lam += step
-        d, info = newton_raphson(asm, d, lam, **nr)
+        d, info = newton_raphson(asm, d, lam, **(dict(nr, step_size=step) if idbc is not None else nr))
+        if idbc is not None and info["iterations"] == 0:
+            d = idbc.sync(d, lam)
         total += info["iterations"]
         per_step.append(info["iterations"])
         ok = info["success"]

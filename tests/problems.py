@@ -55,3 +55,26 @@ def unstructured(mesh, seed, drop=None):
     coords = np.empty((used.shape[0], mesh.dim))
     coords[new_id[used]] = mesh.node_coords[used]
     return o.Mesh(mesh.dim, mesh.order, coords, new_id[en], mesh.corner_coords[keep], mesh.cells)
+
+
+ELASTIC_STRIP_EXPECTED = {
+    # tests/src/testinhomogeneousdbc.cpp:22-33 (load control): (total iterations, u_y at (L/2, 0)); lambda ends at 1
+    ("svk", 1): (6, 1.814746879163122), ("svk", 2): (6, 1.850732157345016),
+    ("neohooke", 1): (7, 2.207111977584091), ("neohooke", 2): (7, 2.1944518710582974),
+}
+
+
+def elastic_strip(mat_kind, order):
+    """tests/src/testelasticstrip.hh:46-118: YaspGrid 10x10 over 10x10, plane strain, u = 0 at x = 0, u_y = 0 and the
+    inhomogeneous value u_x = 10 lambda at x = L.  Materials of testinhomogeneousdbc.cpp:185-190."""
+    L = 10.0
+    mesh = o.structured_mesh((10, 10), (L, L), order=order)
+    lam, mu = o.lame_from_E_nu(100.0, 0.3) if mat_kind == "svk" else (24.0, 6.0)
+    mat = o.Material(mat_kind, lam, mu, plane_strain=True)
+    kind = o.ElementKind(2, order, "gl")
+    flags = o.fix_nodes(mesh, o.boundary_nodes(mesh, 0, 0.0))
+    flags |= o.fix_nodes(mesh, o.boundary_nodes(mesh, 0, L), comps=[1])
+    value = lambda x, lam_: (10.0 * lam_ if abs(x[0] - L) < 1e-12 else 0.0 * lam_, 0.0 * lam_)
+    deriv = lambda x, lam_: (10.0 if abs(x[0] - L) < 1e-12 else 0.0, 0.0)
+    probe = int(np.nonzero(np.all(np.abs(mesh.node_coords - np.array([L / 2, 0.0])) < 1e-9, axis=1))[0][0])
+    return mesh, kind, mat, flags, value, deriv, 2 * probe + 1
