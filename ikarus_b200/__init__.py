@@ -3,7 +3,8 @@
 Host-side mirror of the reference's assembler interface over the C-ABI in include/ikb200.h.
 """
 from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, DeviceMatrix, FERequirements,  # noqa: F401
-                        MatrixAffordance, ScalarAffordance, SparseFlatAssembler, VectorAffordance, elastoStatics,
+                        MatrixAffordance, ResultTypes, ScalarAffordance, SparseFlatAssembler, VectorAffordance,
+                        elastoStatics,
                         makeDenseFlatAssembler, makeSparseFlatAssembler)
 from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, neumannBoundaryLoad,  # noqa: F401
                  nonLinearElastic, planeStrain, skills, toLamesFirstParameterAndShearModulus, volumeLoad)

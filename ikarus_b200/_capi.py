@@ -62,6 +62,7 @@ SYMBOLS = {
     "ikb_update_solution": [C.c_void_p, C.c_int, C.c_void_p],
     "ikb_get_solution": [C.c_void_p, C.c_void_p],
     "ikb_spmv": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "ikb_calculate_at": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
     "ikb_idbc_forces": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
     "ikb_tcg_solve": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TcgInfo)],
     "ikb_set_row_ownership": [C.c_void_p, C.c_int64, C.c_int64],

@@ -29,6 +29,16 @@ class MaterialError(FloatingPointError):
     """The reference aborts on det C <= 0 (materials/materialhelpers.hh:120-126); here it is an exception."""
 
 
+class ResultTypes(enum.IntEnum):
+    """finiteelements/feresulttypes.hh (the stress results of the solid elements)"""
+    linearStress = 0
+    PK2Stress = 1
+    linearStressFull = 2
+    PK2StressFull = 3
+    kirchhoffStress = 4
+    cauchyStress = 5
+
+
 class DBCOption(enum.IntEnum):
     """assembler/dirichletbcenforcement.hh"""
     Raw = capi.DBC_RAW
@@ -240,6 +250,21 @@ class _FlatAssemblerBase:
         full = np.asarray(full, float)
         assert full.shape[0] == self._n, "The full vector you passed has the wrong dimensions."
         return full[~self._dv.container()].copy()
+
+    def calculateAt(self, resultType, req, local):
+        """`fe.calculateAt<RT>(req, local)` of EVERY element at once (mechanics/nonlinearelastic.hh:237-271,
+        linearelastic.hh, enhancedassumedstrains.hh:127-187).  `local`: one position or [npts, dim] positions in the
+        reference element.  Returns [nElem, npts, ncomp] (Voigt), evaluated on the device."""
+        self._push(req)
+        loc = capi.as_f64(np.atleast_2d(local))
+        dim = self._fes.dim
+        if loc.shape[1] != dim:
+            raise ValueError("local positions must have `dim` coordinates")
+        full = resultType in (ResultTypes.linearStressFull, ResultTypes.PK2StressFull)
+        ncomp = 6 if full else dim * (dim + 1) // 2
+        out = np.empty((len(self._fes), loc.shape[0], ncomp))
+        self._check(self._lib.ikb_calculate_at(self._h, int(resultType), capi.ptr(loc), loc.shape[0], capi.ptr(out)))
+        return out
 
     def obtainForcesDueToIDBC(self):
         """utils::obtainForcesDueToIDBC (utils/functionhelper.hh:170-185) for the bound requirement and DBC option:

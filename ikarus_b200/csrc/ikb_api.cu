@@ -13,6 +13,7 @@
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
 #include "ikb_pcg.cuh"
+#include "ikb_results.cuh"
 
 using namespace ikb;
 
@@ -59,7 +60,8 @@ void joinSolution(Handle* h) {
   h->piecesPending = false;
 }
 
-int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
+int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const double* Uoverride = nullptr,
+                   double* alphaOverride = nullptr) {
   ElemArgs A;
   A.X = h->X.p;
   A.elemNode = h->elemNode.p;
@@ -111,7 +113,8 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr) {
     EasArgs EA;
     EA.E = A;
     EA.T0inv = h->T0inv.p;
-    EA.alpha = h->alpha.p;
+    EA.alpha = alphaOverride ? alphaOverride : h->alpha.p;
+    if (Uoverride) EA.E.U = Uoverride;
     EA.dU = dU;
     EA.updateMode = dU ? 1 : 0;
     e = launchEas(h, EA);
@@ -1300,6 +1303,76 @@ int ikb_eas_update(ikb_handle hh, const double* correction) {
   h->stateVersion++;
   return IKB_OK;
 }
+int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPoints, double* out) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!local || !out || nPoints <= 0) return fail(h, IKB_EINVAL, "bad arguments");
+  if (resultType < IKB_RESULT_LINEAR_STRESS || resultType > IKB_RESULT_CAUCHY_STRESS)
+    return fail(h, IKB_EINVAL, "unknown result type");
+  if (!h->meshUploaded) return fail(h, IKB_ESTATE, "mesh missing");
+  const bool linearType = resultType == IKB_RESULT_LINEAR_STRESS || resultType == IKB_RESULT_LINEAR_STRESS_FULL;
+  if (linearType != (h->form == FORM_LE))  // supportsResultType (linearelastic.hh / nonlinearelastic.hh)
+    return fail(h, IKB_ENOTIMPL, "The requested result type is not supported by this element");
+  int rc;
+  if ((rc = ensureSolution(h))) return rc;
+  joinSolution(h);
+  const int S = h->dim * (h->dim + 1) / 2;
+  const bool full = resultType == IKB_RESULT_LINEAR_STRESS_FULL || resultType == IKB_RESULT_PK2_STRESS_FULL;
+  const int ncomp = full ? 6 : S;
+  const int64_t nOut = h->nElem * (int64_t)nPoints * ncomp;
+  if (nOut == 0) return IKB_OK;
+  DevBuf<double> dLocal, dOut, aTmp, uZero;
+  IKB_CUDA(h, dLocal.alloc((size_t)nPoints * h->dim));
+  IKB_CUDA(h, dOut.alloc((size_t)nOut));
+  IKB_CUDA(h, cudaMemcpyAsync(dLocal.p, local, dLocal.bytes(), cudaMemcpyHostToDevice, h->stream));
+  const double* alpha = h->alpha.p;
+  if (h->easM && h->form == FORM_LE) {
+    // linear strains: alpha = -D^-1 L d recomputed from the current d (enhancedassumedstrains.hh:152-157).  The
+    // update kernel evaluates alpha - D^-1 (Rt + L du) at the state it is given; at (d = 0, alpha = 0) Rt vanishes,
+    // so du = d yields exactly -D^-1 L d (D, L do not depend on the state for the linear element).
+    if ((rc = ensureStaging(h))) return rc;
+    IKB_CUDA(h, aTmp.alloc((size_t)h->nElem * h->easM));
+    IKB_CUDA(h, uZero.alloc((size_t)h->nDof));
+    IKB_CUDA(h, cudaMemsetAsync(aTmp.p, 0, aTmp.bytes(), h->stream));
+    IKB_CUDA(h, cudaMemsetAsync(uZero.p, 0, uZero.bytes(), h->stream));
+    if ((rc = launchElements(h, 0, h->U.p, uZero.p, aTmp.p))) return rc;
+    alpha = aTmp.p;
+  }
+  ResultArgs A;
+  A.X = h->X.p;
+  A.elemNode = h->elemNode.p;
+  A.U = h->U.p;
+  A.T0inv = h->T0inv.p;
+  A.alpha = alpha;
+  A.local = dLocal.p;
+  A.out = dOut.p;
+  A.errFlag = h->errFlag.p;
+  A.nElem = h->nElem;
+  A.nNodes = h->nNodes;
+  A.layout = h->layout;
+  A.npts = nPoints;
+  A.form = h->form;
+  A.planeStrain = h->desc.plane_strain;
+  A.easM = h->easM;
+  A.resultType = resultType;
+  A.ncomp = ncomp;
+  A.lambda = h->desc.lambda;
+  A.mu = h->desc.mu;
+  const unsigned grid = gridFor(h->nElem * (int64_t)nPoints, 128);
+  if (h->dim == 3 && h->order == 1)
+    result_at_kernel<3, 1><<<grid, 128, 0, h->stream>>>(A);
+  else if (h->dim == 3)
+    result_at_kernel<3, 2><<<grid, 128, 0, h->stream>>>(A);
+  else if (h->order == 1)
+    result_at_kernel<2, 1><<<grid, 128, 0, h->stream>>>(A);
+  else
+    result_at_kernel<2, 2><<<grid, 128, 0, h->stream>>>(A);
+  IKB_LAUNCH_CHECK(h);
+  markSolutionUse(h);
+  IKB_CUDA(h, cudaMemcpyAsync(out, dOut.p, dOut.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  return checkMaterialError(h);
+}
+
 int ikb_eas_get_alpha(ikb_handle hh, double* alpha) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;

@@ -359,6 +359,26 @@ public:
     return x;
   }
 
+  /** Inner problem of TrustRegion on the device: Steihaug-Toint truncated CG for H eta = rhs under the radius
+   *  info.delta (linearalgebra/truncatedconjugategradient.hh:68-168); the stop reason, iteration count and the
+   *  model terms |eta|, g.eta, eta.H eta come back in `info`. */
+  VectorType truncatedCG(DBCOption dbc, const VectorType& rhs, ikb_tcg_info& info) {
+    VectorType x(rhs.size());
+    check(ikb_tcg_solve(h_, toCode(dbc), rhs.data(), x.data(), &info));
+    return x;
+  }
+  /** utils::obtainForcesDueToIDBC (utils/functionhelper.hh:170-185) with the SpMV on the device:
+   *  K_raw * dInc, zeroed at constrained dofs (Full) or reduced.  dInc = d(d_D)/d(lambda), N entries. */
+  VectorType forcesDueToIDBC(const FERequirement& req, const VectorType& dInc) {
+    if (static_cast<std::size_t>(dInc.size()) != size())
+      IKB_THROW(InvalidState, "The increment of the Dirichlet values must have full size.");
+    push(req);
+    const DBCOption dbc = dBCOption();
+    VectorType f(static_cast<typename VectorType::size_type>(dbc == DBCOption::Full ? size() : reducedSize()));
+    check(ikb_idbc_forces(h_, toCode(dbc), dInc.data(), f.data()));
+    return f;
+  }
+
   // ---- EAS state (mechanics/enhancedassumedstrains.hh:225-248, 350-359) -----------------------------
   /** One call replaces the per-element CORRECTION_UPDATED subscriptions (controlroutinefactory.hh:43-46). */
   void updateInternalVariables(const FERequirement& req, const VectorType& correction) {

@@ -130,6 +130,24 @@ int ikb_eas_update(ikb_handle h, const double* correction);
 int ikb_eas_get_alpha(ikb_handle h, double* alpha /* [n_elem][m] */);
 int ikb_eas_set_alpha(ikb_handle h, const double* alpha);
 
+/* ---- results at local positions ------------------------------------------------- */
+/* fe.calculateAt<RT>(req, local) for EVERY element and n_points local positions (xi in [0,1]^dim):
+ * NonLinearElastic / LinearElastic / EnhancedAssumedStrains::calculateAtImpl
+ * (mechanics/nonlinearelastic.hh:237-271, linearelastic.hh, enhancedassumedstrains.hh:127-187).
+ * out[(e*n_points + q)*ncomp + c] in Voigt order (3D [00,11,22,12,02,01], 2D [00,11,01]);
+ * ncomp = dim(dim+1)/2, or 6 for the *_FULL types (the underlying 3D law of a plane-strain
+ * material).  linearStress* belong to the linear element, the others to the nonlinear one
+ * (IKB_ENOTIMPL otherwise, like the reference's supportsResultType). */
+enum {
+  IKB_RESULT_LINEAR_STRESS = 0,
+  IKB_RESULT_PK2_STRESS = 1,
+  IKB_RESULT_LINEAR_STRESS_FULL = 2,
+  IKB_RESULT_PK2_STRESS_FULL = 3,
+  IKB_RESULT_KIRCHHOFF_STRESS = 4,
+  IKB_RESULT_CAUCHY_STRESS = 5
+};
+int ikb_calculate_at(ikb_handle h, int result_type, const double* local, int n_points, double* out);
+
 /* ---- linear solve --------------------------------------------------------------- */
 /* Jacobi-preconditioned CG on the assembled matrix of mode dbc (Full or Reduced); the
  * analogue of LinearSolver(SolverTypeTag::si_ConjugateGradient)

@@ -405,10 +405,13 @@ def eas_update_alpha(kind, mat, X, u, alpha, du):
     return alpha - np.linalg.solve(q["D"], rhs[..., None])[..., 0]
 
 
-def stress_at(kind, mat, X, u, xi, alpha=None):
-    """PK2/linear stress (Voigt) at local position xi for every element; with EAS and
-    linear strains alpha = -D^-1 L d as in EnhancedAssumedStrains::calculateAtImpl
-    (enhancedassumedstrains.hh:146-176)."""
+def stress_at(kind, mat, X, u, xi, alpha=None, result="native"):
+    """calculateAt (nonlinearelastic.hh:237-271, linearelastic.hh:~200-240, enhancedassumedstrains.hh:127-187): stress in
+    Voigt notation at local position xi for every element.  `result`:
+      "native"    PK2Stress (GL kinematics) / linearStress (linear kinematics), s components
+      "full"      PK2StressFull / linearStressFull: the underlying 3D law of a reduced (plane strain) material, 6 comps
+      "kirchhoff" tau = F S F^T, "cauchy" tau / det F (transformStress, GL kinematics only)
+    With EAS and linear strains alpha = -D^-1 L d as in EnhancedAssumedStrains::calculateAtImpl (:152-157)."""
     d = kind.dim
     _, dN = shape_functions(d, kind.order, xi)
     Jt, Jtinv, detJ = _geometry(kind, X, np.asarray(xi, float))
@@ -427,9 +430,24 @@ def stress_at(kind, mat, X, u, xi, alpha=None):
         T0inv = np.linalg.inv(transformation_matrix(Jt0) * detJ0[:, None, None])
         M = np.einsum("epq,qm->epm", T0inv, eas_Mhat(d, kind.eas_m, xi)) / detJ[:, None, None]
         Ev = Ev + np.einsum("epm,em->ep", M, alpha)
+    if result == "full" and d == 2:
+        E6 = np.zeros(Ev.shape[:-1] + (6,))
+        E6[..., [0, 1, 5]] = Ev
+        psi, S, C = mat._law3d(E6)
+        if kind.strain == "linear":
+            S = np.einsum("epq,eq->ep", C, E6)
+        return S
     psi, S, C = mat.evaluate(Ev)
     if kind.strain == "linear":
         S = np.einsum("epq,eq->ep", C, Ev)
+    if result in ("kirchhoff", "cauchy"):
+        if kind.strain != "gl":
+            raise NotImplementedError("kirchhoffStress / cauchyStress need the nonlinear element")
+        F = H + np.eye(d)
+        tau = np.einsum("eik,ekl,ejl->eij", F, from_voigt(S, strain=False), F)
+        if result == "cauchy":
+            tau = tau / np.linalg.det(F)[:, None, None]
+        return to_voigt(tau, strain=False)
     return S
 
 

@@ -141,6 +141,43 @@ int main(int argc, char** argv) {
   const double E0 = asmb->scalar();
   CHECK(std::isfinite(E0));
 
+  // forces due to inhomogeneous Dirichlet values == K_raw * dInc with constrained entries zeroed (functionhelper.hh:170-185)
+  {
+    std::vector<double> dInc(n, 0.0);
+    for (std::size_t i = 0; i < n; ++i)
+      if (dv.isConstrained(i))
+        dInc[i] = 0.25 + 1e-3 * double(i % 7);
+    const auto F = asmb->forcesDueToIDBC(req, dInc);
+    CHECK(F.size() == n);
+    double maxErr = 0, maxRef = 0;
+    std::vector<double> ref(n, 0.0);
+    for (std::size_t c = 0; c < n; ++c)  // Kraw is symmetric: CSC column c == CSR row c
+      for (std::int64_t p = Kraw.outer[c]; p < Kraw.outer[c + 1]; ++p)
+        ref[c] += Kraw.values[p] * dInc[Kraw.inner[p]];
+    for (std::size_t i = 0; i < n; ++i) {
+      const double r = dv.isConstrained(i) ? 0.0 : ref[i];
+      maxErr         = std::max(maxErr, std::fabs(F[i] - r));
+      maxRef         = std::max(maxRef, std::fabs(r));
+    }
+    CHECK(maxRef > 0 && maxErr <= 1e-12 * maxRef);
+  }
+  // TrustRegion inner solve on the device: a tiny radius ends on the boundary, a huge one on the kappa rule
+  {
+    asmb->vector();
+    asmb->matrix();
+    std::vector<double> minusG(asmb->vector());
+    for (double& v : minusG) v = -v;
+    ikb_tcg_info ti{};
+    ti.kappa = 0.1, ti.theta = 1.0, ti.mininner = 1, ti.precond = IKB_PRECOND_IDENTITY;
+    ti.delta = 1e-6;
+    auto eta = asmb->truncatedCG(DBCOption::Full, minusG, ti);
+    CHECK(ti.stop_reason == IKB_TCG_EXCEEDED_TRUST_REGION && std::fabs(ti.eta_norm - 1e-6) < 1e-15);
+    ti.delta = 1e6;
+    eta      = asmb->truncatedCG(DBCOption::Full, minusG, ti);
+    CHECK(ti.stop_reason == IKB_TCG_REACHED_KAPPA_LINEAR || ti.stop_reason == IKB_TCG_REACHED_THETA_SUPERLINEAR);
+    CHECK(ti.iterations > 1 && ti.rel_error <= 0.1 && ti.g_dot_eta < 0 && ti.eta_h_eta > 0);
+  }
+
   // Newton iteration with the device PCG callable, as NewtonRaphson::solve does (newtonraphson.hh:196-257)
   DevicePCG<A> ls{asmb, 1e-13};
   double rnorm = 0;

@@ -1,0 +1,107 @@
+"""calculateAt (stresses at local positions) on the device against the reference's vertex stress tables
+(tests/src/resultcollection.hh:19-68, 150-163) and against the oracle for every element family."""
+import numpy as np
+import pytest
+
+import ikarus_b200 as ik
+import ikarus_oracle as o
+from devproblems import device_assembler
+from problems import distorted
+
+pytestmark = pytest.mark.gpu
+RT = ik.ResultTypes
+
+
+def _unit(dim):
+    return o.structured_mesh((1,) * dim, (1.0,) * dim)
+
+
+def test_A3_square_vertex_stress_tables():
+    mesh = _unit(2)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material("linear", lam, mu, plane_strain=True)
+    d = np.array([0, 0, 1, 1, 1, 1, 1, 1.0])
+    verts = np.array([(0, 0), (1, 0), (0, 1), (1, 1)], float)
+    exp = np.array([[1923.07692308, 1923.07692308, 769.23076923], [1346.15384615, 576.92307692, 384.61538462],
+                    [576.92307692, 1346.15384615, 384.61538462], [0, 0, 0]])
+    flags = np.zeros(8, dtype=bool)
+    dev = device_assembler(mesh, o.ElementKind(2, 1, "linear"), mat, flags)
+    req = ik.FERequirements(d, 0.0)
+    S = dev.calculateAt(RT.linearStress, req, verts)
+    assert S.shape == (1, 4, 3) and np.allclose(S[0], exp, atol=1e-7)
+    # linearStressFull: the 3D law behind plane strain adds sigma_zz = 1153.84615385 at vertex 0 (:53-68)
+    Sf = dev.calculateAt(RT.linearStressFull, req, verts[:1])
+    assert np.allclose(Sf[0, 0], [1923.07692308, 1923.07692308, 1153.84615385, 0, 0, 769.23076923], atol=1e-7)
+    # with EAS(4): alpha = -D^-1 L d is recomputed from d (resultcollection.hh:39-51)
+    exp4 = np.array([[1510.98901099, 1510.98901099, 384.61538462], [1510.98901099, 412.08791209, 384.61538462],
+                     [412.08791209, 1510.98901099, 384.61538462], [412.08791209, 412.08791209, 384.61538462]])
+    dev4 = device_assembler(mesh, o.ElementKind(2, 1, "linear", 4), mat, flags)
+    S4 = dev4.calculateAt(RT.linearStress, req, verts)
+    assert np.allclose(S4[0], exp4, atol=1e-7)
+    with pytest.raises(Exception):
+        dev.calculateAt(RT.PK2Stress, req, verts)  # not a result of the linear element
+
+
+def test_A4_cube_vertex_stress_table():
+    mesh = _unit(3)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    d = np.zeros(24)
+    d[6:9] = 1.0
+    exp = np.array([
+        [576.92307692, 1346.15384615, 576.92307692, 384.61538462, 0, 384.61538462],
+        [0, 0, 0, 0, 0, 0],
+        [-1346.15384615, 192.30769231, -1346.15384615, 0, -769.23076923, 0],
+        [-1346.15384615, -576.92307692, -576.92307692, 0, -384.61538462, -384.61538462],
+        [0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0],
+        [-576.92307692, -576.92307692, -1346.15384615, -384.61538462, -384.61538462, 0],
+        [0, 0, 0, 0, 0, 0]])
+    verts = np.array([[(v >> k) & 1 for k in range(3)] for v in range(8)], float)
+    dev = device_assembler(mesh, o.ElementKind(3, 1, "linear"), o.Material("linear", lam, mu), np.zeros(24, dtype=bool))
+    S = dev.calculateAt(RT.linearStress, ik.FERequirements(d, 0.0), verts)
+    assert np.allclose(S[0], exp, atol=1e-7)
+
+
+CASES = [
+    # dim, cells, order, strain, material, eas_m
+    (3, (3, 2, 2), 1, "gl", "neohooke", 0),
+    (3, (2, 2, 2), 1, "gl", "svk", 0),
+    (3, (2, 2, 1), 2, "gl", "neohooke", 0),
+    (2, (4, 3), 1, "gl", "neohooke", 0),
+    (2, (3, 2), 2, "gl", "svk", 0),
+    (2, (3, 3), 2, "linear", "linear", 0),
+    (3, (2, 2, 2), 1, "gl", "neohooke", 21),
+    (3, (2, 2, 2), 1, "linear", "linear", 9),
+    (2, (3, 3), 1, "gl", "svk", 7),
+    (2, (3, 3), 1, "linear", "linear", 5),
+]
+
+
+@pytest.mark.parametrize("layout", ["interleaved", "lexicographic"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-Q{c[2]}-{c[3]}-{c[4]}-eas{c[5]}")
+def test_results_match_oracle(case, layout):
+    dim, cells, order, strain, matk, m = case
+    bbox = tuple(float(c) for c in cells)
+    mesh = distorted(o.structured_mesh(cells, bbox, order=order), 0.12, 5)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material(matk, lam, mu, plane_strain=(dim == 2))
+    kind = o.ElementKind(dim, order, strain, m)
+    n = mesh.n_nodes * dim
+    rng = np.random.default_rng(9)
+    d = 0.03 * rng.uniform(-1, 1, n)
+    dev = device_assembler(mesh, kind, mat, np.zeros(n, dtype=bool), layout)
+    req = ik.FERequirements(d, 0.0)
+    alpha = None
+    if m and strain == "gl":
+        alpha = 0.01 * rng.uniform(-1, 1, (mesh.n_elem, m))
+        dev._check(dev._lib.ikb_eas_set_alpha(dev._h, alpha.ctypes.data))
+    pts = np.vstack([np.full(dim, 0.5), rng.uniform(0, 1, (3, dim)), np.zeros(dim), np.ones(dim)])
+    u = d[mesh.elem_dofs(layout)].reshape(mesh.n_elem, -1, dim)
+    types = [(RT.linearStress, "native"), (RT.linearStressFull, "full")] if strain == "linear" else [
+        (RT.PK2Stress, "native"), (RT.PK2StressFull, "full"), (RT.kirchhoffStress, "kirchhoff"), (RT.cauchyStress, "cauchy")]
+    for rt, name in types:
+        S = dev.calculateAt(rt, req, pts)
+        for q, xi in enumerate(pts):
+            ref = o.stress_at(kind, mat, mesh.corner_coords, u, xi, alpha=alpha, result=name)
+            assert S[:, q].shape == ref.shape, (rt, S.shape, ref.shape)
+            assert np.abs(S[:, q] - ref).max() <= 1e-11 * np.abs(ref).max(), (rt, q)
