@@ -305,7 +305,7 @@ def run_ours(args):
             step()
             # TrustRegion inner solve (Steihaug-Toint tCG, diagonal preconditioner) on the same K, g
             from ikarus_b200 import _capi as capi
-            ti = capi.TcgInfo(delta=1e5, kappa=0.1, theta=1.0, mininner=1, max_iters=4, tol=0.0,
+            ti = capi.TcgInfo(delta=1e5, kappa=1e-6, theta=1.0, mininner=1, max_iters=4, tol=0.0,
                               precond=capi.PRECOND_DIAGONAL)
             asm._check(lib.ikb_tcg_solve(h, DBC, None, None, C.byref(ti)))  # untimed warm-up
             ti.max_iters = 0

@@ -244,6 +244,17 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   G.redVecOffset = 0;
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
+  if (!h->gatherTab.p) {
+    std::vector<int16_t> tab;
+    if (h->dim == 3 && h->nn == 8) tab = gatherOffsetTable<3, 8>();
+    if (h->dim == 3 && h->nn == 27) tab = gatherOffsetTable<3, 27>();
+    if (h->dim == 2 && h->nn == 4) tab = gatherOffsetTable<2, 4>();
+    if (h->dim == 2 && h->nn == 9) tab = gatherOffsetTable<2, 9>();
+    IKB_CUDA(h, h->gatherTab.alloc(tab.size()));
+    IKB_CUDA(h, cudaMemcpyAsync(h->gatherTab.p, tab.data(), tab.size() * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+    IKB_CUDA(h, cudaStreamSynchronize(h->stream));  // tab is a local
+  }
+  G.offTab = h->gatherTab.p;
   const int warps = 8;
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
   // one warp per work unit (node-row, or scalar row for Q2)

@@ -7,6 +7,7 @@
 // contributions of its elements in ascending element order (no float atomics), so every run
 // and every GPU count produces bit-identical values.
 #pragma once
+#include <vector>
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
 
@@ -27,6 +28,7 @@ struct GatherArgs {
   int dbc;
   int npair;
   int maxOut;           // doubles of shared memory per warp
+  const int16_t* offTab;  // [N][CHUNK] staged-K_e offsets, see gatherOffsetTable()
   // reduced mode
   const uint16_t* freeCnt;
   const uint16_t* freeTot;
@@ -55,6 +57,26 @@ struct GatherCfg {
   static constexpr bool PERSIST = (N * CHUNK > 2048);
 };
 
+// offTab[la][idx]: offset of value idx = (lb, ii, k) of chunk la inside the symmetric-packed staged K_e for
+// ii = row 0 of the unit, plus bit 14 = "stored directly" (then a further row i0 adds i0*D, else i0)
+template <int D, int N>
+inline std::vector<int16_t> gatherOffsetTable() {
+  using Cfg = GatherCfg<D, N>;
+  constexpr int DD = D * D, RS = Cfg::RS, CHUNK = Cfg::CHUNK, HALF = N / 2;
+  std::vector<int16_t> tab((size_t)(N * CHUNK + 3) / 4 * 4, 0);  // padded to a multiple of 8 bytes
+  for (int t = 0; t < N * CHUNK; ++t) {
+    const int la = t / CHUNK, idx = t - la * CHUNK;
+    const int lb = idx / (RS * D), q = idx - lb * (RS * D);
+    const int i = q / D, k = q - i * D;
+    int k1 = lb - la;
+    if (k1 < 0) k1 += N;
+    const bool direct = (N & 1) ? (k1 <= HALF) : (k1 < HALF || (k1 == HALF && la < HALF));
+    const int off = direct ? (k1 * N + la) * DD + i * D + k : ((N - k1) * N + lb) * DD + k * D + i;
+    tab[t] = (int16_t)(off | (direct ? 0x4000 : 0));
+  }
+  return tab;
+}
+
 template <int D, int N, int DBC, bool INTERLEAVED>
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   using Cfg = GatherCfg<D, N>;
@@ -65,17 +87,11 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   extern __shared__ double gsm[];
   // offTab[la][idx]: offset of value idx = (lb, ii, k) of chunk la inside the symmetric-packed staged K_e for
   // ii = row 0 of the unit, plus bit 14 = "stored directly" (then a further row i0 adds i0*D, else i0)
-  __shared__ int16_t offTab[N * CHUNK];
-  for (int t = threadIdx.x; t < N * CHUNK; t += blockDim.x) {
-    const int la = t / CHUNK, idx = t - la * CHUNK;
-    const int lb = idx / (RS * D), q = idx - lb * (RS * D);
-    const int i = q / D, k = q - i * D;
-    int k1 = lb - la;
-    if (k1 < 0) k1 += N;
-    const bool direct = (N & 1) ? (k1 <= HALF) : (k1 < HALF || (k1 == HALF && la < HALF));
-    const int off = direct ? (k1 * N + la) * DD + i * D + k : ((N - k1) * N + lb) * DD + k * D + i;
-    offTab[t] = (int16_t)(off | (direct ? 0x4000 : 0));
-  }
+  // (the table depends on (D, N) only: it is computed once on the host, gatherOffsetTable(), and copied per CTA)
+  constexpr int TABQ = (N * CHUNK + 3) / 4;  // copied in 8-byte pieces (the device table is padded accordingly)
+  __shared__ __align__(8) int16_t offTab[TABQ * 4];
+  for (int t = threadIdx.x; t < TABQ; t += blockDim.x)
+    reinterpret_cast<int2*>(offTab)[t] = reinterpret_cast<const int2*>(G.offTab)[t];
   __syncthreads();
   const PatternView& P = G.P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -134,6 +134,7 @@ struct Handle {
   uint64_t stagedVersion = 0;
   unsigned stagedWhat = 0;
   double energy = 0.0;
+  DevBuf<int16_t> gatherTab;   // gather offset table of this handle's (dim, nodes per element)
   DevBuf<double> scratch;      // reductions
   int spmvBlocks = 888;        // grid of the SpMV inside PCG: 6 resident blocks x 148 SMs (IKB_SPMV_BLOCKS overrides, for tuning)
   DevBuf<int32_t> errFlag;     // first failing element (material abort), INT_MAX if none
