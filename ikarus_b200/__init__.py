@@ -7,7 +7,7 @@ from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, Dev
                         elastoStatics,
                         makeDenseFlatAssembler, makeSparseFlatAssembler)
 from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, neumannBoundaryLoad,  # noqa: F401
-                 nonLinearElastic, planeStrain, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
+                 nonLinearElastic, planeStrain, planeStress, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
 from .solvers import (ControlInformation, DeviceLinearSolver, DeviceTruncatedCG, LoadControl,  # noqa: F401
                       LoadControlConfig, NewtonRaphson, NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings,
                       PreConditioner, TrustRegion, TRSettings, obtainForcesDueToIDBC)

@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libikb200.so")
 
-IKB_ABI_VERSION = 1
+IKB_ABI_VERSION = 2
 OK, EINVAL, ECUDA, ESTATE, ENOTIMPL, EMATERIAL, ENCCL = 0, -1, -2, -3, -4, -5, -6
 STRAIN_LINEAR, STRAIN_GL = 0, 1
 MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE = 0, 1, 2
@@ -18,7 +18,8 @@ SCALAR, VECTOR, MATRIX = 1, 2, 4
 class Desc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("dim", C.c_int32), ("order", C.c_int32), ("strain", C.c_int32),
                 ("material", C.c_int32), ("plane_strain", C.c_int32), ("eas_m", C.c_int32), ("device", C.c_int32),
-                ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64)]
+                ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64),
+                ("reduce_tol", C.c_double)]
 
 
 class TcgInfo(C.Structure):

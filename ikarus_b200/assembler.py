@@ -145,7 +145,8 @@ class _FlatAssemblerBase:
         self._vec_cb, self._mat_cb, self._scal_cb = [], [], []
         mat = fes.solid.material
         desc = capi.Desc(capi.IKB_ABI_VERSION, fes.dim, fes.order, fes.solid.strain, mat.code, int(mat.reduced),
-                         fes.numberOfInternalVariables(), device, mat.params.lambda_, mat.params.mu, len(fes), self._n)
+                         fes.numberOfInternalVariables(), device, mat.params.lambda_, mat.params.mu, len(fes), self._n,
+                         float(mat.reduce_tol))
         self._h = C.c_void_p()
         rc = self._lib.ikb_create(C.byref(self._h), C.byref(desc))
         if rc == capi.ENOTIMPL:

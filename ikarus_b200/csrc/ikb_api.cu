@@ -79,6 +79,8 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
   A.lambda = h->desc.lambda;
   A.mu = h->desc.mu;
   A.what = what;
+  A.planeStress = h->desc.plane_strain == IKB_REDUCE_PLANE_STRESS;
+  A.psTol = h->desc.reduce_tol > 0.0 ? h->desc.reduce_tol : 1e-12;
   cudaError_t e = cudaErrorInvalidValue;
   if (h->order == 1 && h->easM == 0) {
     // a pipelined solution upload is consumed chunk by chunk: chunk c waits for piece c of d only
@@ -519,7 +521,8 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     form = FORM_NH;
   else
     return IKB_EINVAL;  // the reference statically rejects these strain/material pairings too
-  if (desc->dim == 2 && !desc->plane_strain) return IKB_EINVAL;  // 2D needs a reduced material
+  if (desc->dim == 2 && desc->plane_strain != IKB_REDUCE_PLANE_STRAIN && desc->plane_strain != IKB_REDUCE_PLANE_STRESS)
+    return IKB_EINVAL;  // 2D needs a reduced material
   if (desc->dim == 3 && desc->plane_strain) return IKB_EINVAL;
   const int m = desc->eas_m;
   const bool easOk = m == 0 || (desc->order == 1 && ((desc->dim == 2 && (m == 4 || m == 5 || m == 7)) ||
@@ -1369,6 +1372,7 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
   A.ncomp = ncomp;
   A.lambda = h->desc.lambda;
   A.mu = h->desc.mu;
+  A.psTol = h->desc.reduce_tol > 0.0 ? h->desc.reduce_tol : 1e-12;
   const unsigned grid = gridFor(h->nElem * (int64_t)nPoints, 128);
   if (h->dim == 3 && h->order == 1)
     result_at_kernel<3, 1><<<grid, 128, 0, h->stream>>>(A);

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       Em[i][j] = Em[j][i] = (i == j) ? Ev[q] : 0.5 * Ev[q];
     }
     double mup = mu;
+    double lamR = lam;  // lambda of the (condensed, for planeStress) tangent
     if constexpr (FORM == FORM_NH) {
       double Cm[D][D];
 #pragma unroll
@@ -263,8 +264,17 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
         for (int j = 0; j < D; ++j) Cm[i][j] = 2.0 * Em[i][j] + (i == j ? 1.0 : 0.0);
       const double detC = invSmall<D>(Cm, X);
       if (!(detC > 0.0)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
-      const double lnJ = 0.5 * log(detC);
+      double lnJ = 0.5 * log(detC);
+      bool planeStress = false;
+      if constexpr (D == 2) {
+        if (A.planeStress) {  // see elem_q1_kernel
+          planeStress = true;
+          double c33;
+          if (!reduceC33(lam, mu, A.psTol, detC, c33, lnJ)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+        }
+      }
       mup = mu - lam * lnJ;
+      if (planeStress) lamR = condensedLambda(lam, mup);
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -273,6 +283,14 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) tr += Em[i][i];
+      if constexpr (D == 2) {
+        if (A.planeStress) {
+          double e33;
+          if (!reduceE33(lam, mu, A.psTol, tr, e33)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+          tr += e33;
+          lamR = condensedLambda(lam, mu);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
           X[i][j] = (i == j) ? 1.0 : 0.0;
         }
     }
-    gp[C::O_C1] = lam * w;
+    gp[C::O_C1] = lamR * w;
     gp[C::O_C2] = mup * w;
     gp[C::O_IDET] = invDet;
     // Am = F X ; A2 = c2 Am F^T ; m_a = Am g_a
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       for (int q = p; q < S; ++q) {
         int k, l;
         voigtPair<D>(q, k, l);
-        const double v = w * (lam * X[i][j] * X[k][l] + mup * (X[i][k] * X[j][l] + X[i][l] * X[j][k]));
+        const double v = w * (lamR * X[i][j] * X[k][l] + mup * (X[i][k] * X[j][l] + X[i][l] * X[j][k]));
         CC[p][q] = v;
         CC[q][p] = v;
       }

@@ -44,7 +44,45 @@ struct ElemArgs {
   int layout;
   double lambda, mu;
   unsigned what;
+  int planeStress;  // 2D: Materials::planeStress instead of planeStrain
+  double psTol;     // tolerance of the stress reduction
 };
+
+// VanishingStress::reduceStress for planeStress (materials/vanishingstress.hh:150-199): Newton-Raphson with tolerance
+// tol on |S33|, at most 100 iterations, correction = -(A^-1 r), on the out-of-plane normal strain only (the fixed
+// shear strains stay zero).  Linear / St.Venant-Kirchhoff law: unknown E33 started from 0 (derivative lambda + 2 mu).
+__device__ __forceinline__ bool reduceE33(double lam, double mu, double tol, double tr2, double& e33) {
+  e33 = 0.0;
+  double f;
+  for (int it = 0;; ++it) {
+    f = lam * (tr2 + e33) + 2.0 * mu * e33;
+    if (!(fabs(f) > tol && it < 100)) break;
+    e33 += -((1.0 / (lam + 2.0 * mu)) * f);
+  }
+  return !(fabs(f) > tol);
+}
+// NeoHooke works on the right Cauchy-Green tensor: unknown C33 started from 1 (initUnknownStrains :137-148), residual
+// S33 = mu (1 - 1/C33) + lambda ln J / C33, derivative = moduli_3333 / 2 with moduli_3333 = (lambda + 2 mu') / C33^2.
+// det2 = det of the in-plane C.  Also returns ln J of the solution.
+__device__ __forceinline__ bool reduceC33(double lam, double mu, double tol, double det2, double& c33, double& lnJ) {
+  c33 = 1.0;
+  lnJ = 0.0;
+  double f;
+  for (int it = 0;; ++it) {
+    const double detC = det2 * c33;
+    if (!(detC > 1e-10)) return false;
+    lnJ = log(sqrt(detC));
+    f = mu * (1.0 - 1.0 / c33) + lam * lnJ / c33;
+    if (!(fabs(f) > tol && it < 100)) break;
+    const double df = (lam + 2.0 * (mu - lam * lnJ)) / (c33 * c33) / 2.0;
+    c33 += -((1.0 / df) * f);
+  }
+  return !(fabs(f) > tol);
+}
+// lambda of the condensed in-plane tangent: staticCondensation over the fixed Voigt indices {2,3,4}
+// (utils/linearalgebrahelper.hh:521-535) leaves C_red = lambda_red X(x)X + 2 mu' I_X with
+// lambda_red = lambda - lambda^2 / (lambda + 2 mu')   (mu' = mu for the linear laws).
+__device__ __forceinline__ double condensedLambda(double lam, double mup) { return lam - lam * lam / (lam + 2.0 * mup); }
 
 template <int D>
 __device__ __forceinline__ double invSmall(const double (&A)[D][D], double (&Ai)[D][D]) {
@@ -211,6 +249,16 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) tr += H[i][i];
+      double lamR = lam;
+      if constexpr (D == 2) {
+        if (A.planeStress) {  // sigma_33 = 0: eps_33 joins the trace, condensed lambda (psi = sigma:eps/2 is unchanged)
+          double e33;
+          if (!reduceE33(lam, mu, A.psTol, tr, e33))
+            atomicMin(A.errFlag, (int32_t)(e + A.elemBegin < 0x7fffffff ? e + A.elemBegin : 0x7ffffffe));
+          tr += e33;
+          lamR = condensedLambda(lam, mu);
+        }
+      }
       double psi = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -221,7 +269,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
           sc[C::O_WP + i * D + j] = w * sig;
           psi = fma(eps, sig, psi);
         }
-      sc[C::O_C1] = lam * w;
+      sc[C::O_C1] = lamR * w;
       sc[C::O_C2] = mu * w;
       sc[C::O_PSI] = 0.5 * psi * w;
     } else {
@@ -246,7 +294,17 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
         double tr = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) tr += 0.5 * (Cm[i][i] - 1.0);
-        double ee = 0.0;
+        double ee = 0.0, lamR = lam;
+        if constexpr (D == 2) {
+          if (A.planeStress) {
+            double e33;
+            if (!reduceE33(lam, mu, A.psTol, tr, e33))
+              atomicMin(A.errFlag, (int32_t)(e + A.elemBegin < 0x7fffffff ? e + A.elemBegin : 0x7ffffffe));
+            tr += e33;
+            ee = e33 * e33;
+            lamR = condensedLambda(lam, mu);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -257,7 +315,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
             Am[i][j] = F[i][j];
           }
         psi = 0.5 * lam * tr * tr + mu * ee;
-        sc[C::O_C1] = lam * w;
+        sc[C::O_C1] = lamR * w;
         sc[C::O_C2] = mu * w;
         // A2 = mu w F F^T (sym), wS = w S (sym)
 #pragma unroll
@@ -274,9 +332,18 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
         double Ci[D][D];
         const double detC = invSmall<D>(Cm, Ci);
         if (!(detC > 0.0)) atomicMin(A.errFlag, (int32_t)(e + A.elemBegin < 0x7fffffff ? e + A.elemBegin : 0x7ffffffe));
-        const double lnJ = 0.5 * log(detC);
+        double lnJ = 0.5 * log(detC);
+        double c33 = 1.0;  // plane strain: C_33 = 1
+        bool planeStress = false;
+        if constexpr (D == 2) {
+          if (A.planeStress) {
+            planeStress = true;
+            if (!reduceC33(lam, mu, A.psTol, detC, c33, lnJ))
+              atomicMin(A.errFlag, (int32_t)(e + A.elemBegin < 0x7fffffff ? e + A.elemBegin : 0x7ffffffe));
+          }
+        }
         const double mup = mu - lam * lnJ;
-        double trC = (D == 2) ? 1.0 : 0.0;  // plane strain: C_33 = 1
+        double trC = (D == 2) ? c33 : 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) trC += Cm[i][i];
         psi = 0.5 * mu * (trC - 3.0 - 2.0 * lnJ) + 0.5 * lam * lnJ * lnJ;
@@ -290,7 +357,7 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
             for (int k = 0; k < D; ++k) s = fma(F[i][k], Ci[k][j], s);
             Am[i][j] = s;  // F C^-1 = F^-T
           }
-        sc[C::O_C1] = lam * w;
+        sc[C::O_C1] = (planeStress ? condensedLambda(lam, mup) : lam) * w;
         sc[C::O_C2] = mup * w;
         sc[C::O_C3] = mu * w;
       }

@@ -146,6 +146,15 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) tr += H[i][i];
+      double lamR = lam;
+      if constexpr (D == 2) {
+        if (A.planeStress) {  // see elem_q1_kernel
+          double e33;
+          if (!reduceE33(lam, mu, A.psTol, tr, e33)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+          tr += e33;
+          lamR = condensedLambda(lam, mu);
+        }
+      }
       double psi = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
           sc[C::O_WP + i * D + j] = w * sig;
           psi = fma(eps, sig, psi);
         }
-      sc[C::O_C1] = lam * w;
+      sc[C::O_C1] = lamR * w;
       sc[C::O_C2] = mu * w;
       sc[C::O_PSI] = 0.5 * psi * w;
     } else {
@@ -179,7 +188,16 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
         double tr = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) tr += 0.5 * (Cm[i][i] - 1.0);
-        double ee = 0.0;
+        double ee = 0.0, lamR = lam;
+        if constexpr (D == 2) {
+          if (A.planeStress) {
+            double e33;
+            if (!reduceE33(lam, mu, A.psTol, tr, e33)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+            tr += e33;
+            ee = e33 * e33;
+            lamR = condensedLambda(lam, mu);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
             Am[i][j] = F[i][j];
           }
         psi = 0.5 * lam * tr * tr + mu * ee;
-        sc[C::O_C1] = lam * w;
+        sc[C::O_C1] = lamR * w;
         sc[C::O_C2] = mu * w;
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -206,9 +224,17 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
         double Ci[D][D];
         const double detC = invSmall<D>(Cm, Ci);
         if (!(detC > 0.0)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
-        const double lnJ = 0.5 * log(detC);
+        double lnJ = 0.5 * log(detC);
+        double c33 = 1.0;
+        bool planeStress = false;
+        if constexpr (D == 2) {
+          if (A.planeStress) {
+            planeStress = true;
+            if (!reduceC33(lam, mu, A.psTol, detC, c33, lnJ)) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+          }
+        }
         const double mup = mu - lam * lnJ;
-        double trC = (D == 2) ? 1.0 : 0.0;
+        double trC = (D == 2) ? c33 : 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) trC += Cm[i][i];
         psi = 0.5 * mu * (trC - 3.0 - 2.0 * lnJ) + 0.5 * lam * lnJ * lnJ;
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
             for (int k = 0; k < D; ++k) s = fma(F[i][k], Ci[k][j], s);
             Am[i][j] = s;
           }
-        sc[C::O_C1] = lam * w;
+        sc[C::O_C1] = (planeStress ? condensedLambda(lam, mup) : lam) * w;
         sc[C::O_C2] = mup * w;
         sc[C::O_C3] = mu * w;
       }

@@ -23,7 +23,7 @@ struct ResultArgs {
   int32_t* errFlag;
   int64_t nElem, nNodes;
   int layout, npts, form, planeStrain, easM, resultType, ncomp;
-  double lambda, mu;
+  double lambda, mu, psTol;
 };
 
 template <int D>
@@ -173,7 +173,23 @@ __global__ void __launch_bounds__(128) result_at_kernel(ResultArgs A) {
   } else {
     E6[0] = Ev[0], E6[1] = Ev[1], E6[5] = Ev[2];
   }
-  if (!stress3d(A.form, A.lambda, A.mu, E6, S6)) {
+  bool ok = true;
+  if constexpr (D == 2) {
+    const bool fullType = A.resultType == IKB_RESULT_LINEAR_STRESS_FULL || A.resultType == IKB_RESULT_PK2_STRESS_FULL;
+    if (A.planeStrain == IKB_REDUCE_PLANE_STRESS && !fullType) {
+      // planeStress: the out-of-plane normal strain of the reduced solution (vanishingstress.hh:150-199); the *Full
+      // types evaluate the 3D law at the zero-extended strain, exactly like enlargeIfReduced in calculateStress
+      if (A.form == FORM_NH) {
+        const double det2 = (2.0 * E6[0] + 1.0) * (2.0 * E6[1] + 1.0) - E6[5] * E6[5];
+        double c33, lnJ;
+        ok = reduceC33(A.lambda, A.mu, A.psTol, det2, c33, lnJ);
+        E6[2] = 0.5 * (c33 - 1.0);
+      } else {
+        ok = reduceE33(A.lambda, A.mu, A.psTol, E6[0] + E6[1], E6[2]);
+      }
+    }
+  }
+  if (!(ok && stress3d(A.form, A.lambda, A.mu, E6, S6))) {
     atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
     for (int p = 0; p < 6; ++p) S6[p] = 0.0;
   }

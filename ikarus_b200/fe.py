@@ -33,7 +33,8 @@ class _Material:
     code: int
     strain: int
     params: LamesFirstParameterAndShearModulus
-    reduced: bool = False  # planeStrain wrapper
+    reduced: int = 0  # 0: 3D law, 1: planeStrain wrapper, 2: planeStress wrapper (capi IKB_REDUCE_*)
+    reduce_tol: float = 1e-12
 
     def materialParameters(self):
         return self.params
@@ -58,7 +59,13 @@ class Materials:
 
 def planeStrain(mat: _Material) -> _Material:
     """Materials::planeStrain (mechanics/materials/vanishingstrain.hh:147-198)."""
-    return _Material(mat.name, mat.code, mat.strain, mat.params, True)
+    return _Material(mat.name, mat.code, mat.strain, mat.params, 1)
+
+
+def planeStress(mat: _Material, tol: float = 1e-12) -> _Material:
+    """Materials::planeStress(mat, tol) = VanishingStress with S33 = S23 = S13 = 0
+    (mechanics/materials/vanishingstress.hh:35-230, 252-260)."""
+    return _Material(mat.name, mat.code, mat.strain, mat.params, 2, float(tol))
 
 
 # ------------------------------------------------------------------------------------- skills
@@ -260,7 +267,7 @@ def makeFE(basis, sk, corner_coords=None, elem_dofs=None):
     loads = tuple(s for s in sk if isinstance(s, (_VolumeLoad, _NeumannLoad)))
     mat = solid[0].material
     if dim == 2 and not mat.reduced:
-        raise TypeError("2D elements need a reduced material (planeStrain)")
+        raise TypeError("2D elements need a reduced material (planeStrain or planeStress)")
     if dim == 3 and mat.reduced:
         raise TypeError("3D elements need a full 3D material")
     return FEContainer(dim, order, n_dof, np.ascontiguousarray(corner_coords, float),

@@ -71,6 +71,9 @@ struct ElementAccess
   static int strain(const FE& fe) { return fe.strain; }      // IKB_STRAIN_*
   static int material(const FE& fe) { return fe.material; }  // IKB_MAT_*
   static bool planeStrain(const FE& fe) { return fe.planeStrain; }
+  /** IKB_REDUCE_*: planeStrain / planeStress wrapper of the material; tolerance of the planeStress reduction */
+  static int reduction(const FE& fe) { return fe.planeStress ? IKB_REDUCE_PLANE_STRESS : (fe.planeStrain ? IKB_REDUCE_PLANE_STRAIN : IKB_REDUCE_NONE); }
+  static double reductionTolerance(const FE& fe) { return fe.reduceTol; }
   static double lambda(const FE& fe) { return fe.lambda; }
   static double mu(const FE& fe) { return fe.mu; }
   static int numberOfInternalVariables(const FE& fe) { return fe.easM; }
@@ -101,6 +104,16 @@ struct ElementAccess<FE>
     IKB_THROW(NotImplemented, "material " + n + " is outside the device hot path");
   }
   static bool planeStrain(const FE&) { return FE::Material::isReduced; }
+  /** VanishingStrain / VanishingStress are told apart by the material name (vanishingstrain.hh, vanishingstress.hh:63-70) */
+  static int reduction(const FE& fe) {
+    if constexpr (!FE::Material::isReduced)
+      return IKB_REDUCE_NONE;
+    else
+      return fe.material().name().find("VanishingStress") != std::string::npos ? IKB_REDUCE_PLANE_STRESS
+                                                                               : IKB_REDUCE_PLANE_STRAIN;
+  }
+  /** the tolerance is private to VanishingStress: specialise ElementAccess to pass a non-default one */
+  static double reductionTolerance(const FE&) { return 1e-12; }
   static double lambda(const FE& fe) { return fe.material().materialParameters().lambda; }
   static double mu(const FE& fe) { return fe.material().materialParameters().mu; }
   static int numberOfInternalVariables(const FE& fe) {
@@ -180,7 +193,8 @@ public:
         desc.order        = A::order(fe);
         desc.strain       = A::strain(fe);
         desc.material     = A::material(fe);
-        desc.plane_strain = A::planeStrain(fe) ? 1 : 0;
+        desc.plane_strain = A::reduction(fe);
+        desc.reduce_tol   = A::reductionTolerance(fe);
         desc.eas_m        = A::numberOfInternalVariables(fe);
         desc.lambda       = A::lambda(fe);
         desc.mu           = A::mu(fe);

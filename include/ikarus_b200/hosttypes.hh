@@ -129,7 +129,8 @@ struct HostSparseMatrix
 struct HostFE
 {
   int dim{3}, order{1}, strain{1}, material{2}, easM{0};
-  bool planeStrain{false};
+  bool planeStrain{false}, planeStress{false};
+  double reduceTol{1e-12};
   double lambda{0.0}, mu{0.0};
   std::vector<std::int64_t> dofs;
   std::vector<double> corners;

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IKB_ABI_VERSION 1
+#define IKB_ABI_VERSION 2
 
 typedef struct ikb_handle_s* ikb_handle;
 
@@ -51,19 +51,23 @@ enum { IKB_DBC_RAW = 0, IKB_DBC_REDUCED = 1, IKB_DBC_FULL = 2 };
  * MatrixAffordance::stiffness (finiteelements/ferequirements.hh:35-89) */
 enum { IKB_SCALAR = 1, IKB_VECTOR = 2, IKB_MATRIX = 4 };
 
+enum { IKB_REDUCE_NONE = 0, IKB_REDUCE_PLANE_STRAIN = 1, IKB_REDUCE_PLANE_STRESS = 2 };
+
 typedef struct ikb_desc {
   int32_t abi_version;  /* IKB_ABI_VERSION */
   int32_t dim;          /* 2 | 3 */
   int32_t order;        /* Lagrange order of the power basis: 1 (Quad4/Hex8) | 2 (Quad9/Hex27) */
   int32_t strain;       /* IKB_STRAIN_* */
   int32_t material;     /* IKB_MAT_* */
-  int32_t plane_strain; /* 2D only: Materials::planeStrain(mat) (materials/vanishingstrain.hh) */
+  int32_t plane_strain; /* 2D only, IKB_REDUCE_*: Materials::planeStrain(mat) (materials/vanishingstrain.hh) or
+                           Materials::planeStress(mat, tol) (materials/vanishingstress.hh) */
   int32_t eas_m;        /* eas<...>(m): 0 | 4,5,7 (2D Q1) | 9,21 (3D Q1)  (easvariants/linearandglstrains.hh) */
   int32_t device;       /* CUDA ordinal, -1 = current device */
   double lambda;        /* Lame's first parameter (physicshelper.hh:53-57) */
   double mu;            /* shear modulus */
   int64_t n_elem;       /* elements owned by this handle */
   int64_t n_dof;        /* global dofs = basis.flat().size() */
+  double reduce_tol;    /* planeStress: tolerance of the stress reduction (VanishingStress ctor, default 1e-12) */
 } ikb_desc;
 
 /* ---- lifetime ------------------------------------------------------------------- */

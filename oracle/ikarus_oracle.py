@@ -146,6 +146,9 @@ class Material:
     lam: float
     mu: float
     plane_strain: bool = False
+    # planeStress(mat, tol) = VanishingStress<{2,2},{1,2},{0,2}> (materials/vanishingstress.hh:35-230, 252-260)
+    plane_stress: bool = False
+    ps_tol: float = 1e-12
 
     # --- 3D law on Voigt GL strain (batched: E6[..., 6]) --------------------------------
     def _law3d(self, E6):
@@ -180,13 +183,63 @@ class Material:
             return psi, to_voigt(Sm, strain=False), tensor4_to_voigt(T)
         raise NotImplementedError(self.kind)
 
+    def _reduce_stress(self, Ev):
+        """VanishingStress::reduceStress (vanishingstress.hh:150-199): Newton-Raphson (tol, at most 100 iterations,
+        correction = -(A^-1 r)) on the DIAGONAL fixed strain component only -- E33, or C33 started from 1 for
+        materials whose native measure is the right Cauchy-Green tensor (NeoHooke; derivative = moduli / 2) -- while
+        the fixed shear strains stay zero.  Returns the full 6-Voigt GL strain of the solution."""
+        lam, mu, tol = self.lam, self.mu, self.ps_tol
+        E6 = np.zeros(Ev.shape[:-1] + (6,))
+        E6[..., [0, 1, 5]] = Ev
+        flat = E6.reshape(-1, 6)
+        for row in flat:  # scalar Newton per point, exactly the reference's control flow
+            if self.kind == "neohooke":
+                C2 = np.array([[2 * row[0] + 1, row[5]], [row[5], 2 * row[1] + 1]])
+                det2 = C2[0, 0] * C2[1, 1] - C2[0, 1] * C2[1, 0]
+                c33 = 1.0
+                for it in range(101):
+                    detC = det2 * c33
+                    if detC <= 1e-10:
+                        raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
+                    lnJ = np.log(np.sqrt(detC))
+                    f = mu * (1.0 - 1.0 / c33) + lam * lnJ / c33
+                    if not (abs(f) > tol and it < 100):
+                        break
+                    df = (lam + 2.0 * (mu - lam * lnJ)) / (c33 * c33) / 2.0
+                    c33 += -((1.0 / df) * f)
+                if abs(f) > tol:
+                    raise FloatingPointError("The stress reduction of the material was unsuccessful")
+                row[2] = 0.5 * (c33 - 1.0)
+            else:
+                e33 = 0.0
+                tr2 = row[0] + row[1]
+                for it in range(101):
+                    f = lam * (tr2 + e33) + 2.0 * mu * e33
+                    if not (abs(f) > tol and it < 100):
+                        break
+                    e33 += -((1.0 / (lam + 2.0 * mu)) * f)
+                if abs(f) > tol:
+                    raise FloatingPointError("The stress reduction of the material was unsuccessful")
+                row[2] = e33
+        return flat.reshape(E6.shape)
+
     def evaluate(self, Ev):
         """Return (psi, S_voigt, C_voigt) for Voigt strain Ev[..., s], s = 3 (2D) or 6."""
         if Ev.shape[-1] == 6:
-            assert not self.plane_strain
+            assert not self.plane_strain and not self.plane_stress
             return self._law3d(Ev)
-        assert self.plane_strain, "2D elements need a reduced material (planeStrain)"
-        free = [0, 1, 5]  # vanishingstrain.hh: fixed Voigt indices {2,3,4}
+        free = [0, 1, 5]  # vanishingstrain.hh / vanishingstress.hh: fixed Voigt indices {2,3,4}
+        if self.plane_stress:
+            fixed = [2, 3, 4]
+            E6 = self._reduce_stress(Ev)
+            psi, S6, C6 = self._law3d(E6)
+            # staticCondensation(C, fixedVoigtIndices) (utils/linearalgebrahelper.hh): K11 - K12 K22^-1 K21
+            Cff = C6[..., free, :][..., :, free]
+            Cfx = C6[..., free, :][..., :, fixed]
+            Cxx = C6[..., fixed, :][..., :, fixed]
+            Cred = Cff - Cfx @ np.linalg.solve(Cxx, np.swapaxes(Cfx, -1, -2))
+            return psi, S6[..., free], Cred
+        assert self.plane_strain, "2D elements need a reduced material (planeStrain or planeStress)"
         E6 = np.zeros(Ev.shape[:-1] + (6,))
         E6[..., free] = Ev
         psi, S6, C6 = self._law3d(E6)
@@ -713,6 +766,24 @@ class FlatAssembler:
 # NewtonRaphson + LoadControl (solver/nonlinearsolver/newtonraphson.hh:196-257,
 # controlroutines/loadcontrol.inl:21-57)
 # --------------------------------------------------------------------------------------
+
+
+def volume_load_vector(mesh: Mesh, kind: ElementKind, f, layout="interleaved"):
+    """VolumeLoad::calculateVectorImpl at lambda = 1 summed over the elements (mechanics/loads/volume.hh:86-106):
+    fext_a = sum_gp N_a f(x_gp) detJ w with the element's own Gauss rule; the assembler then uses R -= lambda fext."""
+    pts, wts = tensor_rule(kind.dim, kind.order + 1)
+    X = mesh.corner_coords
+    fext = np.zeros(mesh.n_nodes * kind.dim)
+    dofs = mesh.elem_dofs(layout)
+    for xi, w in zip(pts, wts):
+        N, _ = shape_functions(kind.dim, kind.order, xi)
+        Ng, _ = shape_functions(kind.dim, 1, xi)
+        _, _, detJ = _geometry(kind, X, xi)
+        xg = np.einsum("c,ecj->ej", Ng, X)
+        fv = np.array([np.asarray(f(x), float) for x in xg])
+        contrib = (N[None, :, None] * fv[:, None, :] * (detJ * w)[:, None, None]).reshape(mesh.n_elem, -1)
+        np.add.at(fext, dofs.ravel(), contrib.ravel())
+    return fext
 
 
 class InhomogeneousDirichlet:

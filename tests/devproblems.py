@@ -12,6 +12,8 @@ def device_assembler(mesh, kind, mat, flags, layout="interleaved", fext=None, de
     m = _MAT[mat.kind](p)
     if mat.plane_strain:
         m = ik.planeStrain(m)
+    if getattr(mat, "plane_stress", False):
+        m = ik.planeStress(m, mat.ps_tol)
     solid = ik.linearElastic(m) if kind.strain == "linear" else ik.nonLinearElastic(m)
     sk = [solid]
     if kind.eas_m:

@@ -78,3 +78,25 @@ def elastic_strip(mat_kind, order):
     deriv = lambda x, lam_: (10.0 if abs(x[0] - L) < 1e-12 else 0.0, 0.0)
     probe = int(np.nonzero(np.all(np.abs(mesh.node_coords - np.array([L / 2, 0.0])) < 1e-9, axis=1))[0][0])
     return mesh, kind, mat, flags, value, deriv, 2 * probe + 1
+
+
+def patch_test_mesh():
+    """The five-quad patch of tests/src/testinhomogeneousdbc.cpp:58-73 (Macneal & Harder): vertices and elements in
+    insertion order, DUNE local vertex order (x fastest)."""
+    X = np.array([[0.0, 0.0], [0.24, 0.0], [0.0, 0.12], [0.24, 0.12], [0.04, 0.02], [0.18, 0.03], [0.08, 0.08],
+                  [0.16, 0.08]])
+    en = np.array([[0, 1, 4, 5], [5, 1, 7, 3], [6, 7, 2, 3], [0, 4, 2, 6], [4, 5, 6, 7]])
+    return o.Mesh(2, 1, X, en, X[en], ())
+
+
+PATCH_EXPECTED_D = np.array([0.0, 0.0, 0.001, 0.0, 0.0, -0.000125, 0.001, -0.000125, 0.0001666666666666667,
+                             -0.0000208333333333333, 0.000750, -0.00003125, 0.0003333333333333333,
+                             -0.0000833333333333333, 0.000666666666666667, -0.0000833333333333333])
+
+
+def fixed_distorted_quad():
+    """createUGGridFromCorners<2>(CornerDistortionFlag::fixedDistorted), tests/src/testcommon.hh:179-215."""
+    X = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]) + np.array([[-0.2, -0.05], [-0.15, 0.05], [0.15, 0.15],
+                                                                              [-0.05, -0.1]])
+    en = np.array([[0, 1, 2, 3]])
+    return o.Mesh(2, 1, X, en, X[en], ())
