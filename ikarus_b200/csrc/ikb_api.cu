@@ -263,6 +263,8 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   const int64_t wantBlocks = gridFor(nRowNodes * (h->dim / rs), warps);
   cudaError_t e = cudaSuccess;
   const unsigned vecGrid = gridFor(nRowNodes * h->dim, 256);
+  // pull gather: signed 32-bit staged offsets (in 4-byte units) when the whole staged K_e buffer is addressable that way
+  const bool idx32 = (double)h->nElem * h->npair * h->dim * h->dim * 2.0 < 2147483000.0;
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \
     if (G.vec) {                                                                                                     \
@@ -276,7 +278,18 @@ int launchGather(Handle* h, unsigned what, int dbc) {
       h->launches++;                                                                                                 \
       cudaEventRecord(h->evVec, vs);                                                                                 \
     }                                                                                                                \
-    if (G.vals) {                                                                                                    \
+    if (G.vals && h->gatherPull && h->csrc.p) {                                                                      \
+      if (idx32 && h->pullGroups == 3)                                                                               \
+        gather_pull_kernel<DIM, MODE, IL, true, 3><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(        \
+            G, h->cptr.p, h->csrc.p);                                                                                \
+      else if (idx32)                                                                                                \
+        gather_pull_kernel<DIM, MODE, IL, true, 1><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(        \
+            G, h->cptr.p, h->csrc.p);                                                                                \
+      else                                                                                                           \
+        gather_pull_kernel<DIM, MODE, IL, false, 1><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(       \
+            G, h->cptr.p, h->csrc.p);                                                                                \
+      if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
+    } else if (G.vals) {                                                                                             \
       e = cudaFuncSetAttribute(gather_kernel<DIM, NN, MODE, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                (int)smem);                                                                           \
       int occ = 1;                                                                                                   \
@@ -553,6 +566,8 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     delete h;
     return IKB_EINVAL;
   }
+  if (const char* gm = std::getenv("IKB_GATHER")) h->gatherPull = std::string(gm) != "tile";
+  if (const char* gp = std::getenv("IKB_PULL_GROUPS")) h->pullGroups = std::atoi(gp) == 3 ? 3 : 1;
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one
@@ -947,9 +962,11 @@ int ikb_build_pattern(ikb_handle hh) {
     adjCount.release();
     rowLen.release();
     maxLen.release();
-    // the per-block contribution lists were only needed to derive the adjacency
-    h->csrc.release();
-    h->cptr.release();
+    // the tile gather only needs the adjacency derived from the per-block contribution lists; the pull gather reads them
+    if (!h->gatherPull) {
+      h->csrc.release();
+      h->cptr.release();
+    }
   }
   tmp.release();
   h->patternBuilt = true;

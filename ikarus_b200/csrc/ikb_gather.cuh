@@ -209,6 +209,187 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   } while (PERSIST && unit < nUnits);
 }
 
+// Contribution-list gather ("pull"): one warp per node-row, one lane per matrix entry of a group of 32/(D*D) pattern
+// blocks.  The stable sort of the pattern build leaves, for every pattern block, the list of staged K_e blocks that
+// add into it in ascending element order (cptr/csrc: code = e*npair + p, bit 31 = read transposed) -- the order of
+// the reference's serial element loop (ikarus/assembler/simpleassemblers.inl:126-136).  The D*D lanes of a block read
+// one 8*D*D-byte staged block per contribution and add it in a register; no shared-memory read-modify-write, no
+// atomics, values bit-identical to gather_kernel.  The codes of a chunk of blocks are staged in shared memory with
+// coalesced loads so that the dependent chain per node-row is cptr -> codes -> values (three global latencies), and
+// two block groups with up to four contributions each are in flight per lane.
+constexpr int PULL_CAP = 256;  // staged codes per warp
+
+__device__ __forceinline__ double pullLoad(uint64_t a) {
+  double v;
+  asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
+  return v;
+}
+__device__ __forceinline__ void pullStore(uint64_t a, double v) {
+  asm volatile("st.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
+}
+
+template <int D, int DBC, bool INTERLEAVED, bool IDX32, int GP>
+__global__ void __launch_bounds__(256) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
+                                                          const uint32_t* __restrict__ csrc) {
+  constexpr int DD = D * D;
+  constexpr int BPW = 32 / DD;               // pattern blocks per warp pass
+  constexpr int PASS = GP * BPW;             // GP block groups in flight per lane
+  constexpr int CH = (31 / PASS) * PASS;     // blocks per chunk (their cptr values + 1 fit one warp load)
+  constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
+  constexpr unsigned FULLMASK = 0xffffffffu;
+  __shared__ uint32_t codeBuf[8][PULL_CAP];
+  const PatternView& P = G.P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= P.nRowNodes) return;
+  const int q = lane / DD, v = lane - q * DD, i = v / D, k = v - i * D;
+  const bool active = q < BPW;
+  const int32_t b0 = P.nbrPtr[g], b1 = P.nbrPtr[g + 1];
+  const int nnb = b1 - b0;
+  const int64_t gGlobal = g + P.rowBegin;
+  const bool rowFixed = (DBC != IKB_DBC_RAW) ? (G.flags[dofOf(LAYOUT, D, P.nNodes, gGlobal, i)] != 0) : false;
+  const bool anyRowFixed = (DBC != IKB_DBC_RAW) ? __any_sync(FULLMASK, rowFixed) : false;
+  // Staged codes: w = 2*DD*(e*npair+p) + transposed = offset of the staged block in 4-byte units, flag in bit 0.  The
+  // value of this lane sits at 4-byte unit w + 2*(i*D+k) (direct) or w - 1 + 2*(k*D+i) (transposed), i.e. at
+  // laneBase + 4*(w + t*delta) with laneBase = Kst + 8*(i*D+k) and delta = 2*((k*D+i) - (i*D+k)) - 1: three integer
+  // instructions per value.  IDX32 (checked by the host): w < 2^31.
+  // (lane constants pass through an identity shuffle: ptxas would otherwise recompute them from threadIdx for every
+  // group instead of keeping them in registers)
+  uint64_t laneBase = reinterpret_cast<uint64_t>(G.Kst) + 8 * (i * D + k);
+  int32_t delta = 2 * ((k * D + i) - (i * D + k)) - 1;
+  laneBase = __shfl_sync(FULLMASK, (unsigned long long)laneBase, lane);
+  delta = __shfl_sync(FULLMASK, delta, lane);
+  auto stagedValue = [&](uint32_t w) -> double {
+    const int32_t t = (int32_t)(w & 1u);
+    if (IDX32) {
+      uint64_t a;  // (spelled in PTX: the compiler turns t*delta into a compare and a select)
+      asm("{\n\t.reg .b32 t, x;\n\tand.b32 t, %1, 1;\n\tmad.lo.s32 x, t, %2, %1;\n\tmad.wide.s32 %0, x, 4, %3;\n\t}"
+          : "=l"(a)
+          : "r"(w), "r"(delta), "l"(laneBase));
+      return pullLoad(a);
+    }
+    return pullLoad(laneBase + ((uint64_t)(w >> 1) * (2 * DD) + (int64_t)(t * (delta + 1))) * 4);
+  };
+  uint64_t dst = reinterpret_cast<uint64_t>(
+      (DBC == IKB_DBC_REDUCED) ? G.vals
+                               : G.vals + (INTERLEAVED ? (int64_t)DD * b0 + (int64_t)i * D * nnb + k
+                                                       : (int64_t)i * D * P.nBlocks + (int64_t)D * b0 + (int64_t)k * nnb));
+  dst = __shfl_sync(FULLMASK, (unsigned long long)dst, lane);
+  constexpr int SSTRIDE = INTERLEAVED ? D : 1;  // doubles between the entries (i,k) of consecutive slots
+  int64_t redStart = 0;
+  if (DBC == IKB_DBC_REDUCED) redStart = G.redRowStart[localRowOf(P, g, i)];
+  uint32_t* sm = codeBuf[warp];
+
+  for (int32_t cb = b0; cb < b1; cb += CH) {
+    const int nb = min(CH, b1 - cb);
+    const int32_t cp = cptr[cb + min(lane, nb)];
+    // Dirichlet work only where the row or one of the chunk's column nodes is constrained (warp-uniform)
+    bool slow = anyRowFixed;
+    if (DBC != IKB_DBC_RAW && !slow) {
+      bool f = false;
+      if (lane < nb) {
+        const int64_t gb = P.nbrIdx[cb + lane];
+#pragma unroll
+        for (int c = 0; c < D; ++c) f |= G.flags[dofOf(LAYOUT, D, P.nNodes, gb, c)] != 0;
+      }
+      slow = __any_sync(FULLMASK, f);
+    }
+    const int32_t cbase = __shfl_sync(FULLMASK, cp, 0);
+    const int32_t ncodes = __shfl_sync(FULLMASK, cp, nb) - cbase;
+    const bool staged = ncodes <= PULL_CAP;
+    __syncwarp();
+    if (staged) {
+      for (int t = lane; t < ncodes; t += 32) {
+        const uint32_t c = csrc[cbase + t];
+        sm[t] = IDX32 ? (c & SRC_MASK) * (uint32_t)(2 * DD) + (c >> 31) : __funnelshift_l(c, c, 1);
+      }
+      __syncwarp();
+    }
+    // per block of the chunk: (offset of its first code in the staged list) | (number of codes) << 16
+    const int32_t cnext = __shfl_down_sync(FULLMASK, cp, 1);
+    const uint32_t pack = (lane < nb) ? (uint32_t)(cp - cbase) | ((uint32_t)(cnext - cp) << 16) : 0u;
+    for (int r = 0; r < nb; r += PASS) {
+      int n[GP], s[GP];
+      uint32_t rel[GP];
+      double acc[GP];
+      int nAll = 0;
+#pragma unroll
+      for (int p = 0; p < GP; ++p) {
+        s[p] = r + p * BPW + q;  // block of this lane inside the chunk
+        const uint32_t pk = __shfl_sync(FULLMASK, pack, s[p]);
+        const bool valid = active && s[p] < nb;
+        n[p] = valid ? (int)(pk >> 16) : 0;
+        rel[p] = pk & 0xffffu;
+        nAll = max(nAll, n[p]);
+        acc[p] = 0.0;
+      }
+      if (staged) {
+        // all loads of a batch (4 contributions of GP blocks) are issued before the first add
+        const int nmax = __reduce_max_sync(FULLMASK, nAll);
+        for (int u = 0; u < nmax; u += 4) {
+          uint32_t w[GP][4];
+          double x[GP][4];
+#pragma unroll
+          for (int p = 0; p < GP; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[p][j] = 0.0;
+              w[p][j] = (u + j < n[p]) ? sm[rel[p] + u + j] : 0u;
+            }
+#pragma unroll
+          for (int p = 0; p < GP; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (u + j < n[p]) x[p][j] = stagedValue(w[p][j]);
+            // lanes past their count add +0.0 (the sum starts from +0.0, so this changes no bit)
+#pragma unroll
+          for (int p = 0; p < GP; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[p] += x[p][j];
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < GP; ++p) {
+          const int32_t c0 = cbase + (int32_t)rel[p];
+          // (rel is exact only below 2^16 codes per chunk; longer chunks re-derive the start from cptr)
+          const int32_t c0x = (ncodes < 65536) ? c0 : ((active && s[p] < nb) ? cptr[cb + s[p]] : 0);
+          const int nx = (ncodes < 65536) ? n[p] : ((active && s[p] < nb) ? cptr[cb + s[p] + 1] - c0x : 0);
+          for (int u = 0; u < nx; ++u) {
+            const uint32_t c = csrc[c0x + u];
+            acc[p] += stagedValue(IDX32 ? (c & SRC_MASK) * (uint32_t)(2 * DD) + (c >> 31) : __funnelshift_l(c, c, 1));
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < GP; ++p) {
+        if (!(active && s[p] < nb)) continue;
+        const int sg = (int)(cb - b0) + s[p];  // slot in the row
+        double val = acc[p];
+        if (DBC == IKB_DBC_RAW || !slow) {
+          if (DBC == IKB_DBC_REDUCED) {
+            const int32_t b = b0 + sg;
+            G.vals[redStart + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b, P.nbrIdx[b], k)] = val;
+          } else {
+            pullStore(dst + (uint64_t)(8 * SSTRIDE) * (uint32_t)sg, val);
+          }
+        } else {
+          const int32_t b = b0 + sg;
+          const int64_t gb = P.nbrIdx[b];
+          const bool colFixed = G.flags[dofOf(LAYOUT, D, P.nNodes, gb, k)] != 0;
+          if (DBC == IKB_DBC_REDUCED) {
+            if (!rowFixed && !colFixed)
+              G.vals[redStart + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b, gb, k)] = val;
+          } else {
+            // Full: zero constrained rows and columns, unit diagonal (simpleassemblers.inl:159-167)
+            if (rowFixed || colFixed) val = (gb == gGlobal && i == k) ? 1.0 : 0.0;
+            pullStore(dst + (uint64_t)(8 * SSTRIDE) * (uint32_t)sg, val);
+          }
+        }
+      }
+    }
+  }
+}
+
 // Residual gather: one thread per (node-row, component).  The node's (element, local node) adjacency is walked in
 // ascending element order (VectorFlatAssembler::get*VectorImpl, ikarus/assembler/simpleassemblers.inl:59-118);
 // external load and Dirichlet mode are applied on the fly.  A separate, tiny kernel so that the host can fetch R

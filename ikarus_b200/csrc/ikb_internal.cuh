@@ -116,6 +116,8 @@ struct Handle {
   DevBuf<uint32_t> adjCode;     // [nAdj]  e*n + la
   DevBuf<uint8_t> slotTab;      // [nAdj][n]
   int maxNbr = 0;               // longest pattern row in nodes
+  int pullGroups = 1;           // block groups in flight per lane in the pull gather (IKB_PULL_GROUPS=1|3, tuning)
+  bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)
   // reduced-mode structures
   bool reducedBuilt = false;
   int64_t nRed = 0, nnzRed = 0;
