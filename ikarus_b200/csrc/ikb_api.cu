@@ -244,6 +244,7 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   G.redRowStart = h->redRowStart.p;
   G.cbelow = h->cbelow.p;
   G.redVecOffset = 0;
+  G.pullStageMax = std::min(h->pullStageMax, PULL_CAP);
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
   if (!h->gatherTab.p) {
@@ -264,7 +265,7 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   cudaError_t e = cudaSuccess;
   const unsigned vecGrid = gridFor(nRowNodes * h->dim, 256);
   // pull gather: signed 32-bit staged offsets (in 4-byte units) when the whole staged K_e buffer is addressable that way
-  const bool idx32 = (double)h->nElem * h->npair * h->dim * h->dim * 2.0 < 2147483000.0;
+  const bool idx32 = !h->pullIdx64 && (double)h->nElem * h->npair * h->dim * h->dim * 2.0 < 2147483000.0;
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \
     if (G.vec) {                                                                                                     \
@@ -567,6 +568,9 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     return IKB_EINVAL;
   }
   if (const char* gm = std::getenv("IKB_GATHER")) h->gatherPull = std::string(gm) != "tile";
+  // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
+  if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
+  if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
   if (const char* gp = std::getenv("IKB_PULL_GROUPS")) h->pullGroups = std::atoi(gp) == 3 ? 3 : 1;
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;

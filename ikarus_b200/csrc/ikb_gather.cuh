@@ -35,6 +35,7 @@ struct GatherArgs {
   const int64_t* redRowStart;
   const int32_t* cbelow;
   int64_t redVecOffset;  // index of the first local free row in the reduced vector
+  int pullStageMax;      // pull gather: chunks with at most this many codes are staged in shared memory (<= PULL_CAP)
 };
 
 // One warp per node-row.  For every element touching the node (ascending element order, as the reference's
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256) gather_pull_kernel(GatherArgs G, const in
     }
     const int32_t cbase = __shfl_sync(FULLMASK, cp, 0);
     const int32_t ncodes = __shfl_sync(FULLMASK, cp, nb) - cbase;
-    const bool staged = ncodes <= PULL_CAP;
+    const bool staged = ncodes <= G.pullStageMax;
     __syncwarp();
     if (staged) {
       for (int t = lane; t < ncodes; t += 32) {
