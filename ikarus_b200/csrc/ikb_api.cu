@@ -280,14 +280,11 @@ int launchGather(Handle* h, unsigned what, int dbc) {
       cudaEventRecord(h->evVec, vs);                                                                                 \
     }                                                                                                                \
     if (G.vals && h->gatherPull && h->csrc.p) {                                                                      \
-      if (idx32 && h->pullGroups == 3)                                                                               \
-        gather_pull_kernel<DIM, MODE, IL, true, 3><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(        \
-            G, h->cptr.p, h->csrc.p);                                                                                \
-      else if (idx32)                                                                                                \
-        gather_pull_kernel<DIM, MODE, IL, true, 1><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(        \
+      if (idx32)                                                                                                     \
+        gather_pull_kernel<DIM, MODE, IL, true><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(           \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else                                                                                                           \
-        gather_pull_kernel<DIM, MODE, IL, false, 1><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(       \
+        gather_pull_kernel<DIM, MODE, IL, false><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(          \
             G, h->cptr.p, h->csrc.p);                                                                                \
       if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
     } else if (G.vals) {                                                                                             \
@@ -571,7 +568,6 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
-  if (const char* gp = std::getenv("IKB_PULL_GROUPS")) h->pullGroups = std::atoi(gp) == 3 ? 3 : 1;
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one

@@ -116,7 +116,6 @@ struct Handle {
   DevBuf<uint32_t> adjCode;     // [nAdj]  e*n + la
   DevBuf<uint8_t> slotTab;      // [nAdj][n]
   int maxNbr = 0;               // longest pattern row in nodes
-  int pullGroups = 1;           // block groups in flight per lane in the pull gather (IKB_PULL_GROUPS=1|3, tuning)
   int pullStageMax = 1 << 30;   // clamped to PULL_CAP at launch (IKB_PULL_STAGE_MAX, test hook)
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
   bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)

@@ -350,14 +350,13 @@ def test_unstructured_numbering_and_connectivity(case, layout):
 @pytest.mark.parametrize("layout", ["interleaved", "lexicographic"])
 def test_gather_variants_bit_identical(case, layout, monkeypatch):
     """The matrix gather has two kernels (pull: per-block contribution lists, default; tile: warp tile) and the pull
-    kernel has rarely taken paths (contribution lists too long to stage, 64-bit staged offsets, 3 block groups in
-    flight).  All of them add the same staged values in the same order, so every mode must give identical bits."""
+    kernel has rarely taken paths (contribution lists too long to stage, 64-bit staged offsets).  All of them add the same staged values in the same order, so every mode must give identical bits."""
     mesh, ref, dev, d = _setup(*case, layout=layout)
     req = ik.FERequirements(d, 0.4)
     modes = (ik.DBCOption.Raw, ik.DBCOption.Full, ik.DBCOption.Reduced)
     base = [dev.matrix(req, ik.MatrixAffordance.stiffness, m).data.copy() for m in modes]
     variants = [{"IKB_GATHER": "tile"}, {"IKB_PULL_STAGE_MAX": "0"}, {"IKB_PULL_STAGE_MAX": "5"}, {"IKB_PULL_IDX64": "1"},
-                {"IKB_PULL_GROUPS": "3"}, {"IKB_PULL_GROUPS": "3", "IKB_PULL_IDX64": "1", "IKB_PULL_STAGE_MAX": "7"}]
+                {"IKB_PULL_IDX64": "1", "IKB_PULL_STAGE_MAX": "7"}]
     for env in variants:
         with monkeypatch.context() as mp:
             for k, v in env.items():
