@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(256, 8) gather_pull_kernel(GatherArgs G, const
   laneBase = __shfl_sync(FULLMASK, (unsigned long long)laneBase, lane);
   delta = __shfl_sync(FULLMASK, delta, lane);
   auto stagedValue = [&](uint32_t w) -> double {
-    const int32_t t = (int32_t)(w & 1u);
     if (IDX32) {
       uint64_t a;  // (spelled in PTX: the compiler turns t*delta into a compare and a select)
       asm("{\n\t.reg .b32 t, x;\n\tand.b32 t, %1, 1;\n\tmad.lo.s32 x, t, %2, %1;\n\tmad.wide.s32 %0, x, 4, %3;\n\t}"
@@ -270,7 +269,13 @@ __global__ void __launch_bounds__(256, 8) gather_pull_kernel(GatherArgs G, const
           : "r"(w), "r"(delta), "l"(laneBase));
       return pullLoad(a);
     }
-    return pullLoad(laneBase + ((uint64_t)(w >> 1) * (2 * DD) + (int64_t)(t * (delta + 1))) * 4);
+    // 64-bit offsets (staged codes are 2*(e*npair+p) + transposed here): laneBase + w*4*DD + t*(4*(delta+1) - 4*DD)
+    uint64_t a;
+    asm("{\n\t.reg .b32 t;\n\t.reg .b64 o;\n\tand.b32 t, %1, 1;\n\tmul.wide.s32 o, t, %2;\n\t"
+        "mad.wide.u32 %0, %1, %3, %4;\n\tadd.s64 %0, %0, o;\n\t}"
+        : "=l"(a)
+        : "r"(w), "r"(4 * (delta + 1) - 4 * DD), "n"(4 * DD), "l"(laneBase));
+    return pullLoad(a);
   };
   uint64_t dst = reinterpret_cast<uint64_t>(
       (DBC == IKB_DBC_REDUCED) ? G.vals
