@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1d"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1e"
 go = os.path.join(ROOT, "gpurun_out")
 pr = os.path.join(ROOT, "profiles")
 
@@ -38,8 +38,8 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "l1tex__data_pipe_lsu_wavefront
         "lts__throughput.avg.pct", "issue_stalled_long_scoreboard_per", "issue_stalled_short_scoreboard_per", "issue_stalled_wait_per",
         "issue_stalled_math_pipe", "issue_stalled_barrier_per", "issue_stalled_mio", "lts__t_sectors_srcunit_tex_op"]
 keep = [i for i, h in enumerate(hdr) if any(k in h for k in keys)]
-traffic = {"source": f"profiles/r1_ncu_full_elem_gather_v4.csv (ncu --set full, C2 workload, one launch each): dram__bytes_read.sum + dram__bytes_write.sum"}
-with open(os.path.join(pr, "r1_ncu_full_elem_gather_v4.csv"), "w") as f:
+traffic = {"source": f"profiles/r1_ncu_full_elem_gather_v5.csv (ncu --set full, C2 workload, one launch each): dram__bytes_read.sum + dram__bytes_write.sum"}
+with open(os.path.join(pr, "r1_ncu_full_elem_gather_v5.csv"), "w") as f:
     f.write("# ncu --set full --clock-control none --import-source on -k regex:'elem_q1|gather_pull' -s 6 -c 2 python bench.py --steps 3 --warmup 3 --no-cpu --no-newton (C2 workload)\n")
     for r in rows[2:]:
         for i in keep:
