@@ -171,6 +171,14 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
 
   // ------------------------------------------------------------------ phase 1
   if (active) {
+    if constexpr (USELAP) {
+      // the Laplacian table entries of this thread (node t) are needed only after the Gauss loop of phase 2: pull them
+      // into L2 now (no registers held) instead of paying a DRAM latency at the very end
+#pragma unroll
+      for (int k = 0; k <= C::KMAX; ++k)
+        if (!(k == C::KMAX && t >= N / 2))
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Lap + (size_t)(k * N + t) * A.nElem + e));
+    }
     const double lo = 0.5 - 0.28867513459481287, hi = 0.5 + 0.28867513459481287;
     double xi[D], om[D];
 #pragma unroll
