@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
   using Cfg = GatherCfg<D, N>;
   constexpr int DD = D * D;
   constexpr int RS = Cfg::RS, NU = Cfg::NU, CHUNK = Cfg::CHUNK, NIT = Cfg::NIT;
-  constexpr int HALF = N / 2;
   constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
   extern __shared__ double gsm[];
   // offTab[la][idx]: offset of value idx = (lb, ii, k) of chunk la inside the symmetric-packed staged K_e for
