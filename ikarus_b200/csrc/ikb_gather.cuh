@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
 // one 8*D*D-byte staged block per contribution and add it in a register; no shared-memory read-modify-write, no
 // atomics, values bit-identical to gather_kernel.  The codes of a chunk of blocks are staged in shared memory with
 // coalesced loads so that the dependent chain per node-row is cptr -> codes -> values (three global latencies), and
-// two block groups with up to four contributions each are in flight per lane.
+// up to four contributions of a block are in flight per lane.
 constexpr int PULL_CAP = 256;  // staged codes per warp
 
 __device__ __forceinline__ double pullLoad(uint64_t a) {
