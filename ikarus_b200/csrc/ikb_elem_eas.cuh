@@ -592,8 +592,22 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     const double idk = invd[k];
     for (int i = k + 1 + a; i < M; i += N) {
       const double lik = Dm[i * M + k] * idk;
-#pragma unroll 4
-      for (int j = k + 1; j <= i; ++j) Dm[i * M + j] = fma(-lik, Dm[j * M + k], Dm[i * M + j]);
+      // Row i is updated by this thread only and column k is not written in this loop, so the loads of a batch of
+      // four entries can all be issued before the first store (the compiler cannot prove that through the shared
+      // pointer and would serialise load -> fma -> store per entry).  Same operations, same order per entry.
+      const double* colk = Dm + k;
+      double* rowi = Dm + i * M;
+      for (int j = k + 1; j <= i; j += 4) {
+        const bool p1 = j + 1 <= i, p2 = j + 2 <= i, p3 = j + 3 <= i;  // the last batch of a row may be short
+        const double c0 = colk[j * M], c1 = p1 ? colk[(j + 1) * M] : 0.0, c2 = p2 ? colk[(j + 2) * M] : 0.0,
+                     c3 = p3 ? colk[(j + 3) * M] : 0.0;
+        const double d0 = rowi[j], d1 = p1 ? rowi[j + 1] : 0.0, d2 = p2 ? rowi[j + 2] : 0.0,
+                     d3 = p3 ? rowi[j + 3] : 0.0;
+        rowi[j] = fma(-lik, c0, d0);
+        if (p1) rowi[j + 1] = fma(-lik, c1, d1);
+        if (p2) rowi[j + 2] = fma(-lik, c2, d2);
+        if (p3) rowi[j + 3] = fma(-lik, c3, d3);
+      }
     }
     __syncwarp();
     for (int i = k + 1 + a; i < M; i += N) Dm[i * M + k] *= idk;
