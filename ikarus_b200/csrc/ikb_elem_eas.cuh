@@ -582,10 +582,8 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   }
 
   // ------------------------------------------------------------------ cooperative LDL^T (lower triangle, in place)
-  // One barrier per pivot: the thread that updates row k+1 (its first row, a single entry: the next pivot) computes the
-  // reciprocal of that pivot at once, so the division overlaps the other rows' updates and nobody waits on it; the
-  // columns are divided by their pivots in one pass after the elimination (the elimination itself works on the
-  // unscaled columns), and the solves below need no divisions at all.
+  // The reciprocal of pivot k+1 is computed by the owner of row k+1 while the others scale column k, so no
+  // thread waits on a division inside the elimination, and the solves below need no divisions at all.
   double* invd = Pm + N * M;  // [M]
   if (a == 0) invd[0] = 1.0 / Dm[0];
   __syncwarp();
@@ -605,30 +603,17 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
                      c3 = p3 ? colk[(j + 3) * M] : 0.0;
         const double d0 = rowi[j], d1 = p1 ? rowi[j + 1] : 0.0, d2 = p2 ? rowi[j + 2] : 0.0,
                      d3 = p3 ? rowi[j + 3] : 0.0;
-        const double v0 = fma(-lik, c0, d0);
-        rowi[j] = v0;
+        rowi[j] = fma(-lik, c0, d0);
         if (p1) rowi[j + 1] = fma(-lik, c1, d1);
         if (p2) rowi[j + 2] = fma(-lik, c2, d2);
         if (p3) rowi[j + 3] = fma(-lik, c3, d3);
-        if (i == k + 1) invd[k + 1] = 1.0 / v0;  // row k+1 has the single entry (k+1, k+1): the next pivot, now final
       }
     }
     __syncwarp();
+    for (int i = k + 1 + a; i < M; i += N) Dm[i * M + k] *= idk;
+    if (k + 1 < M && ((k + 1) % N) == a) invd[k + 1] = 1.0 / Dm[(k + 1) * M + k + 1];
+    __syncwarp();
   }
-  // L = (unscaled columns) / pivots, row-wise: thread a owns rows a, a+N, ...
-  for (int i = a; i < M; i += N) {
-    double* rowi = Dm + i * M;
-    for (int k = 0; k < i; k += 4) {
-      const bool p1 = k + 1 < i, p2 = k + 2 < i, p3 = k + 3 < i;
-      const double d0 = rowi[k], d1 = p1 ? rowi[k + 1] : 0.0, d2 = p2 ? rowi[k + 2] : 0.0, d3 = p3 ? rowi[k + 3] : 0.0;
-      const double s0 = invd[k], s1 = p1 ? invd[k + 1] : 0.0, s2 = p2 ? invd[k + 2] : 0.0, s3 = p3 ? invd[k + 3] : 0.0;
-      rowi[k] = d0 * s0;
-      if (p1) rowi[k + 1] = d1 * s1;
-      if (p2) rowi[k + 2] = d2 * s2;
-      if (p3) rowi[k + 3] = d3 * s3;
-    }
-  }
-  __syncwarp();
   // ------------------------------------------------------------------ solves
   // With D = Lf diag(d) Lf^T:  L^T D^-1 L = Y^T diag(1/d) Y  and  L^T D^-1 Rt = Y^T diag(1/d) y_R  with
   // Y = Lf^-1 L, y_R = Lf^-1 Rt, so the assembly only needs FORWARD substitutions.  Thread a does the D columns
