@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1e"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1f"
 go = os.path.join(ROOT, "gpurun_out")
 pr = os.path.join(ROOT, "profiles")
 
