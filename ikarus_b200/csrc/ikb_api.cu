@@ -259,6 +259,7 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   }
   G.offTab = h->gatherTab.p;
   const int warps = 8;
+  const int pw = h->pullWarps;  // warps per CTA of the pull gather
   const size_t smem = (size_t)warps * G.maxOut * sizeof(double);
   // one warp per work unit (node-row, or scalar row for Q2)
   const int64_t wantBlocks = gridFor(nRowNodes * (h->dim / rs), warps);
@@ -281,10 +282,10 @@ int launchGather(Handle* h, unsigned what, int dbc) {
     }                                                                                                                \
     if (G.vals && h->gatherPull && h->csrc.p) {                                                                      \
       if (idx32)                                                                                                     \
-        gather_pull_kernel<DIM, MODE, IL, true><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(           \
+        gather_pull_kernel<DIM, MODE, IL, true><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(                 \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else                                                                                                           \
-        gather_pull_kernel<DIM, MODE, IL, false><<<gridFor(nRowNodes, warps), warps * 32, 0, h->stream>>>(          \
+        gather_pull_kernel<DIM, MODE, IL, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(                \
             G, h->cptr.p, h->csrc.p);                                                                                \
       if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
     } else if (G.vals) {                                                                                             \
@@ -568,6 +569,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
+  if (const char* w = std::getenv("IKB_PULL_WARPS")) h->pullWarps = std::min(std::max(std::atoi(w), 1), 8);
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one

@@ -117,6 +117,7 @@ struct Handle {
   DevBuf<uint8_t> slotTab;      // [nAdj][n]
   int maxNbr = 0;               // longest pattern row in nodes
   int pullStageMax = 1 << 30;   // clamped to PULL_CAP at launch (IKB_PULL_STAGE_MAX, test hook)
+  int pullWarps = 4;            // warps per CTA of the pull gather (IKB_PULL_WARPS, tuning; 4 measured 2 % faster than 8)
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
   bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)
   // reduced-mode structures
