@@ -569,7 +569,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
-  if (const char* w = std::getenv("IKB_PULL_WARPS")) h->pullWarps = std::min(std::max(std::atoi(w), 1), 8);
+  if (const char* w = std::getenv("IKB_PULL_WARPS")) h->pullWarps = std::min(std::max(std::atoi(w), 1), PULL_WARPS_MAX);
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one

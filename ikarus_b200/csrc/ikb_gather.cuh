@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
 // coalesced loads so that the dependent chain per node-row is cptr -> codes -> values (three global latencies), and
 // up to four contributions of a block are in flight per lane.
 constexpr int PULL_CAP = 256;  // staged codes per warp
+constexpr int PULL_WARPS_MAX = 4;  // warps per CTA (sizes the staging buffer: 4 KB per CTA, 64 KB per SM at 16 CTAs)
 
 __device__ __forceinline__ double pullLoad(uint64_t a) {
   double v;
@@ -228,17 +229,17 @@ __device__ __forceinline__ void pullStore(uint64_t a, double v) {
   asm volatile("st.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
 }
 
-// 32 registers per thread (8 CTAs of 8 warps per SM): the kernel is latency bound, 64 resident warps per SM measured
-// 13 % faster than the 48 warps the unconstrained 40-register build reaches.
+// 32 registers per thread (16 CTAs of 4 warps per SM): the kernel is latency bound, 64 resident warps per SM measured
+// 13 % faster than the 48 warps the unconstrained 40-register build reaches; 4 warps per CTA 2 % faster than 8.
 template <int D, int DBC, bool INTERLEAVED, bool IDX32>
-__global__ void __launch_bounds__(256, 8) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
+__global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
                                                           const uint32_t* __restrict__ csrc) {
   constexpr int DD = D * D;
   constexpr int BPW = 32 / DD;               // pattern blocks per warp pass
   constexpr int CH = (31 / BPW) * BPW;       // blocks per chunk (their cptr values + 1 fit one warp load)
   constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
   constexpr unsigned FULLMASK = 0xffffffffu;
-  __shared__ uint32_t codeBuf[8][PULL_CAP];
+  __shared__ uint32_t codeBuf[PULL_WARPS_MAX][PULL_CAP];
   const PatternView& P = G.P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
