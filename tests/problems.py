@@ -2,6 +2,7 @@
 import numpy as np
 
 import ikarus_oracle as o
+from golden_data import GOLDEN
 
 
 def cantilever(dim, mat_kind, eas_m, cells=None, E=100.0, nu=0.3, L=10.0, h=2.0):
@@ -57,11 +58,9 @@ def unstructured(mesh, seed, drop=None):
     return o.Mesh(mesh.dim, mesh.order, coords, new_id[en], mesh.corner_coords[keep], mesh.cells)
 
 
-ELASTIC_STRIP_EXPECTED = {
-    # tests/src/testinhomogeneousdbc.cpp:22-33 (load control): (total iterations, u_y at (L/2, 0)); lambda ends at 1
-    ("svk", 1): (6, 1.814746879163122), ("svk", 2): (6, 1.850732157345016),
-    ("neohooke", 1): (7, 2.207111977584091), ("neohooke", 2): (7, 2.1944518710582974),
-}
+# tests/src/testinhomogeneousdbc.cpp:22-33 (load control): (total iterations, u_y at (L/2, 0)); lambda ends at 1
+ELASTIC_STRIP_EXPECTED = {(c["material"], c["order"]): (c["iterations"], c["u_y"])
+                          for c in GOLDEN["elastic_strip"]["cases"]}
 
 
 def elastic_strip(mat_kind, order):
@@ -89,9 +88,7 @@ def patch_test_mesh():
     return o.Mesh(2, 1, X, en, X[en], ())
 
 
-PATCH_EXPECTED_D = np.array([0.0, 0.0, 0.001, 0.0, 0.0, -0.000125, 0.001, -0.000125, 0.0001666666666666667,
-                             -0.0000208333333333333, 0.000750, -0.00003125, 0.0003333333333333333,
-                             -0.0000833333333333333, 0.000666666666666667, -0.0000833333333333333])
+PATCH_EXPECTED_D = np.array(GOLDEN["plane_stress_patch_test"]["displacements"], float)
 
 
 def fixed_distorted_quad():

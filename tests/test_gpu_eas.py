@@ -7,6 +7,7 @@ import ikarus_b200 as ik
 import ikarus_oracle as o
 from devproblems import device_assembler, entry_error
 from problems import cantilever, distorted
+from golden_data import GOLDEN
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -74,12 +75,9 @@ def test_eas_zero_parameters_is_plain_element():
 
 @pytest.mark.parametrize(
     "dim,matk,m,iters,maxd",
-    [
-        (3, "neohooke", 21, 80, 4.781820664768682),  # tests/src/testcantileverbeamEAS.cpp:66-67
-        (3, "svk", 21, 80, 4.7692391315649365),  # :64-65
-        (2, "neohooke", 4, 80, 4.479930218997457),  # :28-29
-        (2, "svk", 4, 80, 4.459851990257645),  # :26-27
-    ],
+    # tests/src/testcantileverbeamEAS.cpp:26-29, 64-67 (tests/golden/reference_known_answers.json)
+    [(c["dim"], c["material"], c["eas"], c["newton_iterations"], c["max_abs_d"])
+     for c in GOLDEN["cantilever_eas"]["cases"]],
 )
 def test_reference_cantilever_known_answers_on_device(dim, matk, m, iters, maxd):
     """The reference's own golden values (80 Newton iterations, max|d| to 1e-10) with the device assembler
@@ -107,4 +105,4 @@ def test_cantilever_with_device_pcg_matches_golden_iterations():
     nr = ik.NewtonRaphson(dev, ik.NewtonRaphsonConfig(ik.NRSettings(tol=1e-10), ik.DeviceLinearSolver(1e-14)))
     info = ik.LoadControl(nr, ik.LoadControlConfig(20, 0.0, 1.0)).run(req)
     assert info.success and info.totalIterations == 80
-    assert abs(np.abs(req.globalSolution()).max() - 4.781820664768682) < 1e-8
+    assert abs(np.abs(req.globalSolution()).max() - GOLDEN["cantilever_eas"]["cases"][0]["max_abs_d"]) < 1e-8

@@ -6,6 +6,7 @@ import pytest
 import ikarus_b200 as ik
 import ikarus_oracle as o
 from devproblems import device_assembler, entry_error
+from golden_data import GOLDEN
 from problems import PATCH_EXPECTED_D, distorted, fixed_distorted_quad, patch_test_mesh
 
 pytestmark = pytest.mark.gpu
@@ -79,10 +80,10 @@ def test_B2_single_element_eigenvalues_on_device():
     lam, mu = o.lame_from_E_nu(1000.0, 0.0)
     mat = o.Material("svk", lam, mu, plane_stress=True, ps_tol=1e-8)
     dev = device_assembler(mesh, o.ElementKind(2, 1, "gl"), mat, np.zeros(8, dtype=bool))
-    req = ik.FERequirements(np.array([2, 4, 3.25, -1.2, 0.003, 6, 3, 2.864]), 0.0)
+    gold = GOLDEN["plane_stress_single_element_eigenvalues"]
+    req = ik.FERequirements(np.array(gold["d"], float), 0.0)
     K = dev.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Raw).toarray()
-    exp = np.array([0, 0, 1845.6296388251504753, 14192.4707553121224317, 19964.32719133414782, 29973.7943273325380486,
-                    46641.183728849332812, 95447.6156712376251918])
+    exp = np.array(gold["abs_eigenvalues"], float)
     assert np.abs(np.sort(np.abs(np.linalg.eigvalsh(K))) - exp).max() < 1e-8
 
 
@@ -112,4 +113,4 @@ def test_linear_patch_test_with_idbc_on_device(dbc):
     big = np.abs(PATCH_EXPECTED_D) > 1e-10
     assert np.abs(d[big] - PATCH_EXPECTED_D[big]).max() < 1e-10
     sig = asm.calculateAt(ik.ResultTypes.linearStress, req, [0.5, 0.5])
-    assert np.abs(sig[:, 0, 0] - 4.1666666666666667).max() < 1e-10
+    assert np.abs(sig[:, 0, 0] - GOLDEN["plane_stress_patch_test"]["sigma_xx"]).max() < 1e-10

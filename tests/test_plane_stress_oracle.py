@@ -9,6 +9,7 @@ import numpy as np
 import scipy.sparse.linalg as spla
 
 import ikarus_oracle as o
+from golden_data import GOLDEN
 from problems import PATCH_EXPECTED_D, fixed_distorted_quad, patch_test_mesh
 
 
@@ -16,11 +17,11 @@ def test_B2_single_element_eigenvalues():
     mesh = fixed_distorted_quad()
     lam, mu = o.lame_from_E_nu(1000.0, 0.0)
     mat = o.Material("svk", lam, mu, plane_stress=True, ps_tol=1e-8)
-    d = np.array([2, 4, 3.25, -1.2, 0.003, 6, 3, 2.864])
+    g = GOLDEN["plane_stress_single_element_eigenvalues"]
+    d = np.array(g["d"], float)
     K = o.element_quantities(o.ElementKind(2, 1, "gl"), mat, mesh.corner_coords, d.reshape(1, 4, 2))["K"][0]
     ev = np.abs(np.linalg.eigvalsh(K))
-    exp = np.array([0, 0, 1845.6296388251504753, 14192.4707553121224317, 19964.32719133414782, 29973.7943273325380486,
-                    46641.183728849332812, 95447.6156712376251918])
+    exp = np.array(g["abs_eigenvalues"], float)
     assert np.abs(np.sort(ev) - exp).max() < 1e-8
 
 
@@ -66,4 +67,4 @@ def test_linear_patch_test_with_inhomogeneous_dirichlet_values():
         assert np.abs(d[big] - PATCH_EXPECTED_D[big]).max() < 1e-10
         u = d[mesh.elem_dofs()].reshape(5, 4, 2)
         sig = o.stress_at(kind, mat, mesh.corner_coords, u, np.array([0.5, 0.5]))
-        assert np.abs(sig[:, 0] - 4.1666666666666667).max() < 1e-10  # constant stress state
+        assert np.abs(sig[:, 0] - GOLDEN["plane_stress_patch_test"]["sigma_xx"]).max() < 1e-10  # constant stress state

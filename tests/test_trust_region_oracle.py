@@ -5,6 +5,7 @@ import numpy as np
 import scipy.sparse as sp
 
 import ikarus_oracle as o
+from golden_data import GOLDEN
 
 
 def _f3(x):
@@ -23,14 +24,15 @@ def _ddf3(x):
 
 
 def test_trust_region3_identity_and_diagonal_iteration_counts():
-    expected = np.array([2.3066301277034750861, -0.33230864873179355445])
-    for precond, iters in (("identity", 11), ("diagonal", 8)):
+    g = GOLDEN["trust_region"]
+    expected = np.array(g["minimiser"])
+    for precond, iters in g["iterations"].items():
         x, info = o.trust_region(_f3, _df3, _ddf3, np.array([0.7, -3.3]), precond=precond, max_iter=30, grad_tol=1e-12,
                                  corr_tol=1e-12, Delta0=1)
         assert info["success"] and info["iterations"] == iters
         assert info["residual_norm"] < 1e-12
         assert np.abs(x - expected).max() < 1e-12
-        assert abs(_f3(x) - (-31.180733385187978)) < 1e-12
+        assert abs(_f3(x) - g["energy"]) < 1e-12
 
 
 def test_truncated_cg_stop_reasons():
