@@ -353,6 +353,9 @@ def run_ours(args):
 
 
 def main():
+    # keep stdout to the one JSON line: a box-wide NCCL_DEBUG=VERSION makes NCCL print its banner there
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
