@@ -7,6 +7,7 @@
 
 #include "ikb_dist.cuh"
 #include "ikb_elem_eas.cuh"
+#include "ikb_elem_h8mma.cuh"
 #include "ikb_elem_q1.cuh"
 #include "ikb_elem_q2.cuh"
 #include "ikb_gather.cuh"
@@ -99,7 +100,11 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
         A.Est = h->Est.p + b;
         if (c) h->launches++;
       }
-      if (h->dim == 3) {
+      if (h->dim == 3 && h->elemMma && A.Lap && h->form != FORM_SVK) {
+        // Hex8 with the contraction on the FP64 tensor cores (ikb_elem_h8mma.cuh); IKB_ELEM=fma selects the FMA kernel
+        if (h->form == FORM_LE) e = launchElemH8Mma<FORM_LE>(A, h->stream, h->h8MinBlocks);
+        if (h->form == FORM_NH) e = launchElemH8Mma<FORM_NH>(A, h->stream, h->h8MinBlocks);
+      } else if (h->dim == 3) {
         if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
         if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
         if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
@@ -566,6 +571,8 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     return IKB_EINVAL;
   }
   if (const char* gm = std::getenv("IKB_GATHER")) h->gatherPull = std::string(gm) != "tile";
+  if (const char* em = std::getenv("IKB_ELEM")) h->elemMma = std::string(em) != "fma";
+  if (const char* mb = std::getenv("IKB_H8_MINB")) h->h8MinBlocks = std::atoi(mb);
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
@@ -1904,7 +1911,7 @@ int ikb_time_phase(ikb_handle hh, const char* phase, int dbc, int reps, float* m
   IKB_CUDA(h, cudaEventCreate(&e1));
   int rc = IKB_OK;
   DevBuf<double> tmp;
-  if (p == "dfma_peak") IKB_CUDA(h, tmp.alloc((size_t)148 * 16 * 256));
+  if (p == "dfma_peak" || p == "dmma_peak") IKB_CUDA(h, tmp.alloc((size_t)148 * 16 * 256));
   if (p == "elements" || p == "gather") {
     if ((rc = ikb_assemble(hh, IKB_MATRIX | IKB_VECTOR, dbc))) return rc;
   } else if (p == "spmv") {
@@ -1925,6 +1932,10 @@ int ikb_time_phase(ikb_handle hh, const char* phase, int dbc, int reps, float* m
       rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p);
     else if (p == "dfma_peak") {
       dfma_peak_kernel<<<148 * 16, 256, 0, h->stream>>>(tmp.p, 2048);
+      h->launches++;
+    } else if (p == "dmma_peak") {
+      // 8 tiles x 2048 DMMAs per warp, 256 FMA each
+      dmma_peak_kernel<<<148 * 16, 256, 0, h->stream>>>(tmp.p, 2048);
       h->launches++;
     } else
       rc = fail(h, IKB_EINVAL, "unknown phase");

@@ -458,13 +458,14 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
         for (int i = 0; i < D; ++i) acc[k][i * D + i] += sab;
       }
     }
-    // park the uncondensed blocks in the staging array (this thread re-reads them after the solve)
+    // park the uncondensed blocks in the staging array (this thread re-reads them after the solve) -- only when the
+    // matrix was asked for: a VECTOR-only sweep must leave a staged, already condensed K_e of the same state untouched
     double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
       double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
-      if (active) {
+      if (active && (A.what & IKB_MATRIX)) {
 #pragma unroll
         for (int q = 0; q < DD; ++q) dst[q] = acc[k][q];
       }

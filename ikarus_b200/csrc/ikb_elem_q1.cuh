@@ -70,7 +70,7 @@ __device__ __forceinline__ bool reduceC33(double lam, double mu, double tol, dou
   double f;
   for (int it = 0;; ++it) {
     const double detC = det2 * c33;
-    if (!(detC > 1e-10)) return false;
+    if (!(detC > 0.0)) return false;  // checkPositiveOrAbort: relativeWeak compare against 0 == (detC <= 0)
     lnJ = log(sqrt(detC));
     f = mu * (1.0 - 1.0 / c33) + lam * lnJ / c33;
     if (!(fabs(f) > tol && it < 100)) break;

@@ -119,6 +119,8 @@ struct Handle {
   int pullStageMax = 1 << 30;   // clamped to PULL_CAP at launch (IKB_PULL_STAGE_MAX, test hook)
   int pullWarps = 4;            // warps per CTA of the pull gather (IKB_PULL_WARPS, tuning; 4 measured 2 % faster than 8)
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
+  bool elemMma = true;          // Hex8 NeoHooke/LinearElastic: tangent contraction by DMMA (IKB_ELEM=fma: FMA kernel)
+  int h8MinBlocks = 5;          // register budget of the DMMA kernel as resident CTAs per SM (IKB_H8_MINB, tuning)
   bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)
   // reduced-mode structures
   bool reducedBuilt = false;

@@ -58,7 +58,7 @@ __device__ __forceinline__ bool stress3d(int form, double lambda, double mu, con
   const double c12 = E6[3], c02 = E6[4], c01 = E6[5];
   const double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
   const double detC = c00 * a00 + c01 * a01 + c02 * a02;
-  if (!(detC > 1e-10)) return false;
+  if (!(detC > 0.0)) return false;  // checkPositiveOrAbort (relativeWeak compare against 0 == detC <= 0)
   const double id = 1.0 / detC;
   const double i00 = a00 * id, i01 = a01 * id, i02 = a02 * id;
   const double i11 = (c00 * c22 - c02 * c02) * id, i12 = (c01 * c02 - c00 * c12) * id, i22 = (c00 * c11 - c01 * c01) * id;

@@ -88,7 +88,7 @@ static int law3d(const ikref_cfg* c, const double E6[6], double* psi, double S6[
     Cm[i][j] = Cm[j][i] = v;
   }
   double detC = inv_small(3, Cm, Ci);
-  if (!(detC > 1e-10)) return 1; /* materialhelpers.hh:120-126 aborts */
+  if (!(detC > 0.0)) return 1; /* materialhelpers.hh:120-126: FloatCmp::le(det, 0, 1e-10) with the default relativeWeak style == det <= 0 */
   double logJ = log(sqrt(detC));
   *psi = 0.5 * mu * (Cm[0][0] + Cm[1][1] + Cm[2][2] - 3 - 2 * logJ) + 0.5 * lam * logJ * logJ;
   double T[3][3][3][3];

@@ -168,7 +168,7 @@ class Material:
             # neohooke.hh:79-142 with C = 2E + I (strainconversions.hh:88-106)
             Cm = 2.0 * from_voigt(E6, strain=True) + np.eye(3)
             detC = np.linalg.det(Cm)
-            if np.any(detC <= 1e-10):  # materialhelpers.hh:120-126 (abort in the reference)
+            if np.any(detC <= 0.0):  # materialhelpers.hh:120-126: Dune::FloatCmp::le(det, 0, 1e-10), relativeWeak == (det <= 0)
                 raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
             logJ = np.log(np.sqrt(detC))
             invC = np.linalg.inv(Cm)
@@ -199,7 +199,7 @@ class Material:
                 c33 = 1.0
                 for it in range(101):
                     detC = det2 * c33
-                    if detC <= 1e-10:
+                    if detC <= 0.0:  # same check, see above
                         raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
                     lnJ = np.log(np.sqrt(detC))
                     f = mu * (1.0 - 1.0 / c33) + lam * lnJ / c33

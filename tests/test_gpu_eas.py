@@ -63,6 +63,25 @@ def test_eas_matrix_vector_and_alpha_update(case):
         dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
 
 
+def test_eas_vector_only_sweep_keeps_the_staged_condensed_matrix():
+    """matrix(Full) -> vector() -> matrix(Reduced) at one state through the dense assembler, which asks for MATRIX and
+    VECTOR separately: the VECTOR-only sweep must not replace the condensed staged K_e by the uncondensed blocks
+    (enhancedassumedstrains.hh:292-296)."""
+    mesh, ref, _, d, alpha, _ = _setup(3, 9, "neohooke", "gl")
+    dense = device_assembler(mesh, ref.kind, ref.mat, ref.flags, dense=True)
+    ref.alpha = alpha.copy()
+    dense.setInternalVariables(alpha)
+    req = ik.FERequirements(d, 0.0)
+    Kf = dense.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Full)
+    R = dense.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Full)
+    Kr = dense.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Reduced)
+    for K, mode in ((Kf, "full"), (Kr, "reduced")):
+        Kref = ref.matrix(d, 0.0, mode).toarray()
+        assert np.abs(np.asarray(K) - Kref).max() <= 5e-12 * np.abs(Kref).max(), mode
+    Rr = ref.vector(d, 0.0, "full")
+    assert np.abs(R - Rr).max() <= 5e-12 * np.abs(Rr).max()
+
+
 def test_eas_zero_parameters_is_plain_element():
     # testnonlineareas.cpp:145-189: eas(0) == displacement element; here E9 with alpha = 0 at d = 0 has the same R
     mesh, ref, dev, d, alpha, rng = _setup(3, 9, "neohooke", "gl")

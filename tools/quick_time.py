@@ -24,11 +24,12 @@ req = ik.FERequirements(d, 0.0)
 dev.bind(req, ik.elastoStatics, ik.DBCOption.Full)
 A = dev.matrix(); R = dev.vector()
 print(f"mesh {cells} {matk}: {mesh.n_elem} elements, {flags.shape[0]} dofs; mesh gen {t1-t0:.2f}s setup {t2-t1:.2f}s |R|={np.linalg.norm(R):.6e}")
-for ph in ("elements", "gather", "spmv", "dfma_peak"):
+for ph in ("elements", "gather", "spmv", "dfma_peak", "dmma_peak"):
     for _ in range(2):
-        ms = dev.timePhase(ph, ik.DBCOption.Full, 20 if ph != "dfma_peak" else 3)
-    if ph == "dfma_peak":
-        fl = 148 * 16 * 256 * 2048 * 16
+        ms = dev.timePhase(ph, ik.DBCOption.Full, 20 if not ph.endswith("_peak") else 3)
+    if ph.endswith("_peak"):
+        # dfma: 8 chains x 2048 FMAs per thread; dmma: 8 tiles x 2048 m8n8k4 (256 FMA) per warp
+        fl = 148 * 16 * 256 * 2048 * 16 if ph == "dfma_peak" else 148 * 16 * 8 * 2048 * 8 * 512
         print(f"{ph}: {ms:.4f} ms  -> {fl/ms/1e9:.2f} TFLOP/s FP64")
     else:
         print(f"{ph}: {ms:.4f} ms  -> {mesh.n_elem/ms/1e3:.1f} Melem/s")
