@@ -10,6 +10,7 @@
 #include "ikb_elem_h8mma.cuh"
 #include "ikb_elem_q1.cuh"
 #include "ikb_elem_q2.cuh"
+#include "ikb_fused.cuh"
 #include "ikb_gather.cuh"
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
@@ -144,11 +145,12 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
   return IKB_OK;
 }
 
-int ensureStaging(Handle* h) {
+// staging arrays of the two-kernel path, allocated for what is actually staged (the fused sweep needs Est only)
+int ensureStaging(Handle* h, unsigned what) {
   const size_t dd = (size_t)h->dim * h->dim;
-  if (!h->Kst.p) IKB_CUDA(h, h->Kst.alloc((size_t)h->nElem * h->npair * dd));
-  if (!h->Rst.p) IKB_CUDA(h, h->Rst.alloc((size_t)h->nElem * h->nd));
-  if (!h->Est.p) IKB_CUDA(h, h->Est.alloc((size_t)h->nElem));
+  if ((what & IKB_MATRIX) && !h->Kst.p) IKB_CUDA(h, h->Kst.alloc((size_t)h->nElem * h->npair * dd));
+  if ((what & IKB_VECTOR) && !h->Rst.p) IKB_CUDA(h, h->Rst.alloc((size_t)h->nElem * h->nd));
+  if ((what & IKB_SCALAR) && !h->Est.p) IKB_CUDA(h, h->Est.alloc((size_t)h->nElem));
   return IKB_OK;
 }
 
@@ -226,7 +228,7 @@ int ensureReduced(Handle* h) {
 int64_t rowsOf(Handle* h, int dbc) { return dbc == IKB_DBC_REDUCED ? h->nRed : h->nRowsLocal(); }
 int64_t nnzOf(Handle* h, int dbc) { return dbc == IKB_DBC_REDUCED ? h->nnzRed : h->nnzRaw(); }
 
-int launchGather(Handle* h, unsigned what, int dbc) {
+GatherArgs makeGatherArgs(Handle* h, unsigned what, int dbc) {
   GatherArgs G;
   G.P = h->view();
   G.adjPtr = h->adjPtr.p;
@@ -244,12 +246,252 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   // tile rows are padded to a stride == D (mod 16) doubles; Q2 kinds gather one scalar row per warp (GatherCfg)
   const int rs = h->nn > 8 ? 1 : h->dim;
   G.maxOut = rs * (h->dim * std::max(h->maxNbr, 1) + 16);
+  G.offTab = nullptr;
   G.freeCnt = h->freeCnt.p;
   G.freeTot = h->freeTot.p;
   G.redRowStart = h->redRowStart.p;
   G.cbelow = h->cbelow.p;
   G.redVecOffset = 0;
   G.pullStageMax = std::min(h->pullStageMax, PULL_CAP);
+  return G;
+}
+
+ElemArgs makeElemArgs(Handle* h, unsigned what) {
+  ElemArgs A;
+  A.X = h->X.p;
+  A.elemNode = h->elemNode.p;
+  A.U = h->U.p;
+  A.Kst = h->Kst.p;
+  A.Rst = h->Rst.p;
+  A.Est = h->Est.p;
+  A.errFlag = h->errFlag.p;
+  A.Lap = h->Lap.p;
+  A.nElem = h->nElem;
+  A.elemBegin = 0;
+  A.elemCount = h->nElem;
+  A.nNodes = h->nNodes;
+  A.layout = h->layout;
+  A.lambda = h->desc.lambda;
+  A.mu = h->desc.mu;
+  A.what = what;
+  A.planeStress = h->desc.plane_strain == IKB_REDUCE_PLANE_STRESS;
+  A.psTol = h->desc.reduce_tol > 0.0 ? h->desc.reduce_tol : 1e-12;
+  return A;
+}
+
+// One-time maps, ring and guards of the pipelined sweep (after the pattern build).  Leaves fusedOk false when the mesh or
+// element kind is outside what the sweep covers; the back-to-back two-kernel path serves those.
+int ensureFused(Handle* h) {
+  if (h->fusedTried) return IKB_OK;
+  h->fusedTried = true;
+  h->fusedOk = false;
+  if (!h->fusedEnabled || h->dim != 3 || h->nn != 8 || h->easM != 0 || h->form == FORM_SVK || !h->Lap.p) return IKB_OK;
+  if (!h->gatherPull || !h->cptr.p || !h->csrc.p || !h->adjPtr.p || h->nBlocks == 0 || h->nElem == 0) return IKB_OK;
+  const int64_t nRowNodes = h->rowEnd - h->rowBegin;
+  if (nRowNodes == 0) return IKB_OK;
+  const int tpb = 256;
+  int32_t nAdj = 0, nContrib = 0;
+  IKB_CUDA(h, cudaMemcpy(&nAdj, h->adjPtr.p + nRowNodes, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  IKB_CUDA(h, cudaMemcpy(&nContrib, h->cptr.p + h->nBlocks, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  h->nElemTickets = (unsigned)((h->nElem + 3) / 4);
+  h->nRowTickets = (unsigned)((nRowNodes + SWEEP_RB - 1) / SWEEP_RB);
+  h->nElemGroups = (h->nElemTickets + SWEEP_EG - 1) / SWEEP_EG;
+  h->nRowGroups = (h->nRowTickets + SWEEP_RG - 1) / SWEEP_RG;
+  // dependency data: per consumer ticket the producer-ticket range, per producer ticket its highest row
+  DevBuf<int32_t> dLo, dHi, dMaxRow;
+  IKB_CUDA(h, dLo.alloc(h->nRowTickets));
+  IKB_CUDA(h, dHi.alloc(h->nRowTickets));
+  IKB_CUDA(h, dMaxRow.alloc(h->nElemTickets));
+  sweep_row_range_kernel<<<gridFor(h->nRowTickets, tpb), tpb, 0, h->stream>>>(nRowNodes, h->adjPtr.p, h->adjCode.p, dLo.p, dHi.p);
+  IKB_LAUNCH_CHECK(h);
+  sweep_ticket_rows_kernel<<<gridFor(h->nElemTickets, tpb), tpb, 0, h->stream>>>(h->elemNode.p, h->nElem, h->rowBegin, h->rowEnd,
+                                                                               dMaxRow.p);
+  IKB_LAUNCH_CHECK(h);
+  std::vector<int32_t> rowLo(h->nRowTickets), rowHi(h->nRowTickets), maxRow(h->nElemTickets);
+  IKB_CUDA(h, cudaMemcpyAsync(rowLo.data(), dLo.p, dLo.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaMemcpyAsync(rowHi.data(), dHi.p, dHi.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaMemcpyAsync(maxRow.data(), dMaxRow.p, dMaxRow.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<uint32_t> wait((size_t)h->nRowTickets * 2);
+  for (size_t t = 0; t < rowLo.size(); ++t) {
+    if (rowHi[t] < 0) {
+      wait[2 * t] = 1;  // rows without elements: nothing to wait for
+      wait[2 * t + 1] = 0;
+    } else {
+      wait[2 * t] = (uint32_t)(rowLo[t] / SWEEP_EG);
+      wait[2 * t + 1] = (uint32_t)(rowHi[t] / SWEEP_EG);
+    }
+  }
+  // Ring size (a multiple of 4 elements = whole producer tickets): starts at the budget and grows until no producer
+  // ticket would have to wait for a consumer ticket that depends on one of the `margin` newest producer tickets --
+  // the tickets that can be in flight when every resident producer warp holds one, times two for uneven progress.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int64_t margin = h->sweepMargin >= 0 ? h->sweepMargin : 2 * (int64_t)sms * h->sweepElemCtas * H8Cfg::WARPS;
+  const int64_t elemsPadded = (h->nElem + 3) / 4 * 4;
+  int64_t ringElems = std::min<int64_t>(elemsPadded, std::max<int64_t>(8, (int64_t)(h->fusedRingMB * 1048576.0 / (348.0 * 8.0)) / 4 * 4));
+  std::vector<uint32_t> guard;
+  while (ringElems < elemsPadded &&
+         !sweepBuildGuards(h->nElemTickets, h->nRowTickets, rowHi, maxRow, ringElems, margin, guard))
+    ringElems = std::min<int64_t>(elemsPadded, (ringElems + ringElems / 4 + 3) / 4 * 4);
+  h->ringElems = ringElems;
+  h->fusedGuards = ringElems < elemsPadded;
+  IKB_CUDA(h, h->ring.alloc((size_t)ringElems * 36 * 9));
+  IKB_CUDA(h, h->rring.alloc((size_t)ringElems * 24));
+  if (h->fusedGuards) {
+    IKB_CUDA(h, h->sweepGuard.alloc(guard.size()));
+    IKB_CUDA(h, cudaMemcpy(h->sweepGuard.p, guard.data(), h->sweepGuard.bytes(), cudaMemcpyHostToDevice));
+  }
+  IKB_CUDA(h, h->sweepRowWait.alloc(wait.size()));
+  IKB_CUDA(h, cudaMemcpy(h->sweepRowWait.p, wait.data(), h->sweepRowWait.bytes(), cudaMemcpyHostToDevice));
+  IKB_CUDA(h, h->csrcRing.alloc((size_t)std::max(nContrib, 1)));
+  IKB_CUDA(h, h->adjRing.alloc((size_t)std::max(nAdj, 1)));
+  sweep_ring_codes_kernel<<<gridFor(nContrib, tpb), tpb, 0, h->stream>>>(h->csrc.p, nContrib, h->npair, (uint32_t)ringElems,
+                                                                        h->csrcRing.p);
+  IKB_LAUNCH_CHECK(h);
+  sweep_ring_adj_kernel<<<gridFor(nAdj, tpb), tpb, 0, h->stream>>>(h->adjCode.p, nAdj, (uint32_t)ringElems, h->adjRing.p);
+  IKB_LAUNCH_CHECK(h);
+  IKB_CUDA(h, h->sweepDone.alloc((size_t)(h->nElemGroups + h->nRowGroups)));
+  IKB_CUDA(h, cudaMemsetAsync(h->sweepDone.p, 0, h->sweepDone.bytes(), h->stream));
+  IKB_CUDA(h, h->sweepCtl.alloc(8));
+  IKB_CUDA(h, cudaMemsetAsync(h->sweepCtl.p, 0, h->sweepCtl.bytes(), h->stream));
+  h->fusedEpoch = 0;
+  h->elemTicketBase = h->rowTicketBase = 0;
+  if (!h->stream3) {
+    int prioLo = 0, prioHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);
+    IKB_CUDA(h, cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prioLo));
+    IKB_CUDA(h, cudaEventCreateWithFlags(&h->evSweepFork, cudaEventDisableTiming));
+    IKB_CUDA(h, cudaEventCreateWithFlags(&h->evSweepJoin, cudaEventDisableTiming));
+  }
+  // Load both kernels NOW: with lazy module loading the first launch of a kernel synchronises with running work, and a
+  // consumer kernel that cannot start until the producer has left would leave the producer waiting for it forever.
+  {
+    cudaFuncAttributes fa;
+    cudaError_t le = cudaSuccess;
+    auto touch = [&](const void* f) {
+      if (le == cudaSuccess) le = cudaFuncGetAttributes(&fa, f);
+    };
+    touch((const void*)sweep_elem_kernel<FORM_LE>);
+    touch((const void*)sweep_elem_kernel<FORM_NH>);
+#define IKB_TOUCH_ROWS(MODE)                                         \
+  touch((const void*)sweep_rows_kernel<MODE, true, 16>);             \
+  touch((const void*)sweep_rows_kernel<MODE, false, 16>);            \
+  touch((const void*)sweep_rows_kernel<MODE, true, 12>);             \
+  touch((const void*)sweep_rows_kernel<MODE, false, 12>);
+    IKB_TOUCH_ROWS(IKB_DBC_RAW)
+    IKB_TOUCH_ROWS(IKB_DBC_FULL)
+    IKB_TOUCH_ROWS(IKB_DBC_REDUCED)
+#undef IKB_TOUCH_ROWS
+    if (le != cudaSuccess) return fail(h, IKB_ECUDA, std::string("pipelined sweep: ") + cudaGetErrorString(le));
+  }
+  h->sweepElemGrid = sms * h->sweepElemCtas;
+  h->sweepRowGrid = sms * h->sweepRowCtas;
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->fusedOk = true;
+  return IKB_OK;
+}
+
+// K, R and E of the current state: producer and consumer kernel side by side (Hex8 pipelined sweep)
+int launchFused(Handle* h, unsigned what, int dbc) {
+  SweepArgs S;
+  S.E = makeElemArgs(h, what);
+  S.O.Kst = h->ring.p;
+  S.O.Rst = h->rring.p;
+  S.O.ringElems = h->ringElems;
+  S.guard = h->fusedGuards ? h->sweepGuard.p : nullptr;
+  S.G = makeGatherArgs(h, what, dbc);
+  S.G.Kst = h->ring.p;
+  S.G.Rst = h->rring.p;
+  S.cptr = h->cptr.p;
+  S.csrcRing = h->csrcRing.p;
+  S.adjRing = h->adjRing.p;
+  S.rowWait = reinterpret_cast<const uint2*>(h->sweepRowWait.p);
+  S.ctl = reinterpret_cast<SweepCtl*>(h->sweepCtl.p);
+  S.elemDone = h->sweepDone.p;
+  S.rowDone = h->sweepDone.p + h->nElemGroups;
+  S.nElemTickets = h->nElemTickets;
+  S.nRowTickets = h->nRowTickets;
+  S.elemTicketBase = h->elemTicketBase;
+  S.rowTicketBase = h->rowTicketBase;
+  S.epoch = h->fusedEpoch;
+  S.what = what;
+  S.timing = h->sweepDebug ? 1 : 0;
+  if (h->sweepDebug) {
+    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    cudaMemcpyAsync(h->sweepCtl.p + 4, init, sizeof(init), cudaMemcpyHostToDevice, h->stream);
+  }
+  joinSolution(h);
+  // fork: the consumer kernel on its own stream, behind everything queued on the main stream so far
+  cudaEventRecord(h->evSweepFork, h->stream);
+  cudaStreamWaitEvent(h->stream3, h->evSweepFork, 0);
+  // Both kernels ask for the largest shared-memory carve-out: an SM only changes its carve-out when it is idle, so a
+  // consumer CTA whose shared memory did not fit next to the producer's configuration would wait for the producer to
+  // leave the SM -- and the producer may be waiting for the consumer.
+  const void* ek = h->form == FORM_LE ? (const void*)sweep_elem_kernel<FORM_LE> : (const void*)sweep_elem_kernel<FORM_NH>;
+  cudaError_t e = cudaFuncSetAttribute(ek, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8Cfg::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ek, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) {
+    if (h->form == FORM_LE)
+      sweep_elem_kernel<FORM_LE><<<h->sweepElemGrid, 32 * H8Cfg::WARPS, H8Cfg::SMEM, h->stream>>>(S);
+    else
+      sweep_elem_kernel<FORM_NH><<<h->sweepElemGrid, 32 * H8Cfg::WARPS, H8Cfg::SMEM, h->stream>>>(S);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && (what & (IKB_MATRIX | IKB_VECTOR))) {
+    const int tpbR = 32 * PULL_WARPS_MAX;
+#define IKB_SWEEP_ROWS2(MODE, IL)                                                               \
+  if (h->sweepRowCtas > 6) {                                                                    \
+    cudaFuncSetAttribute(sweep_rows_kernel<MODE, IL, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                         cudaSharedmemCarveoutMaxShared);                                       \
+    sweep_rows_kernel<MODE, IL, 16><<<h->sweepRowGrid, tpbR, 0, h->stream3>>>(S);              \
+  } else {                                                                                      \
+    cudaFuncSetAttribute(sweep_rows_kernel<MODE, IL, 12>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                         cudaSharedmemCarveoutMaxShared);                                       \
+    sweep_rows_kernel<MODE, IL, 12><<<h->sweepRowGrid, tpbR, 0, h->stream3>>>(S);              \
+  }
+#define IKB_SWEEP_ROWS(MODE)                                                                    \
+  if (h->layout == LAYOUT_INTERLEAVED) {                                                        \
+    IKB_SWEEP_ROWS2(MODE, true)                                                                 \
+  } else {                                                                                      \
+    IKB_SWEEP_ROWS2(MODE, false)                                                                \
+  }
+    if (dbc == IKB_DBC_RAW) {
+      IKB_SWEEP_ROWS(IKB_DBC_RAW)
+    } else if (dbc == IKB_DBC_FULL) {
+      IKB_SWEEP_ROWS(IKB_DBC_FULL)
+    } else {
+      IKB_SWEEP_ROWS(IKB_DBC_REDUCED)
+    }
+#undef IKB_SWEEP_ROWS2
+#undef IKB_SWEEP_ROWS
+    e = cudaGetLastError();
+    h->launches++;
+    h->rowTicketBase += (unsigned long long)h->nRowTickets + (unsigned long long)h->sweepRowGrid * PULL_WARPS_MAX;
+  }
+  // join
+  cudaEventRecord(h->evSweepJoin, h->stream3);
+  cudaStreamWaitEvent(h->stream, h->evSweepJoin, 0);
+  if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("pipelined sweep: ") + cudaGetErrorString(e));
+  h->launches++;
+  h->elemTicketBase += (unsigned long long)h->nElemTickets + (unsigned long long)h->sweepElemGrid * H8Cfg::WARPS;
+  h->fusedEpoch++;
+  markSolutionUse(h);
+  if (what & IKB_VECTOR) cudaEventRecord(h->evVec, h->stream);
+  if (h->sweepDebug) {
+    unsigned long long t[4];
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(t, h->sweepCtl.p + 4, sizeof(t), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[ikb sweep] producer %.1f us, consumer %.1f us, consumer starts %.1f us after producer, total %.1f us\n",
+                 (t[1] - t[0]) * 1e-3, (t[3] - t[2]) * 1e-3, ((double)t[2] - (double)t[0]) * 1e-3,
+                 (std::max(t[1], t[3]) - std::min(t[0], t[2])) * 1e-3);
+  }
+  return IKB_OK;
+}
+
+int launchGather(Handle* h, unsigned what, int dbc) {
+  GatherArgs G = makeGatherArgs(h, what, dbc);
+  const int rs = h->nn > 8 ? 1 : h->dim;
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
   if (!h->gatherTab.p) {
@@ -341,6 +583,41 @@ int checkMaterialError(Handle* h) {
   if (flag != INT_MAX) {
     const int32_t reset = INT_MAX;
     cudaMemcpyAsync(h->errFlag.p, &reset, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    if (flag == -2) {
+      if (std::getenv("IKB_SWEEP_DEBUG") && h->sweepDone.p) {
+        // where the two kernels stood when a wait gave up
+        cudaStreamSynchronize(h->stream);
+        std::vector<unsigned> done((size_t)(h->nElemGroups + h->nRowGroups));
+        unsigned long long ctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpy(done.data(), h->sweepDone.p, done.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        cudaMemcpy(ctl, h->sweepCtl.p, sizeof(ctl), cudaMemcpyDeviceToHost);
+        int64_t fe = -1, fr = -1;
+        for (int64_t k = 0; k < h->nElemGroups && fe < 0; ++k) {
+          const unsigned sz = (unsigned)std::min<int64_t>(SWEEP_EG, h->nElemTickets - k * SWEEP_EG);
+          if (done[(size_t)k] != h->fusedEpoch * sz) fe = k;
+        }
+        for (int64_t k = 0; k < h->nRowGroups && fr < 0; ++k) {
+          const unsigned sz = (unsigned)std::min<int64_t>(SWEEP_RG, h->nRowTickets - k * SWEEP_RG);
+          if (done[(size_t)(h->nElemGroups + k)] != h->fusedEpoch * sz) fr = k;
+        }
+        std::fprintf(stderr,
+                     "[ikb sweep] epoch %u ring %lld elems (guards %d) tickets e %u r %u | claimed e %llu (base %llu) r %llu (base %llu) "
+                     "watermark %llx | first incomplete producer group %lld of %lld (count %u), consumer group %lld of %lld (count %u)\n",
+                     h->fusedEpoch, (long long)h->ringElems, (int)h->fusedGuards, h->nElemTickets, h->nRowTickets, ctl[0],
+                     h->elemTicketBase, ctl[1], h->rowTicketBase, ctl[2], (long long)fe, (long long)h->nElemGroups,
+                     fe >= 0 ? done[(size_t)fe] : 0u, (long long)fr, (long long)h->nRowGroups,
+                     fr >= 0 ? done[(size_t)(h->nElemGroups + fr)] : 0u);
+      }
+      // a dependency wait of the fused sweep ran into its spin limit (should not happen): results are invalid; start
+      // the counters afresh and serve this handle by the two-kernel path from now on
+      if (h->sweepDone.p) cudaMemsetAsync(h->sweepDone.p, 0, h->sweepDone.bytes(), h->stream);
+      if (h->sweepCtl.p) cudaMemsetAsync(h->sweepCtl.p, 0, h->sweepCtl.bytes(), h->stream);
+      h->fusedEpoch = 0;
+      h->elemTicketBase = h->rowTicketBase = 0;
+      h->fusedOk = false;
+      h->stateVersion++;
+      return fail(h, IKB_ECUDA, "fused sweep: dependency wait timed out");
+    }
     // the reference aborts here (materials/materialhelpers.hh:120-126)
     return fail(h, IKB_EMATERIAL,
                 "Determinant of right Cauchy Green tensor C must be greater than zero (first failing element " +
@@ -573,6 +850,17 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   if (const char* gm = std::getenv("IKB_GATHER")) h->gatherPull = std::string(gm) != "tile";
   if (const char* em = std::getenv("IKB_ELEM")) h->elemMma = std::string(em) != "fma";
   if (const char* mb = std::getenv("IKB_H8_MINB")) h->h8MinBlocks = std::atoi(mb);
+  if (const char* fu = std::getenv("IKB_FUSED")) h->fusedEnabled = std::atoi(fu) != 0;
+  h->sweepDebug = std::getenv("IKB_SWEEP_DEBUG") != nullptr;
+  if (const char* sm = std::getenv("IKB_SWEEP_MARGIN")) h->sweepMargin = std::atoi(sm);  // test hook: 0 = smallest legal ring
+  if (const char* sc = std::getenv("IKB_SWEEP_CTAS")) {
+    int a = 0, b = 0;
+    if (std::sscanf(sc, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1) {
+      h->sweepElemCtas = a;
+      h->sweepRowCtas = b;
+    }
+  }
+  if (const char* rm = std::getenv("IKB_RING_MB")) h->fusedRingMB = std::max(0.01, std::atof(rm));
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
@@ -634,6 +922,18 @@ int ikb_destroy(ikb_handle hh) {
   if (h->comm) nccl().commDestroy(h->comm);
   h->cgPglob.release();
   h->cgState.release();
+  h->ring.release();
+  h->rring.release();
+  h->csrcRing.release();
+  h->adjRing.release();
+  h->sweepGuard.release();
+  h->sweepRowWait.release();
+  h->sweepCtl.release();
+  h->sweepDone.release();
+  if (h->stream3) cudaStreamDestroy(h->stream3);
+  if (h->evSweepFork) cudaEventDestroy(h->evSweepFork);
+  if (h->evSweepJoin) cudaEventDestroy(h->evSweepJoin);
+  h->gatherTab.release();
   if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
   h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
@@ -735,6 +1035,7 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->meshUploaded = true;
   h->patternBuilt = false;
   h->reducedBuilt = false;
+  h->fusedTried = h->fusedOk = false;
   h->stateVersion++;
   h->Lap.release();
   if (h->order == 1 && h->easM == 0 && h->form != FORM_SVK) {
@@ -980,6 +1281,7 @@ int ikb_build_pattern(ikb_handle hh) {
   tmp.release();
   h->patternBuilt = true;
   h->reducedBuilt = false;
+  h->fusedTried = h->fusedOk = false;
   for (int i = 0; i < 3; ++i) {
     h->vals[i].release();
     h->vec[i].release();
@@ -1171,8 +1473,8 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
                 "EAS element do not support any scalar calculations, i.e. they are not derivable from a potential");
   int rc;
   if ((rc = ensureSolution(h))) return rc;
-  if ((rc = ensureStaging(h))) return rc;
   if (dbc == IKB_DBC_REDUCED && (rc = ensureReduced(h))) return rc;
+  if ((rc = ensureFused(h))) return rc;
 
   // which outputs are stale for the current (d, lambda, alpha)?
   unsigned needGather = 0;
@@ -1180,8 +1482,28 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
   if ((what & IKB_VECTOR) && h->vecVersion[dbc] != h->stateVersion) needGather |= IKB_VECTOR;
   const bool needEnergy = (what & IKB_SCALAR) && h->energyVersion != h->stateVersion;
   unsigned needStage = needGather | (needEnergy ? IKB_SCALAR : 0);
+  if (h->fusedOk && needGather) {
+    // Hex8 fused sweep: elements and row assembly in one launch, nothing staged in HBM (ikb_fused.cuh)
+    const bool stagedE = h->stagedVersion == h->stateVersion && (h->stagedWhat & IKB_SCALAR);
+    const unsigned fw = needGather | ((needEnergy && !stagedE) ? IKB_SCALAR : 0);
+    if ((rc = ensureStaging(h, fw & IKB_SCALAR))) return rc;
+    if ((needGather & IKB_MATRIX) && !h->vals[dbc].p)
+      IKB_CUDA(h, h->vals[dbc].alloc((size_t)std::max<int64_t>(nnzOf(h, dbc), 1)));
+    if ((needGather & IKB_VECTOR) && !h->vec[dbc].p)
+      IKB_CUDA(h, h->vec[dbc].alloc((size_t)std::max<int64_t>(rowsOf(h, dbc), 1)));
+    if ((rc = launchFused(h, fw, dbc))) return rc;
+    if (needGather & IKB_MATRIX) h->valsVersion[dbc] = h->stateVersion;
+    if (needGather & IKB_VECTOR) h->vecVersion[dbc] = h->stateVersion;
+    if (fw & IKB_SCALAR) {
+      h->stagedWhat = (h->stagedVersion == h->stateVersion ? h->stagedWhat : 0) | IKB_SCALAR;
+      h->stagedVersion = h->stateVersion;
+    }
+    needGather = 0;
+    needStage = 0;
+  }
   if (h->stagedVersion == h->stateVersion) needStage &= ~h->stagedWhat;
   if (needStage) {
+    if ((rc = ensureStaging(h, needStage))) return rc;
     const unsigned stageWhat = needStage;
     if ((rc = launchElements(h, stageWhat))) return rc;
     h->stagedWhat = (h->stagedVersion == h->stateVersion ? h->stagedWhat : 0) | stageWhat;
@@ -1330,7 +1652,7 @@ int ikb_eas_update(ikb_handle hh, const double* correction) {
   if (!h->meshUploaded) return fail(h, IKB_ESTATE, "mesh missing");
   int rc;
   if ((rc = ensureSolution(h))) return rc;
-  if ((rc = ensureStaging(h))) return rc;
+  if ((rc = ensureStaging(h, 0))) return rc;  // update mode stages nothing
   if (h->Corr.n < (size_t)h->nDof) {
     if (!correction) return fail(h, IKB_ESTATE, "no resident correction");
     IKB_CUDA(h, h->Corr.alloc((size_t)h->nDof));
@@ -1370,7 +1692,7 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
     // linear strains: alpha = -D^-1 L d recomputed from the current d (enhancedassumedstrains.hh:152-157).  The
     // update kernel evaluates alpha - D^-1 (Rt + L du) at the state it is given; at (d = 0, alpha = 0) Rt vanishes,
     // so du = d yields exactly -D^-1 L d (D, L do not depend on the state for the linear element).
-    if ((rc = ensureStaging(h))) return rc;
+    if ((rc = ensureStaging(h, 0))) return rc;  // update mode stages nothing
     IKB_CUDA(h, aTmp.alloc((size_t)h->nElem * h->easM));
     IKB_CUDA(h, uZero.alloc((size_t)h->nDof));
     IKB_CUDA(h, cudaMemsetAsync(aTmp.p, 0, aTmp.bytes(), h->stream));
@@ -1912,8 +2234,11 @@ int ikb_time_phase(ikb_handle hh, const char* phase, int dbc, int reps, float* m
   int rc = IKB_OK;
   DevBuf<double> tmp;
   if (p == "dfma_peak" || p == "dmma_peak") IKB_CUDA(h, tmp.alloc((size_t)148 * 16 * 256));
-  if (p == "elements" || p == "gather") {
+  if (p == "elements" || p == "gather" || p == "fused") {
     if ((rc = ikb_assemble(hh, IKB_MATRIX | IKB_VECTOR, dbc))) return rc;
+    if (p == "fused" && !h->fusedOk) return fail(h, IKB_ESTATE, "the fused sweep does not serve this handle");
+    if (p != "fused" && (rc = ensureStaging(h, IKB_MATRIX | IKB_VECTOR))) return rc;
+    if (p == "gather" && h->fusedOk && (rc = launchElements(h, IKB_MATRIX | IKB_VECTOR))) return rc;
   } else if (p == "spmv") {
     if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "assemble first");
     const int64_t n = std::max(rowsOf(h, dbc), h->nDof);
@@ -1928,6 +2253,8 @@ int ikb_time_phase(ikb_handle hh, const char* phase, int dbc, int reps, float* m
       rc = launchElements(h, IKB_MATRIX | IKB_VECTOR);
     else if (p == "gather")
       rc = launchGather(h, IKB_MATRIX | IKB_VECTOR, dbc);
+    else if (p == "fused")
+      rc = launchFused(h, IKB_MATRIX | IKB_VECTOR, dbc);
     else if (p == "spmv")
       rc = launchSpmv(h, dbc, h->cgP.p, h->cgQ.p);
     else if (p == "dfma_peak") {

@@ -33,16 +33,28 @@ struct H8Cfg {
   static constexpr int GPS = 28;                // doubles per Gauss-point record: V (24), c1, c2, 2 pad
   static constexpr int HS = 4 * GPS + 2;        // stride between the two Gauss-point halves (== 2 mod 16)
   static constexpr int ES = 2 * HS + 1;         // element stride (odd): phase-1 stores and phase-2 loads conflict-free
-  static constexpr int KBUF = 36 * 9;           // packed K_e for the coalesced write-out
-  static constexpr int WARP_DOUBLES = 4 * ES + KBUF + (4 * ES + KBUF) % 2;
+  static constexpr int REC = 4 * ES + (4 * ES) % 2;  // records of the warp's four elements (kept 16-byte aligned)
+  // packed K_e for the coalesced write-out: rows k = 0..4 of the pair table (p = k*8 + a), row stride 74 doubles
+  // instead of 72 so that the 8-byte stores of a half-warp (lanes (a,q): k = (2q+r-a)&7) hit 16 distinct banks
+  static constexpr int KROW = 74;
+  static constexpr int KBUF = 4 * KROW + 36;
+  static constexpr int WARP_DOUBLES = REC + KBUF;
   static constexpr int WARPS = 4;               // warps per CTA (no block-level synchronisation anywhere)
   static constexpr size_t SMEM = (size_t)WARPS * WARP_DOUBLES * 8;
 };
 
+// Where the element results go: symmetric-packed K_e (36 blocks) and R_e of element e at slot e of the staging arrays,
+// or at slot e mod ringElems when the staging arrays are a ring (pipelined sweep, ikb_fused.cuh).
+struct H8Out {
+  double* Kst = nullptr;
+  double* Rst = nullptr;
+  int64_t ringElems = 0;  // 0: one slot per element
+};
+
 // One warp, four elements e0..e0+3 (those >= elemCount are skipped).  wsm: WARP_DOUBLES doubles of shared memory
-// private to the warp.  Kdst(e) -> where the packed K_e of element e goes (the staging array, or a ring slot).
-template <int FORM, typename KDst>
-__device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, int64_t e0, double* wsm, KDst Kdst) {
+// private to the warp.
+template <int FORM>
+__device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, const H8Out& O, int64_t e0, double* wsm) {
   constexpr int D = 3, N = 8;
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -255,8 +267,9 @@ __device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, int64_t e0, 
         s3[i] = keep + __shfl_xor_sync(FULL, send, 1);
       }
       if (active) {
+        const int64_t slot = O.ringElems ? e % O.ringElems : e;
 #pragma unroll
-        for (int i = 0; i < D; ++i) A.Rst[(size_t)e * (N * D) + t * D + i] = s3[i];
+        for (int i = 0; i < D; ++i) O.Rst[(size_t)slot * (N * D) + t * D + i] = s3[i];
       }
     }
   }
@@ -265,7 +278,7 @@ __device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, int64_t e0, 
 
   // ------------------------------------------------------------------ phase 2: one element at a time on the tensor cores
   const int a = lane >> 2, q = lane & 3;
-  double* kbuf = wsm + 4 * H8Cfg::ES;
+  double* kbuf = wsm + H8Cfg::REC;
 #pragma unroll 1
   for (int j = 0; j < 4; ++j) {
     const int64_t ej = e0 + j;
@@ -296,32 +309,40 @@ __device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, int64_t e0, 
           dmma884(acc[i][jj][0], acc[i][jj][1], v[i][h], vb1[jj][h]);
           dmma884(acc[i][jj][0], acc[i][jj][1], v[jj][h], vb2[i][h]);
         }
-    // lane (a,q) now holds the blocks (a, 2q) and (a, 2q+1); the packed K_e keeps pair p = k*8 + a' for block
-    // (a', (a'+k) mod 8), k <= 4 (k == 4: a' < 4 only)
+    // lane (a,q) now holds the blocks (a, 2q) and (a, 2q+1)
     __syncwarp();  // kbuf of the previous element has been copied out
+    {
+      // the packed K_e keeps pair p = k*8 + a' for block (a', (a'+k) mod 8), k <= 4 (k == 4: a' < 4 only)
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int b = 2 * q + r;
-      const int k = (b - a) & 7;
-      if (k < 4 || (k == 4 && a < 4)) {
-        const double lap = A.mu * __ldg(A.Lap + (size_t)(k * N + a) * A.nElem + ej);
-        double* dst = kbuf + (k * N + a) * 9;
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * q + r;
+        const int k = (b - a) & 7;
+        if (k < 4 || (k == 4 && a < 4)) {
+          const double lap = A.mu * __ldg(A.Lap + (size_t)(k * N + a) * A.nElem + ej);
+          double* dst = kbuf + k * H8Cfg::KROW + a * 9;
 #pragma unroll
-        for (int i = 0; i < D; ++i)
+          for (int i = 0; i < D; ++i)
 #pragma unroll
-          for (int jj = 0; jj < D; ++jj) {
-            // diagonal block: mirror the upper triangle so K_e is exactly symmetric
-            double x = (k == 0 && i > jj) ? acc[jj][i][r] : acc[i][jj][r];
-            if (i == jj) x += lap;
-            dst[i * D + jj] = x;
-          }
+            for (int jj = 0; jj < D; ++jj) {
+              // diagonal block: mirror the upper triangle so K_e is exactly symmetric
+              double x = (k == 0 && i > jj) ? acc[jj][i][r] : acc[i][jj][r];
+              if (i == jj) x += lap;
+              dst[i * D + jj] = x;
+            }
+        }
+      }
+      __syncwarp();
+      const double2* src2 = reinterpret_cast<const double2*>(kbuf);
+      double2* dst2 = reinterpret_cast<double2*>(O.Kst + (size_t)(O.ringElems ? ej % O.ringElems : ej) * 36 * 9);
+#pragma unroll
+      for (int it = 0; it < 6; ++it) {
+        const int idx2 = lane + 32 * it;  // 162 double2: rows k < 4 hold 36, row 4 holds 18
+        if (idx2 < 162) {
+          const int k = idx2 / 36;
+          dst2[idx2] = src2[idx2 + k];  // row stride 37 double2 in kbuf
+        }
       }
     }
-    __syncwarp();
-    const double2* src2 = reinterpret_cast<const double2*>(kbuf);
-    double2* dst2 = reinterpret_cast<double2*>(Kdst(ej));
-#pragma unroll
-    for (int idx = lane; idx < H8Cfg::KBUF / 2; idx += 32) dst2[idx] = src2[idx];
   }
 }
 
@@ -332,8 +353,10 @@ __global__ void __launch_bounds__(32 * H8Cfg::WARPS, MINB) elem_h8_mma_kernel(El
   double* wsm = smem + (size_t)warp * H8Cfg::WARP_DOUBLES;
   const int64_t e0 = ((int64_t)blockIdx.x * H8Cfg::WARPS + warp) * 4;
   if (e0 >= A.elemCount) return;
-  double* Kst = A.Kst;
-  h8_warp_elements<FORM>(A, e0, wsm, [Kst](int64_t e) { return Kst + (size_t)e * 36 * 9; });
+  H8Out O;
+  O.Kst = A.Kst;
+  O.Rst = A.Rst;
+  h8_warp_elements<FORM>(A, O, e0, wsm);
 }
 
 // minBlocks = resident CTAs per SM the register allocation is held to: 4 -> 128 registers, 5 -> 96, 6 -> 80 (spills)

@@ -220,30 +220,31 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs G) {
 constexpr int PULL_CAP = 256;  // staged codes per warp
 constexpr int PULL_WARPS_MAX = 4;  // warps per CTA (sizes the staging buffer: 4 KB per CTA, 64 KB per SM at 16 CTAs)
 
+// staged values: read-only for the lifetime of the gather kernel -> non-coherent path; inside the pipelined sweep the
+// staging ring is rewritten while the kernel runs -> L2 (ld.global.cg), the coherence point with the producing kernel
+template <bool RING>
 __device__ __forceinline__ double pullLoad(uint64_t a) {
   double v;
-  asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
+  if (RING)
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(a) : "memory");
+  else
+    asm("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
   return v;
 }
 __device__ __forceinline__ void pullStore(uint64_t a, double v) {
   asm volatile("st.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
 }
 
-// 32 registers per thread (16 CTAs of 4 warps per SM): the kernel is latency bound, 64 resident warps per SM measured
-// 13 % faster than the 48 warps the unconstrained 40-register build reaches; 4 warps per CTA 2 % faster than 8.
-template <int D, int DBC, bool INTERLEAVED, bool IDX32>
-__global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
-                                                          const uint32_t* __restrict__ csrc) {
+// one node-row of the pull gather; sm: PULL_CAP words of shared memory private to the warp
+template <int D, int DBC, bool INTERLEAVED, bool IDX32, bool RING>
+__device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __restrict__ cptr,
+                                        const uint32_t* __restrict__ csrc, int64_t g, uint32_t* sm, int lane) {
   constexpr int DD = D * D;
   constexpr int BPW = 32 / DD;               // pattern blocks per warp pass
   constexpr int CH = (31 / BPW) * BPW;       // blocks per chunk (their cptr values + 1 fit one warp load)
   constexpr int LAYOUT = INTERLEAVED ? LAYOUT_INTERLEAVED : LAYOUT_LEXICOGRAPHIC;
   constexpr unsigned FULLMASK = 0xffffffffu;
-  __shared__ uint32_t codeBuf[PULL_WARPS_MAX][PULL_CAP];
   const PatternView& P = G.P;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (g >= P.nRowNodes) return;
   const int q = lane / DD, v = lane - q * DD, i = v / D, k = v - i * D;
   const bool active = q < BPW;
   const int32_t b0 = P.nbrPtr[g], b1 = P.nbrPtr[g + 1];
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(Ga
       asm("{\n\t.reg .b32 t, x;\n\tand.b32 t, %1, 1;\n\tmad.lo.s32 x, t, %2, %1;\n\tmad.wide.s32 %0, x, 4, %3;\n\t}"
           : "=l"(a)
           : "r"(w), "r"(delta), "l"(laneBase));
-      return pullLoad(a);
+      return pullLoad<RING>(a);
     }
     // 64-bit offsets (staged codes are 2*(e*npair+p) + transposed here): laneBase + w*4*DD + t*(4*(delta+1) - 4*DD)
     uint64_t a;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(Ga
         "mad.wide.u32 %0, %1, %3, %4;\n\tadd.s64 %0, %0, o;\n\t}"
         : "=l"(a)
         : "r"(w), "r"(4 * (delta + 1) - 4 * DD), "n"(4 * DD), "l"(laneBase));
-    return pullLoad(a);
+    return pullLoad<RING>(a);
   };
   uint64_t dst = reinterpret_cast<uint64_t>(
       (DBC == IKB_DBC_REDUCED) ? G.vals
@@ -285,7 +286,6 @@ __global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(Ga
   constexpr int SSTRIDE = INTERLEAVED ? D : 1;  // doubles between the entries (i,k) of consecutive slots
   int64_t redStart = 0;
   if (DBC == IKB_DBC_REDUCED) redStart = G.redRowStart[localRowOf(P, g, i)];
-  uint32_t* sm = codeBuf[warp];
 
   for (int32_t cb = b0; cb < b1; cb += CH) {
     const int nb = min(CH, b1 - cb);
@@ -405,6 +405,18 @@ __global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(Ga
       }
     }
   }
+}
+
+// 32 registers per thread (16 CTAs of 4 warps per SM): the kernel is latency bound, 64 resident warps per SM measured
+// 13 % faster than the 48 warps the unconstrained 40-register build reaches; 4 warps per CTA 2 % faster than 8.
+template <int D, int DBC, bool INTERLEAVED, bool IDX32>
+__global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
+                                                          const uint32_t* __restrict__ csrc) {
+  __shared__ uint32_t codeBuf[PULL_WARPS_MAX][PULL_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= G.P.nRowNodes) return;
+  pullRow<D, DBC, INTERLEAVED, IDX32, false>(G, cptr, csrc, g, codeBuf[warp], lane);
 }
 
 // Residual gather: one thread per (node-row, component).  The node's (element, local node) adjacency is walked in

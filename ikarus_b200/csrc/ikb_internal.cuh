@@ -120,7 +120,7 @@ struct Handle {
   int pullWarps = 4;            // warps per CTA of the pull gather (IKB_PULL_WARPS, tuning; 4 measured 2 % faster than 8)
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
   bool elemMma = true;          // Hex8 NeoHooke/LinearElastic: tangent contraction by DMMA (IKB_ELEM=fma: FMA kernel)
-  int h8MinBlocks = 5;          // register budget of the DMMA kernel as resident CTAs per SM (IKB_H8_MINB, tuning)
+  int h8MinBlocks = 4;          // register budget of the DMMA kernel as resident CTAs per SM (IKB_H8_MINB, tuning)
   bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)
   // reduced-mode structures
   bool reducedBuilt = false;
@@ -144,6 +144,27 @@ struct Handle {
   DevBuf<double> scratch;      // reductions
   int spmvBlocks = 888;        // grid of the SpMV inside PCG: 6 resident blocks x 148 SMs (IKB_SPMV_BLOCKS overrides, for tuning)
   DevBuf<int32_t> errFlag;     // first failing element (material abort), INT_MAX if none
+
+  // pipelined sweep (ikb_fused.cuh): Hex8, NeoHooke / LinearElastic
+  bool fusedEnabled = false;    // IKB_FUSED=1 selects the pipelined sweep (measured slower than back-to-back)
+  bool fusedTried = false, fusedOk = false;
+  double fusedRingMB = 32.0;    // ring budget (IKB_RING_MB); grown until no producer ticket has to wait, cut to the mesh
+  int64_t ringElems = 0;
+  unsigned nElemTickets = 0, nRowTickets = 0, fusedEpoch = 0;
+  unsigned long long elemTicketBase = 0, rowTicketBase = 0;
+  int sweepElemGrid = 0, sweepRowGrid = 0;
+  int sweepElemCtas = 2, sweepRowCtas = 8;  // resident CTAs per SM of the two persistent kernels (IKB_SWEEP_CTAS=e,r)
+  int sweepMargin = -1;         // IKB_SWEEP_MARGIN (test hook): producer tickets assumed in flight when sizing the ring
+  bool sweepDebug = false;      // IKB_SWEEP_DEBUG: kernel start/end stamps and a state dump when a wait gives up
+  bool fusedGuards = false;     // the ring is smaller than the mesh: producer tickets carry write-after-read guards
+  DevBuf<double> ring, rring;   // [ringElems][36*9], [ringElems][24]
+  DevBuf<uint32_t> csrcRing, adjRing, sweepGuard;
+  DevBuf<uint32_t> sweepRowWait;  // uint2 per consumer ticket
+  DevBuf<unsigned long long> sweepCtl;
+  DevBuf<unsigned> sweepDone;   // producer groups, then consumer groups
+  int64_t nElemGroups = 0, nRowGroups = 0;
+  cudaStream_t stream3 = nullptr;  // the consumer kernel runs beside the producer
+  cudaEvent_t evSweepFork = nullptr, evSweepJoin = nullptr;
 
   // EAS
   DevBuf<double> alpha;        // [nElem][m]

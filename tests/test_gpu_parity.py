@@ -365,3 +365,48 @@ def test_gather_variants_bit_identical(case, layout, monkeypatch):
         for m, a in zip(modes, base):
             b = other.matrix(req, ik.MatrixAffordance.stiffness, m).data
             assert np.array_equal(a, b), (env, m)
+    # Pipelined sweep (IKB_FUSED=1; serves Hex8 NeoHooke/LinearElastic, other kinds fall through to the same path as
+    # above): producer and consumer kernel side by side, K_e through a ring.  Same staged values added in the same order
+    # => the same bits, also with a tiny ring (wrap-around with write-after-read guards) and over repeated sweeps
+    # (one epoch of the completion counters per launch).
+    for ring in (None, "0.01"):
+        with monkeypatch.context() as mp:
+            mp.setenv("IKB_FUSED", "1")
+            if ring:
+                mp.setenv("IKB_RING_MB", ring)
+            sweep = device_assembler(mesh, ref.kind, ref.mat, ref.flags, layout, fext=ref.fext)
+        for m, a in zip(modes, base):
+            for _ in range(2):
+                sweep.matrix(ik.FERequirements(d, 0.5), ik.MatrixAffordance.stiffness, m)
+                assert np.array_equal(sweep.matrix(req, ik.MatrixAffordance.stiffness, m).data, a), (ring, m)
+        R0 = dev.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Full)
+        assert np.array_equal(sweep.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Full), R0), ring
+
+
+def test_pipelined_sweep_ring_guards_bit_identical(monkeypatch):
+    """IKB_FUSED=1 on a mesh large enough for the ring to wrap (24x8x8 Hex8, 384 producer tickets in 6 completion groups):
+    the smallest legal ring (IKB_SWEEP_MARGIN=0) forces write-after-read waits between the two kernels on every lap.
+    Values must equal the back-to-back path bit for bit in all three Dirichlet modes, sweep after sweep."""
+    mesh = o.structured_mesh((24, 8, 8), (3.0, 1.0, 1.0))
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material("neohooke", lam, mu)
+    kind = o.ElementKind(3, 1, "gl")
+    flags = o.fix_nodes(mesh, o.boundary_nodes(mesh, 0, 0.0))
+    d = 0.01 * np.random.default_rng(7).uniform(-1, 1, flags.shape[0])
+    d[flags] = 0.0
+    req = ik.FERequirements(d, 0.0)
+    dev = device_assembler(mesh, kind, mat, flags)
+    with monkeypatch.context() as mp:
+        mp.setenv("IKB_FUSED", "1")
+        mp.setenv("IKB_RING_MB", "0.01")
+        mp.setenv("IKB_SWEEP_MARGIN", "0")
+        sweep = device_assembler(mesh, kind, mat, flags)
+    for m in (ik.DBCOption.Raw, ik.DBCOption.Full, ik.DBCOption.Reduced):
+        a = dev.matrix(req, ik.MatrixAffordance.stiffness, m).data
+        ra = dev.vector(req, ik.VectorAffordance.forces, m)
+        for _ in range(3):
+            sweep.matrix(ik.FERequirements(d, 0.5), ik.MatrixAffordance.stiffness, m)
+            assert np.array_equal(sweep.matrix(req, ik.MatrixAffordance.stiffness, m).data, a), m
+            assert np.array_equal(sweep.vector(req, ik.VectorAffordance.forces, m), ra), m
+    assert sweep.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy) == dev.scalar(
+        req, ik.ScalarAffordance.mechanicalPotentialEnergy)
