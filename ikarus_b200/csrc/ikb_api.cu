@@ -514,6 +514,20 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   const unsigned vecGrid = gridFor(nRowNodes * h->dim, 256);
   // pull gather: signed 32-bit staged offsets (in 4-byte units) when the whole staged K_e buffer is addressable that way
   const bool idx32 = !h->pullIdx64 && (double)h->nElem * h->npair * h->dim * h->dim * 2.0 < 2147483000.0;
+  // mirrored pull: one-time maps (diagonal block and leading foreign blocks per row, mirror block per block)
+  const bool mirror = h->pullMirror && h->gatherPull && h->csrc.p && G.vals && dbc != IKB_DBC_REDUCED;
+  if (mirror && !h->mirrorBlk.p) {
+    IKB_CUDA(h, h->rowDiag.alloc((size_t)nRowNodes));
+    IKB_CUDA(h, h->rowLowEnd.alloc((size_t)nRowNodes));
+    IKB_CUDA(h, h->mirrorBlk.alloc((size_t)h->nBlocks));
+    mirror_rows_kernel<<<gridFor(nRowNodes, 256), 256, 0, h->stream>>>(G.P, h->rowDiag.p, h->rowLowEnd.p);
+    IKB_LAUNCH_CHECK(h);
+    mirror_blocks_kernel<<<gridFor(h->nBlocks, 256), 256, 0, h->stream>>>(G.P, h->mirrorBlk.p);
+    IKB_LAUNCH_CHECK(h);
+  }
+  G.rowDiag = h->rowDiag.p;
+  G.rowLowEnd = h->rowLowEnd.p;
+  G.mirrorBlk = h->mirrorBlk.p;
 #define IKB_GATHER3(DIM, NN, MODE, IL)                                                                              \
   {                                                                                                                  \
     if (G.vec) {                                                                                                     \
@@ -528,11 +542,18 @@ int launchGather(Handle* h, unsigned what, int dbc) {
       cudaEventRecord(h->evVec, vs);                                                                                 \
     }                                                                                                                \
     if (G.vals && h->gatherPull && h->csrc.p) {                                                                      \
-      if (idx32)                                                                                                     \
-        gather_pull_kernel<DIM, MODE, IL, true><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(                 \
+      constexpr bool canMirror = MODE != IKB_DBC_REDUCED;                                                            \
+      if (canMirror && mirror && idx32)                                                                              \
+        gather_pull_kernel<DIM, MODE, IL, true, canMirror><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(      \
+            G, h->cptr.p, h->csrc.p);                                                                                \
+      else if (canMirror && mirror)                                                                                  \
+        gather_pull_kernel<DIM, MODE, IL, false, canMirror><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(     \
+            G, h->cptr.p, h->csrc.p);                                                                                \
+      else if (idx32)                                                                                                \
+        gather_pull_kernel<DIM, MODE, IL, true, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(          \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else                                                                                                           \
-        gather_pull_kernel<DIM, MODE, IL, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(                \
+        gather_pull_kernel<DIM, MODE, IL, false, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(         \
             G, h->cptr.p, h->csrc.p);                                                                                \
       if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
     } else if (G.vals) {                                                                                             \
@@ -864,6 +885,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   // test hooks for the rarely taken paths of the pull gather (long contribution lists, > 2^31 staged offsets)
   if (const char* sm = std::getenv("IKB_PULL_STAGE_MAX")) h->pullStageMax = std::max(std::atoi(sm), -1);
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
+  if (const char* pm = std::getenv("IKB_PULL_MIRROR")) h->pullMirror = std::atoi(pm) != 0;
   if (const char* w = std::getenv("IKB_PULL_WARPS")) h->pullWarps = std::min(std::max(std::atoi(w), 1), PULL_WARPS_MAX);
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
@@ -922,6 +944,9 @@ int ikb_destroy(ikb_handle hh) {
   if (h->comm) nccl().commDestroy(h->comm);
   h->cgPglob.release();
   h->cgState.release();
+  h->rowDiag.release();
+  h->rowLowEnd.release();
+  h->mirrorBlk.release();
   h->ring.release();
   h->rring.release();
   h->csrcRing.release();
@@ -1023,9 +1048,14 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
       h->chunkDofEnd.push_back(((int64_t)runMax + 1) * D);
     }
   }
+  // Corner coordinates are kept RELATIVE to corner 0 of their element: every kernel only forms the Jacobian
+  // sum_c dN_c x_c (the shape-function derivatives sum to zero, so the shift changes nothing mathematically), and with
+  // absolute coordinates that sum cancels |x|-sized terms down to h-sized ones -- a relative error of eps*|x|/h in J
+  // (6e-14 on the 256^3 unit cube).  The subtraction itself is correctly rounded, error <= eps*h.
   std::vector<double> xs((size_t)nc * D * ne);
   for (int64_t e = 0; e < ne; ++e)
-    for (int q = 0; q < nc * D; ++q) xs[(size_t)q * ne + e] = corner[(size_t)e * nc * D + q];
+    for (int q = 0; q < nc * D; ++q)
+      xs[(size_t)q * ne + e] = corner[(size_t)e * nc * D + q] - corner[(size_t)e * nc * D + (q % D)];
   h->layout = layout;
   IKB_CUDA(h, h->elemNode.alloc(en.size()));
   IKB_CUDA(h, h->X.alloc(xs.size()));
@@ -1060,7 +1090,7 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
           double dn = ((c >> i) & 1) ? 1.0 : -1.0;
           for (int k = 0; k < D; ++k)
             if (k != i) dn *= 0.5;
-          for (int k = 0; k < D; ++k) J[i][k] += dn * corner[(size_t)e * nc * D + c * D + k];
+          for (int k = 0; k < D; ++k) J[i][k] += dn * (corner[(size_t)e * nc * D + c * D + k] - corner[(size_t)e * nc * D + k]);
         }
       double T[6][6], Ti[6][6];
       double det;
@@ -1281,6 +1311,9 @@ int ikb_build_pattern(ikb_handle hh) {
   tmp.release();
   h->patternBuilt = true;
   h->reducedBuilt = false;
+  h->rowDiag.release();
+  h->rowLowEnd.release();
+  h->mirrorBlk.release();
   h->fusedTried = h->fusedOk = false;
   for (int i = 0; i < 3; ++i) {
     h->vals[i].release();

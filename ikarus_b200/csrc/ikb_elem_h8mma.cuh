@@ -12,8 +12,9 @@
 // i.e. four m8n8k4 DMMAs.  The A operand of lane l is V_c[l>>2][4h + (l&3)], the B operand is the SAME register scaled
 // by c1 / c2 of that Gauss point, so a lane needs 6 + 4 doubles per element from shared memory instead of the ~32
 // loads per Gauss point of the FMA formulation (which ncu showed bound by shared-memory wavefronts, not by the FP64
-// pipe).  After the 36 DMMAs lane (a = l>>2, q = l&3) holds the complete 3x3 blocks of the node pairs (a, 2q) and
-// (a, 2q+1).
+// pipe).  Only the six pairs i <= j are contracted (24 DMMAs); K^{ji} is the node-transpose of K^{ij} and comes from
+// the owning lane by shuffle.  Then lane (a = l>>2, q = l&3) holds the complete 3x3 blocks of the node pairs (a, 2q)
+// and (a, 2q+1).
 //
 // Phase 1 (kinematics + material per Gauss point) keeps the thread-per-Gauss-point layout: a warp evaluates four
 // elements at once, lane = 8*el + g.  R_e is reduce-scattered over the 8 Gauss-point lanes of an element with
@@ -300,15 +301,29 @@ __device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, const H8Out&
     for (int i = 0; i < D; ++i)
 #pragma unroll
       for (int jj = 0; jj < D; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+    // component pairs i <= j only (24 DMMAs): K^{ji} = (K^{ij})^T as 8 x 8 node matrices, i.e. K^{ji}[a][b] = K^{ij}[b][a],
+    // which lane (b, a>>1) holds in accumulator register a&1 -- fetched with shuffles below
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int jj = 0; jj < D; ++jj) {
+        for (int jj = i; jj < D; ++jj) {
           dmma884(acc[i][jj][0], acc[i][jj][1], v[i][h], vb1[jj][h]);
           dmma884(acc[i][jj][0], acc[i][jj][1], v[jj][h], vb2[i][h]);
         }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int srcLane = 4 * (2 * q + r) + (a >> 1);
+#pragma unroll
+      for (int i = 1; i < D; ++i)
+#pragma unroll
+        for (int jj = 0; jj < i; ++jj) {
+          const double t0 = __shfl_sync(0xffffffffu, acc[jj][i][0], srcLane);
+          const double t1 = __shfl_sync(0xffffffffu, acc[jj][i][1], srcLane);
+          acc[i][jj][r] = (a & 1) ? t1 : t0;
+        }
+    }
     // lane (a,q) now holds the blocks (a, 2q) and (a, 2q+1)
     __syncwarp();  // kbuf of the previous element has been copied out
     {
@@ -324,8 +339,8 @@ __device__ __forceinline__ void h8_warp_elements(const ElemArgs& A, const H8Out&
           for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) {
-              // diagonal block: mirror the upper triangle so K_e is exactly symmetric
-              double x = (k == 0 && i > jj) ? acc[jj][i][r] : acc[i][jj][r];
+              // (the diagonal block is exactly symmetric by construction: its lower entries are the shuffled upper ones)
+              double x = acc[i][jj][r];
               if (i == jj) x += lap;
               dst[i * D + jj] = x;
             }

@@ -36,6 +36,11 @@ struct GatherArgs {
   const int32_t* cbelow;
   int64_t redVecOffset;  // index of the first local free row in the reduced vector
   int pullStageMax;      // pull gather: chunks with at most this many codes are staged in shared memory (<= PULL_CAP)
+  // mirrored pull (Raw/Full): a row computes its blocks (g, g') with g' >= g (and those whose column node belongs to
+  // another rank) and stores each off-diagonal one a second time, transposed, as block (g', g) of row g'
+  const int32_t* rowDiag = nullptr;    // [nRowNodes] block index of the diagonal block of the row
+  const int32_t* rowLowEnd = nullptr;  // [nRowNodes] end of the leading blocks whose column node is not owned
+  const int32_t* mirrorBlk = nullptr;  // [nBlocks] block index of (g', g) for block (g, g') with g' owned
 };
 
 // One warp per node-row.  For every element touching the node (ascending element order, as the reference's
@@ -236,7 +241,7 @@ __device__ __forceinline__ void pullStore(uint64_t a, double v) {
 }
 
 // one node-row of the pull gather; sm: PULL_CAP words of shared memory private to the warp
-template <int D, int DBC, bool INTERLEAVED, bool IDX32, bool RING>
+template <int D, int DBC, bool INTERLEAVED, bool IDX32, bool RING, bool MIRROR = false>
 __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __restrict__ cptr,
                                         const uint32_t* __restrict__ csrc, int64_t g, uint32_t* sm, int lane) {
   constexpr int DD = D * D;
@@ -287,9 +292,33 @@ __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __re
   int64_t redStart = 0;
   if (DBC == IKB_DBC_REDUCED) redStart = G.redRowStart[localRowOf(P, g, i)];
 
-  for (int32_t cb = b0; cb < b1; cb += CH) {
-    const int nb = min(CH, b1 - cb);
+  // K is symmetric and so is every staged K_e (the packed form keeps one of (a,b), (b,a)), so block (g', g) is bit for
+  // bit the transpose of block (g, g'): with MIRROR only pass 0 (column node owned by another rank) and pass 1 (from the
+  // diagonal block on) are gathered, halving the staged reads; the blocks in between arrive from their mirror rows.
+  int32_t lowEnd = b1, diag = b1;
+  if (MIRROR) {
+    lowEnd = G.rowLowEnd[g];
+    diag = G.rowDiag[g];
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < (MIRROR ? 2 : 1); ++pass) {
+  const int32_t r0 = (MIRROR && pass == 1) ? diag : b0;
+  const int32_t r1 = (MIRROR && pass == 0) ? lowEnd : b1;
+  for (int32_t cb = r0; cb < r1; cb += CH) {
+    const int nb = min(CH, r1 - cb);
     const int32_t cp = cptr[cb + min(lane, nb)];
+    // where the transposed copy of block (cb + lane) goes: first entry of block (g', g) in row g', length of that row
+    int64_t mBase = -1;
+    int nnbM = 0;
+    if (MIRROR && pass == 1 && lane < nb) {
+      const int64_t gl = (int64_t)P.nbrIdx[cb + lane] - P.rowBegin;
+      if (gl != g && gl >= 0 && gl < P.nRowNodes) {
+        const int32_t mb = G.mirrorBlk[cb + lane];
+        const int32_t p0 = P.nbrPtr[gl];
+        nnbM = P.nbrPtr[gl + 1] - p0;
+        mBase = INTERLEAVED ? (int64_t)DD * p0 + (int64_t)D * (mb - p0) : (int64_t)D * p0 + (mb - p0);
+      }
+    }
     // Dirichlet work only where the row or one of the chunk's column nodes is constrained (warp-uniform)
     bool slow = anyRowFixed;
     if (DBC != IKB_DBC_RAW && !slow) {
@@ -317,13 +346,15 @@ __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __re
     const uint32_t pack = (lane < nb) ? (uint32_t)(cp - cbase) | ((uint32_t)(cnext - cp) << 16) : 0u;
     const int slotBase = (int)(cb - b0);
     // writes the finished entry of pattern block (slot sg of the row) with the Dirichlet mode applied
-    auto emit = [&](int sg, double val) {
+    auto emit = [&](int sg, double val, int64_t mB, int nM) {
       if (DBC == IKB_DBC_RAW || !slow) {
         if (DBC == IKB_DBC_REDUCED) {
           const int32_t b = b0 + sg;
           G.vals[redStart + reducedRank(P, G.flags, G.freeCnt, G.freeTot, g, b, P.nbrIdx[b], k)] = val;
         } else {
           pullStore(dst + (uint64_t)(8 * SSTRIDE) * (uint32_t)sg, val);
+          if (MIRROR && mB >= 0)  // entry (i,k) of (g,g') = entry (k,i) of (g',g)
+            G.vals[mB + (INTERLEAVED ? (int64_t)k * D * nM + i : (int64_t)k * D * P.nBlocks + (int64_t)i * nM)] = val;
         }
       } else {
         const int32_t b = b0 + sg;
@@ -336,6 +367,8 @@ __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __re
           // Full: zero constrained rows and columns, unit diagonal (simpleassemblers.inl:159-167)
           if (rowFixed || colFixed) val = (gb == gGlobal && i == k) ? 1.0 : 0.0;
           pullStore(dst + (uint64_t)(8 * SSTRIDE) * (uint32_t)sg, val);
+          if (MIRROR && mB >= 0)  // the mirrored entry has row and column flags swapped: same rule, same value
+            G.vals[mB + (INTERLEAVED ? (int64_t)k * D * nM + i : (int64_t)k * D * P.nBlocks + (int64_t)i * nM)] = val;
         }
       }
     };
@@ -380,7 +413,14 @@ __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __re
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc += x[j];
         }
-        if (active && grp.s < nb) emit(slotBase + grp.s, acc);
+        int64_t mB = -1;
+        int nM = 0;
+        if (MIRROR && pass == 1) {  // warp-uniform
+          const int sl = grp.s < nb ? grp.s : 0;
+          mB = __shfl_sync(FULLMASK, (long long)mBase, sl);
+          nM = __shfl_sync(FULLMASK, nnbM, sl);
+        }
+        if (active && grp.s < nb) emit(slotBase + grp.s, acc, mB, nM);
       };
       // (issuing the loads of the next group before the adds of the current one was measured: the extra registers cost
       // more occupancy than the overlap gains -- 64 resident warps per SM hide the latency better)
@@ -401,22 +441,67 @@ __device__ __forceinline__ void pullRow(const GatherArgs& G, const int32_t* __re
           const uint32_t cc = csrc[c];
           acc += stagedValue(IDX32 ? (cc & SRC_MASK) * (uint32_t)(2 * DD) + (cc >> 31) : __funnelshift_l(cc, cc, 1));
         }
-        if (valid) emit(slotBase + sl, acc);
+        int64_t mB = -1;
+        int nM = 0;
+        if (MIRROR && pass == 1) {
+          const int sl2 = sl < nb ? sl : 0;
+          mB = __shfl_sync(FULLMASK, (long long)mBase, sl2);
+          nM = __shfl_sync(FULLMASK, nnbM, sl2);
+        }
+        if (valid) emit(slotBase + sl, acc, mB, nM);
       }
     }
+  }
   }
 }
 
 // 32 registers per thread (16 CTAs of 4 warps per SM): the kernel is latency bound, 64 resident warps per SM measured
 // 13 % faster than the 48 warps the unconstrained 40-register build reaches; 4 warps per CTA 2 % faster than 8.
-template <int D, int DBC, bool INTERLEAVED, bool IDX32>
-__global__ void __launch_bounds__(32 * PULL_WARPS_MAX, 16) gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr,
-                                                          const uint32_t* __restrict__ csrc) {
+template <int D, int DBC, bool INTERLEAVED, bool IDX32, bool MIRROR>
+__global__ void __launch_bounds__(32 * PULL_WARPS_MAX, MIRROR ? 12 : 16)
+    gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr, const uint32_t* __restrict__ csrc) {
   __shared__ uint32_t codeBuf[PULL_WARPS_MAX][PULL_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (g >= G.P.nRowNodes) return;
-  pullRow<D, DBC, INTERLEAVED, IDX32, false>(G, cptr, csrc, g, codeBuf[warp], lane);
+  pullRow<D, DBC, INTERLEAVED, IDX32, false, MIRROR>(G, cptr, csrc, g, codeBuf[warp], lane);
+}
+
+// one-time maps of the mirrored pull
+__global__ void mirror_rows_kernel(PatternView P, int32_t* rowDiag, int32_t* rowLowEnd) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.nRowNodes) return;
+  const int32_t b0 = P.nbrPtr[g], b1 = P.nbrPtr[g + 1];
+  // first block whose column node is >= rowBegin (the lists ascend), and the diagonal block
+  int32_t lo = b0, hi = b1;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (P.nbrIdx[mid] < P.rowBegin)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  rowLowEnd[g] = lo;
+  rowDiag[g] = diagBlockOf(P, g);
+}
+__global__ void mirror_blocks_kernel(PatternView P, int32_t* mirrorBlk) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.nBlocks) return;
+  const int64_t gl = (int64_t)P.nbrIdx[b] - P.rowBegin;  // row of the mirrored block
+  int32_t out = -1;
+  if (gl >= 0 && gl < P.nRowNodes) {
+    const int32_t target = (int32_t)(P.nbrRow[b] + P.rowBegin);
+    int32_t lo = P.nbrPtr[gl], hi = P.nbrPtr[gl + 1];
+    while (lo < hi) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (P.nbrIdx[mid] < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < P.nbrPtr[gl + 1] && P.nbrIdx[lo] == target) out = lo;
+  }
+  mirrorBlk[b] = out;
 }
 
 // Residual gather: one thread per (node-row, component).  The node's (element, local node) adjacency is walked in

@@ -118,6 +118,8 @@ struct Handle {
   int maxNbr = 0;               // longest pattern row in nodes
   int pullStageMax = 1 << 30;   // clamped to PULL_CAP at launch (IKB_PULL_STAGE_MAX, test hook)
   int pullWarps = 4;            // warps per CTA of the pull gather (IKB_PULL_WARPS, tuning; 4 measured 2 % faster than 8)
+  bool pullMirror = false;      // IKB_PULL_MIRROR=1: gather the upper block triangle only and store every block twice (bit-identical; measured slower: 0.205 vs 0.184 ms on C2)
+  DevBuf<int32_t> rowDiag, rowLowEnd, mirrorBlk;
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
   bool elemMma = true;          // Hex8 NeoHooke/LinearElastic: tangent contraction by DMMA (IKB_ELEM=fma: FMA kernel)
   int h8MinBlocks = 4;          // register budget of the DMMA kernel as resident CTAs per SM (IKB_H8_MINB, tuning)

@@ -11,6 +11,18 @@ from golden_data import GOLDEN
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
+# Static condensation K - L^T D^-1 L subtracts matrices of the size of K itself, so entries of the condensed tangent
+# that come out small carry the rounding of the large ones: in the SURVEY 8d norm (floor 1e-3 of the row maximum) two
+# double-precision evaluations -- the oracle inverts D, the device factorises it -- differ by up to 5e-12, while relative
+# to the row maximum (the scale of what is subtracted) they agree to north_star's 1e-12.  Both are asserted.
+TOL_8D = 5e-12
+
+
+def _row_scaled_error(dev, ref, rows):
+    rowmax = np.zeros(rows.max() + 1)
+    np.maximum.at(rowmax, rows, np.abs(ref))
+    rm = np.where(rowmax[rows] == 0.0, 1.0, rowmax[rows])
+    return float((np.abs(np.asarray(dev) - np.asarray(ref)) / rm).max(initial=0.0))
 
 EAS_CASES = [(3, 21, "neohooke", "gl"), (3, 9, "svk", "gl"), (3, 9, "neohooke", "gl"), (2, 4, "neohooke", "gl"),
              (2, 5, "svk", "gl"), (2, 7, "neohooke", "gl"), (2, 4, "linear", "linear"), (3, 9, "linear", "linear")]
@@ -43,10 +55,12 @@ def test_eas_matrix_vector_and_alpha_update(case):
         outer, inner = ref.pattern(mode)
         assert np.array_equal(K.indptr, outer) and np.array_equal(K.indices, inner)
         rows = np.repeat(np.arange(outer.shape[0] - 1), np.diff(outer))
-        assert entry_error(K.data, ref.matrix_values(d, 0.0, mode), rows) <= 5e-12, mode
+        Kref = ref.matrix_values(d, 0.0, mode)
+        assert entry_error(K.data, Kref, rows) <= TOL_8D, mode
+        assert _row_scaled_error(K.data, Kref, rows) <= TOL, mode
         R = dev.vector(req, ik.VectorAffordance.forces, dbc)
         Rr = ref.vector(d, 0.0, mode)
-        assert np.abs(R - Rr).max() <= 5e-12 * np.abs(Rr).max(), mode
+        assert np.abs(R - Rr).max() <= TOL_8D * np.abs(Rr).max(), mode
     Kd = dev.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Raw).toarray()
     assert np.array_equal(Kd, Kd.T)  # condensed K mirrored from the upper triangle (:294-295)
     # alpha update at the old (d, alpha)

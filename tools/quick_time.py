@@ -25,7 +25,7 @@ dev.bind(req, ik.elastoStatics, ik.DBCOption.Full)
 A = dev.matrix(); R = dev.vector()
 print(f"mesh {cells} {matk}: {mesh.n_elem} elements, {flags.shape[0]} dofs; mesh gen {t1-t0:.2f}s setup {t2-t1:.2f}s |R|={np.linalg.norm(R):.6e}")
 for ph in ("fused", "elements", "gather", "spmv", "dfma_peak", "dmma_peak"):
-    if ph == "fused" and os.environ.get("IKB_FUSED", "1") == "0":
+    if ph == "fused" and os.environ.get("IKB_FUSED", "0") != "1":
         continue
     for _ in range(2):
         ms = dev.timePhase(ph, ik.DBCOption.Full, 20 if not ph.endswith("_peak") else 3)
