@@ -86,34 +86,62 @@ struct ElementAccess
 };
 
 #if IKB_HAVE_IKARUS
+/** Which device material law and reduction an Ikarus material type maps to, decided on the TYPE (not on name()). */
+template <typename M>
+struct MaterialCode
+{
+  static constexpr int material  = -1;  // outside the device hot path
+  static constexpr int reduction = IKB_REDUCE_NONE;
+};
+template <typename ST>
+struct MaterialCode<Ikarus::Materials::LinearElasticityT<ST>>
+{
+  static constexpr int material = IKB_MAT_LINEAR_ELASTICITY, reduction = IKB_REDUCE_NONE;
+};
+template <typename ST>
+struct MaterialCode<Ikarus::Materials::StVenantKirchhoffT<ST>>
+{
+  static constexpr int material = IKB_MAT_SVK, reduction = IKB_REDUCE_NONE;
+};
+template <typename ST>
+struct MaterialCode<Ikarus::Materials::NeoHookeT<ST>>
+{
+  static constexpr int material = IKB_MAT_NEOHOOKE, reduction = IKB_REDUCE_NONE;
+};
+/** planeStrain(mat) (materials/vanishingstrain.hh:186-198) */
+template <auto pairs, typename MI>
+struct MaterialCode<Ikarus::Materials::VanishingStrain<pairs, MI>>
+{
+  static constexpr int material = MaterialCode<MI>::material, reduction = IKB_REDUCE_PLANE_STRAIN;
+};
+/** planeStress(mat, tol) (materials/vanishingstress.hh:254-265) */
+template <auto pairs, typename MI>
+struct MaterialCode<Ikarus::Materials::VanishingStress<pairs, MI>>
+{
+  static constexpr int material = MaterialCode<MI>::material, reduction = IKB_REDUCE_PLANE_STRESS;
+};
+
 /** Adapter for real Ikarus finite elements FE<PreFE, Skills...> (finiteelements/mixin.hh, febase.hh). */
 template <typename FE>
 requires requires(const FE& fe) { fe.localView(); fe.material(); }
 struct ElementAccess<FE>
 {
+  using Mat = std::remove_cvref_t<decltype(std::declval<const FE&>().material())>;
   static int dim(const FE&) { return FE::Traits::mydim; }
   static int order(const FE& fe) { return fe.order(); }
   static int strain(const FE&) {
-    return FE::Material::strainTag == Ikarus::StrainTags::linear ? IKB_STRAIN_LINEAR : IKB_STRAIN_GREEN_LAGRANGE;
+    return Mat::strainTag == Ikarus::StrainTags::linear ? IKB_STRAIN_LINEAR : IKB_STRAIN_GREEN_LAGRANGE;
   }
   static int material(const FE& fe) {
-    const std::string n = fe.material().name();
-    if (n.find("NeoHooke") != std::string::npos) return IKB_MAT_NEOHOOKE;
-    if (n.find("StVenantKirchhoff") != std::string::npos) return IKB_MAT_SVK;
-    if (n.find("LinearElasticity") != std::string::npos) return IKB_MAT_LINEAR_ELASTICITY;
-    IKB_THROW(NotImplemented, "material " + n + " is outside the device hot path");
+    if constexpr (MaterialCode<Mat>::material < 0)
+      IKB_THROW(NotImplemented, "material " + fe.material().name() + " is outside the device hot path");
+    return MaterialCode<Mat>::material;
   }
-  static bool planeStrain(const FE&) { return FE::Material::isReduced; }
-  /** VanishingStrain / VanishingStress are told apart by the material name (vanishingstrain.hh, vanishingstress.hh:63-70) */
-  static int reduction(const FE& fe) {
-    if constexpr (!FE::Material::isReduced)
-      return IKB_REDUCE_NONE;
-    else
-      return fe.material().name().find("VanishingStress") != std::string::npos ? IKB_REDUCE_PLANE_STRESS
-                                                                               : IKB_REDUCE_PLANE_STRAIN;
-  }
-  /** the tolerance is private to VanishingStress: specialise ElementAccess to pass a non-default one */
-  static double reductionTolerance(const FE&) { return 1e-12; }
+  static bool planeStrain(const FE&) { return MaterialCode<Mat>::reduction == IKB_REDUCE_PLANE_STRAIN; }
+  static int reduction(const FE&) { return MaterialCode<Mat>::reduction; }
+  /** VanishingStress keeps its tolerance private (vanishingstress.hh:231); planeStress() defaults to 1e-8
+   *  (vanishingstress.hh:254-257).  Specialise ElementAccess to pass another one. */
+  static double reductionTolerance(const FE&) { return 1e-8; }
   static double lambda(const FE& fe) { return fe.material().materialParameters().lambda; }
   static double mu(const FE& fe) { return fe.material().materialParameters().mu; }
   static int numberOfInternalVariables(const FE& fe) {
@@ -162,6 +190,12 @@ public:
   using VectorType               = HostTraits::Vector;
   using MatrixType               = HostTraits::SparseMatrix;
   using DBCOption                = HostTraits::DBCOption;
+#if IKB_HAVE_IKARUS
+  // assembler/interface.hh:32-42
+  using GlobalIndex = typename FE::GlobalIndex;
+  using Basis       = typename DV::Basis;
+  using GridView    = typename Basis::GridView;
+#endif
 
   /** FlatAssemblerBase ctor (assembler/interface.hh:51-62) + one-time device upload. */
   DeviceSparseFlatAssembler(FEC&& fes, const DV& dirichletValues, int device = -1)
@@ -203,6 +237,32 @@ public:
       A::corners(fe, corners);
       ++nElem;
     }
+    // number of grid vertices for estimateOfConnectivity(): the distinct nodes at element corners (for Q2 the corner
+    // nodes are the lattice positions with every coordinate in {0, 2}; local order is lexicographic, x fastest)
+    if (nElem > 0) {
+      const int dim = desc.dim, n1 = desc.order + 1;
+      int nn = 1;
+      for (int k = 0; k < dim; ++k)
+        nn *= n1;
+      std::vector<std::uint8_t> seen(n / static_cast<std::size_t>(dim) + 1, 0);
+      std::vector<std::int64_t> minDof(static_cast<std::size_t>(nn));
+      for (std::int64_t e = 0; e < nElem; ++e) {
+        for (int a = 0; a < nn; ++a) {
+          bool corner = true;
+          for (int k = 0, q = a; k < dim; ++k, q /= n1)
+            corner = corner && (q % n1 == 0 || q % n1 == desc.order);
+          if (!corner)
+            continue;
+          const std::int64_t d0 = dofs[static_cast<std::size_t>(e) * nn * dim + static_cast<std::size_t>(a) * dim];
+          // FlatInterleaved: dim*node + 0, FlatLexicographic: node
+          const std::size_t node = static_cast<std::size_t>(dofs[1] == dofs[0] + 1 ? d0 / dim : d0);
+          if (node < seen.size() && !seen[node]) {
+            seen[node] = 1;
+            ++vertexCount_;
+          }
+        }
+      }
+    }
     desc.device = device;
     desc.n_elem = nElem;
     desc.n_dof  = static_cast<std::int64_t>(n);
@@ -229,7 +289,13 @@ public:
   const auto& dirichletValues() const { return dirichletValues_; }
   std::size_t constraintsBelow(std::size_t i) const { return constraintsBelow_[i]; }
   bool isConstrained(std::size_t i) const { return dirichletValues_.isConstrained(i); }
-  std::size_t estimateOfConnectivity() const { return fes_.size() * 8; }
+  /** assembler/interface.hh:141: gridView.size(dim) * 8, i.e. eight times the number of grid vertices */
+  std::size_t estimateOfConnectivity() const { return vertexCount_ * 8; }
+#if IKB_HAVE_IKARUS
+  /** assembler/interface.hh:110-116 */
+  const auto& basis() const { return dirichletValues_.basis(); }
+  const auto& gridView() const { return Dune::resolveRef(dirichletValues_.basis().gridView()); }
+#endif
 
   VectorType createFullVector(const VectorType& reducedVector) const {
     assert(static_cast<std::size_t>(reducedVector.size()) == reducedSize() &&
@@ -289,7 +355,47 @@ public:
   }
 
   // ---- ScalarAssembler / VectorAssembler / MatrixAssembler (interface.hh:300-462) -----------------
-  const ScalarType& scalar(const FERequirement& req, HostTraits::ScalarAffordance aff) {
+  // Public calls dispatch on the DBCOption to the get*Impl hooks exactly like the reference's CRTP interfaces
+  // (interface.hh:355-389, 430-462); the hooks are protected so that the reference's AssemblerManipulator
+  // (assemblermanipulatorfuser.hh:242-385, which derives privately from the wrapped assembler and calls
+  // A::get*Impl) can wrap this class and run its callbacks on the returned quantity.
+  const ScalarType& scalar(const FERequirement& req, HostTraits::ScalarAffordance aff) { return getScalarImpl(req, aff); }
+  const ScalarType& scalar() { return scalar(requirement(), affordanceCollection().scalarAffordance()); }
+
+  const VectorType& vector(const FERequirement& req, HostTraits::VectorAffordance aff,
+                           DBCOption dbc = DBCOption::Full) {
+    if (dbc == DBCOption::Raw)
+      return getRawVectorImpl(req, aff);
+    if (dbc == DBCOption::Reduced)
+      return getReducedVectorImpl(req, aff);
+    return getVectorImpl(req, aff);
+  }
+  const VectorType& vector(DBCOption dbc) { return vector(requirement(), affordanceCollection().vectorAffordance(), dbc); }
+  const VectorType& vector() { return vector(dBCOption()); }
+
+  const MatrixType& matrix(const FERequirement& req, HostTraits::MatrixAffordance aff,
+                           DBCOption dbc = DBCOption::Full) {
+    if (dbc == DBCOption::Raw)
+      return getRawMatrixImpl(req, aff);
+    if (dbc == DBCOption::Reduced)
+      return getReducedMatrixImpl(req, aff);
+    return getMatrixImpl(req, aff);
+  }
+  const MatrixType& matrix(DBCOption dbc) { return matrix(requirement(), affordanceCollection().matrixAffordance(), dbc); }
+  const MatrixType& matrix() { return matrix(dBCOption()); }
+
+  /**
+   * One element sweep yields K and R together.  With the fused sweep on (default) vector() also asks for the matrix
+   * whenever a stiffness affordance is bound (or nothing is bound), so that NewtonRaphson's `residual(x); jacobian(x)`
+   * pair (solver/nonlinearsolver/newtonraphson.hh:204-205, 242-243) costs ONE element kernel + ONE gather; the matrix
+   * call that follows is served from the device cache because push() leaves an unchanged state alone.  Switch it off
+   * where gradients are evaluated without the Hessian (TrustRegion's rejected steps, trustregion.hh:309-340).
+   */
+  void setFusedSweep(bool on) { fusedSweep_ = on; }
+  bool fusedSweep() const { return fusedSweep_; }
+
+protected:
+  ScalarType& getScalarImpl(const FERequirement& req, HostTraits::ScalarAffordance aff) {
     if (aff != HostTraits::ScalarAffordance::mechanicalPotentialEnergy)
       IKB_THROW(NotImplemented, "ScalarAffordance not implemented");
     push(req);
@@ -297,32 +403,46 @@ public:
     check(ikb_get_scalar(h_, &scal_));
     return scal_;
   }
-  const ScalarType& scalar() { return scalar(requirement(), affordanceCollection().scalarAffordance()); }
+  VectorType& getRawVectorImpl(const FERequirement& req, HostTraits::VectorAffordance aff) {
+    return vectorImpl(req, aff, DBCOption::Raw);
+  }
+  VectorType& getVectorImpl(const FERequirement& req, HostTraits::VectorAffordance aff) {
+    return vectorImpl(req, aff, DBCOption::Full);
+  }
+  VectorType& getReducedVectorImpl(const FERequirement& req, HostTraits::VectorAffordance aff) {
+    return vectorImpl(req, aff, DBCOption::Reduced);
+  }
+  MatrixType& getRawMatrixImpl(const FERequirement& req, HostTraits::MatrixAffordance aff) {
+    return matrixImpl(req, aff, DBCOption::Raw);
+  }
+  MatrixType& getMatrixImpl(const FERequirement& req, HostTraits::MatrixAffordance aff) {
+    return matrixImpl(req, aff, DBCOption::Full);
+  }
+  MatrixType& getReducedMatrixImpl(const FERequirement& req, HostTraits::MatrixAffordance aff) {
+    return matrixImpl(req, aff, DBCOption::Reduced);
+  }
 
-  const VectorType& vector(const FERequirement& req, HostTraits::VectorAffordance aff,
-                           DBCOption dbc = DBCOption::Full) {
+private:
+  bool matrixLikelyNext() const {
+    return fusedSweep_ && (!aff_.has_value() || aff_->matrixAffordance() == HostTraits::MatrixAffordance::stiffness);
+  }
+  VectorType& vectorImpl(const FERequirement& req, HostTraits::VectorAffordance aff, DBCOption dbc) {
     if (aff != HostTraits::VectorAffordance::forces)
       IKB_THROW(NotImplemented, "VectorAffordance not implemented");
     push(req);
     const int d = toCode(dbc);
-    // K and R leave the same fused sweep; the matrix call that follows in every Newton iteration
-    // (solver/nonlinearsolver/newtonraphson.hh:242-243) is then served from the device cache.
-    check(ikb_assemble(h_, IKB_VECTOR | IKB_MATRIX, d));
+    check(ikb_assemble(h_, IKB_VECTOR | (matrixLikelyNext() ? IKB_MATRIX : 0u), d));
     VectorType& out = vec_[d];
     out.resize(dbc == DBCOption::Reduced ? reducedSize() : size());
     check(ikb_get_vector(h_, d, out.data()));
     return out;
   }
-  const VectorType& vector(DBCOption dbc) { return vector(requirement(), affordanceCollection().vectorAffordance(), dbc); }
-  const VectorType& vector() { return vector(dBCOption()); }
-
-  const MatrixType& matrix(const FERequirement& req, HostTraits::MatrixAffordance aff,
-                           DBCOption dbc = DBCOption::Full) {
+  MatrixType& matrixImpl(const FERequirement& req, HostTraits::MatrixAffordance aff, DBCOption dbc) {
     if (aff != HostTraits::MatrixAffordance::stiffness)
       IKB_THROW(NotImplemented, "MatrixAffordance not implemented");
     push(req);
     const int d = toCode(dbc);
-    check(ikb_assemble(h_, IKB_MATRIX | IKB_VECTOR, d));
+    check(ikb_assemble(h_, IKB_MATRIX | (fusedSweep_ ? IKB_VECTOR : 0u), d));
     MatrixType& A = mat_[d];
     if (not patternReady_[d]) {  // preProcessSparseMatrix(Reduced) (simpleassemblers.inl:289-299)
       std::int64_t rows = 0, nnz = 0;
@@ -336,9 +456,8 @@ public:
     check(ikb_get_matrix_values(h_, d, HostTraits::valuePtr(A)));
     return A;
   }
-  const MatrixType& matrix(DBCOption dbc) { return matrix(requirement(), affordanceCollection().matrixAffordance(), dbc); }
-  const MatrixType& matrix() { return matrix(dBCOption()); }
 
+public:
   // ---- DenseFlatAssembler view (assembler/simpleassemblers.hh:188-231, simpleassemblers.inl:301-375) --------
   /** Column-major rows x rows copy of the assembled matrix (Eigen::MatrixXd layout); small problems only. */
   const std::vector<double>& denseMatrix(const FERequirement& req, HostTraits::MatrixAffordance aff,
@@ -424,12 +543,23 @@ private:
   static int toCode(DBCOption dbc) {
     return dbc == DBCOption::Raw ? IKB_DBC_RAW : (dbc == DBCOption::Reduced ? IKB_DBC_REDUCED : IKB_DBC_FULL);
   }
+  /** Uploads d only when it differs from what the device holds: ikb_set_solution invalidates every cached result, and
+   *  a Newton iteration asks for residual and tangent of the SAME state one after the other. */
   void push(const FERequirement& req) {
     const auto& d = req.globalSolution();
     assert(static_cast<std::size_t>(d.size()) == size());
-    check(ikb_set_solution(h_, d.data()));
+    const double* p = d.data();
+    if (lastD_.size() != size() || !std::equal(lastD_.begin(), lastD_.end(), p)) {
+      check(ikb_set_solution(h_, p));
+      check(ikb_sync(h_));  // the copy has read the caller's buffer
+      lastD_.assign(p, p + size());
+    }
     check(ikb_set_parameter(h_, req.parameter()));
   }
+public:
+  /** The device state was changed behind the wrapper's back (ikb_update_solution, ikb_set_solution on handle()). */
+  void invalidateSolutionCache() { lastD_.clear(); }
+private:
   void check(int rc) const {
     if (rc == IKB_OK)
       return;
@@ -449,6 +579,9 @@ private:
   std::optional<DBCOption> dbc_;
   std::vector<std::size_t> constraintsBelow_;
   std::size_t fixedDofs_{};
+  std::size_t vertexCount_{0};
+  bool fusedSweep_{true};
+  std::vector<double> lastD_;
   ikb_handle h_{nullptr};
   ScalarType scal_{0.0};
   VectorType vec_[3];

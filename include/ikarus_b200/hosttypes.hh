@@ -23,6 +23,7 @@
   #include <Eigen/Sparse>
 
   #include <dune/common/exceptions.hh>
+  #include <dune/common/referencehelper.hh>
 
   #include <ikarus/assembler/dirichletbcenforcement.hh>
   #include <ikarus/finiteelements/fehelper.hh>

@@ -11,7 +11,13 @@
 
 #include <ikarus_b200/deviceflatassembler.hh>
 
+#include "flatassembler_concept.hh"
+
 using namespace Ikarus::B200;
+
+// the class models the reference's assembler concept (utils/concepts.hh:517-585), checked at compile time
+using TestAssembler = DeviceSparseFlatAssembler<std::vector<HostFE>&, HostDirichletValues>;
+static_assert(TestConcepts::MatrixFlatAssembler<TestAssembler, std::vector<double>, DBCOption>);
 
 #define CHECK(cond)                                                        \
   do {                                                                     \
@@ -176,6 +182,66 @@ int main(int argc, char** argv) {
     eta      = asmb->truncatedCG(DBCOption::Full, minusG, ti);
     CHECK(ti.stop_reason == IKB_TCG_REACHED_KAPPA_LINEAR || ti.stop_reason == IKB_TCG_REACHED_THETA_SUPERLINEAR);
     CHECK(ti.iterations > 1 && ti.rel_error <= 0.1 && ti.g_dot_eta < 0 && ti.eta_h_eta > 0);
+  }
+
+  // estimateOfConnectivity = 8 x number of grid vertices (assembler/interface.hh:141)
+  CHECK(asmb->estimateOfConnectivity() == 8u * (nx + 1) * (ny + 1) * (nz + 1));
+
+  // One Newton iteration = ONE element sweep + ONE gather: residual(x) then jacobian(x) at the same state
+  // (newtonraphson.hh:242-243); the second call must be served from the device cache, also when the caller hands in a
+  // different requirement object holding the same d.
+  {
+    auto launches = [&]() {
+      std::int64_t n0 = 0;
+      ikb_launch_count(asmb->handle(), &n0);
+      return n0;
+    };
+    req.d[n - 1] += 1e-9;  // new state
+    const std::int64_t l0 = launches();
+    asmb->vector();
+    const std::int64_t l1 = launches();
+    asmb->matrix();
+    const std::int64_t l2 = launches();
+    HostRequirement copy = req;
+    asmb->matrix(copy, MatrixAffordance::stiffness, DBCOption::Full);
+    asmb->vector(copy, VectorAffordance::forces, DBCOption::Full);
+    const std::int64_t l3 = launches();
+    CHECK(l1 - l0 == 3);  // element kernel, residual gather, matrix gather
+    CHECK(l2 == l1 && l3 == l2);
+    // with the fused sweep off, vector() alone leaves the matrix gather out
+    asmb->setFusedSweep(false);
+    req.d[n - 1] += 1e-9;
+    asmb->vector();
+    const std::int64_t l4 = launches();
+    CHECK(l4 - l3 == 2);  // element kernel (R only) + residual gather
+    asmb->setFusedSweep(true);
+  }
+  // vector() -> matrix() -> forcesDueToIDBC() -> solve(): the pushes in between must not invalidate the matrix the
+  // PCG is about to use (NewtonRaphson with inhomogeneous Dirichlet values, newtonraphson.hh:214-226)
+  {
+    const auto& rx = asmb->vector();
+    asmb->matrix();
+    std::vector<double> dInc(n, 0.0);
+    asmb->forcesDueToIDBC(req, dInc);
+    int its = 0;
+    auto x = asmb->solve(DBCOption::Full, rx, 1e-10, -1, &its);
+    CHECK(its > 0 && x.size() == n);
+  }
+  // The reference's AssemblerManipulator pattern: private base, hooks reached from the derived class, callback
+  // mutates the returned vector (the cantilever anchors apply their point load this way, testcantileverbeam.hh:56-80)
+  {
+    using Manip = TestConcepts::Manipulator<TestAssembler, DBCOption>;
+    Manip m(fes, dv);
+    m.bind(req, elastoStatics, DBCOption::Full);
+    const std::vector<double> plain = m.vector(req, VectorAffordance::forces, DBCOption::Full);
+    m.vf = [](const TestAssembler& a, const HostRequirement& r, DBCOption, std::vector<double>& v) { v[a.size() - 1] -= -r.parameter(); };
+    const std::vector<double>& loaded = m.vector(req, VectorAffordance::forces, DBCOption::Full);
+    CHECK(loaded[n - 1] == plain[n - 1] + req.lambda);
+    m.mf = [](const TestAssembler&, const HostRequirement&, DBCOption, HostSparseMatrix& K) { K.values[0] += 1.0; };
+    const double k00 = m.matrix(req, MatrixAffordance::stiffness, DBCOption::Raw).values[0];
+    m.mf          = nullptr;
+    CHECK(k00 == m.matrix(req, MatrixAffordance::stiffness, DBCOption::Raw).values[0] + 1.0);
+    CHECK(std::isfinite(m.scalar(req, ScalarAffordance::mechanicalPotentialEnergy)));
   }
 
   // Newton iteration with the device PCG callable, as NewtonRaphson::solve does (newtonraphson.hh:196-257)
