@@ -71,6 +71,8 @@ SYMBOLS = {
     "ikb_comm_init": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "ikb_halo_intervals": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ikb_halo_exchange": [C.c_void_p, C.c_char_p],
+    "ikb_comm_ipc_export": [C.c_void_p, C.c_void_p],
+    "ikb_comm_ipc_import": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ikb_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
     "ikb_sync": [C.c_void_p],
     "ikb_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],

@@ -15,6 +15,7 @@
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
 #include "ikb_pcg.cuh"
+#include "ikb_pcg_peer.cuh"
 #include "ikb_results.cuh"
 
 using namespace ikb;
@@ -757,7 +758,84 @@ int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int 
   double rr = bb;
   const double threshold = std::max(relTol * relTol * bb, 1e-300);
   (void)threshold;
-  if (bb > 0.0) {
+  if (bb > 0.0 && h->peerReady) {
+    // Peer-memory transport (ikb_pcg_peer.cuh): halo stores and partial sums go straight into the neighbours' memory
+    // from inside the three kernels of an iteration; batches are replayed from a CUDA graph.
+    if ((rc = haloExchange(h, h->cgPglob.p))) return rc;  // initial direction (NCCL, once)
+    if (!h->peerState.p) IKB_CUDA(h, h->peerState.alloc(256));
+    PeerState* st = reinterpret_cast<PeerState*>(h->peerState.p);
+    const PeerComm& PC = *reinterpret_cast<const PeerComm*>(h->peerCommHost);
+    h->peerEpoch++;
+    peer_init_kernel<<<1, 1, 0, h->stream>>>(st, scal + 0, scal + 4, relTol, maxIt, h->peerEpoch);
+    IKB_LAUNCH_CHECK(h);
+    const PatternView P = h->view();
+    if (h->peerFirstInterior < 0) {
+      DevBuf<int32_t> fe;
+      IKB_CUDA(h, fe.alloc(2));
+      const int32_t init[2] = {0, (int32_t)P.nRowNodes};
+      IKB_CUDA(h, cudaMemcpyAsync(fe.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+      peer_boundary_rows_kernel<<<gridFor(P.nRowNodes, tpb), tpb, 0, h->stream>>>(P, h->rowEnd, fe.p, fe.p + 1);
+      IKB_LAUNCH_CHECK(h);
+      int32_t out[2];
+      IKB_CUDA(h, cudaMemcpyAsync(out, fe.p, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (out[0] > out[1]) out[0] = out[1] = 0;  // every row may touch the halo: no interior phase
+      h->peerFirstInterior = out[0];
+      h->peerEndInterior = out[1];
+      fe.release();
+    }
+    double* pqPartial = h->scratch.p;
+    double* rzPartial = h->scratch.p + MAX_SPMV_BLOCKS;
+    PeerState* hs = reinterpret_cast<PeerState*>(h->hostScal);
+    const int batch = 32;
+    auto enqueueBatch = [&]() {
+      for (int b = 0; b < batch; ++b) {
+        if (h->dim == 3)
+          peer_spmv_kernel<3><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p, pqPartial,
+                                                                     st, PC, h->peerWin.p, h->peerFirstInterior,
+                                                                     h->peerEndInterior);
+        else
+          peer_spmv_kernel<2><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgPglob.p, h->cgQ.p, p, pqPartial,
+                                                                     st, PC, h->peerWin.p, h->peerFirstInterior,
+                                                                     h->peerEndInterior);
+        peer_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, PC, h->peerWin.p, p, h->cgQ.p, h->cgDinv.p, h->cgX.p,
+                                                              h->cgR.p, h->cgZ.p, rzPartial);
+        peer_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, off, st, PC, h->peerWin.p, h->cgZ.p, h->cgPglob.p);
+      }
+    };
+    if (!h->peerGraph || h->peerGraphKey[0] != h->vals[dbc].p || h->peerGraphKey[1] != h->cgPglob.p) {
+      if (h->peerGraph) cudaGraphExecDestroy(h->peerGraph);
+      h->peerGraph = nullptr;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueueBatch();
+        if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
+          if (cudaGraphInstantiate(&h->peerGraph, graph, 0) != cudaSuccess) h->peerGraph = nullptr;
+          cudaGraphDestroy(graph);
+        }
+      }
+      cudaGetLastError();
+      h->peerGraphKey[0] = h->vals[dbc].p;
+      h->peerGraphKey[1] = h->cgPglob.p;
+    }
+    static_assert(sizeof(PeerState) <= 16 * sizeof(double), "hostScal holds the state");
+    while (true) {
+      if (h->peerGraph) {
+        IKB_CUDA(h, cudaGraphLaunch(h->peerGraph, h->stream));
+      } else {
+        enqueueBatch();
+      }
+      h->launches += 3 * batch;
+      IKB_CUDA(h, cudaGetLastError());
+      IKB_CUDA(h, cudaMemcpyAsync(hs, st, sizeof(PeerState), cudaMemcpyDeviceToHost, h->stream));
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (hs->timeout) return fail(h, IKB_ENCCL, "distributed PCG: a peer did not arrive (peer-memory wait timed out)");
+      if (hs->done || hs->iter >= maxIt) break;
+    }
+    it = hs->iter;
+    rr = hs->rr;
+    if (hs->done == 2) return fail(h, IKB_ECUDA, "PCG produced NaN (matrix not positive definite?)");
+  } else if (bb > 0.0) {
     // No host round trip per iteration: convergence is decided on the device from the all-reduced |r|^2 (identical
     // on every rank, so all ranks stop at the same iteration); NCCL calls are stream ordered.  The host looks at the
     // 48-byte state once per batch; iterations enqueued after convergence are no-ops apart from the (harmless)
@@ -873,6 +951,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   if (const char* mb = std::getenv("IKB_H8_MINB")) h->h8MinBlocks = std::atoi(mb);
   if (const char* fu = std::getenv("IKB_FUSED")) h->fusedEnabled = std::atoi(fu) != 0;
   h->sweepDebug = std::getenv("IKB_SWEEP_DEBUG") != nullptr;
+  if (const char* pp = std::getenv("IKB_PCG_PEER")) h->peerEnabled = std::atoi(pp) != 0;
   if (const char* sm = std::getenv("IKB_SWEEP_MARGIN")) h->sweepMargin = std::atoi(sm);  // test hook: 0 = smallest legal ring
   if (const char* sc = std::getenv("IKB_SWEEP_CTAS")) {
     int a = 0, b = 0;
@@ -941,6 +1020,11 @@ int ikb_destroy(ikb_handle hh) {
   h->redInner.release();
   h->redOuter.release();
   h->errFlag.release();
+  for (void* pp : h->peerOpened) cudaIpcCloseMemHandle(pp);
+  if (h->peerGraph) cudaGraphExecDestroy(h->peerGraph);
+  delete reinterpret_cast<PeerComm*>(h->peerCommHost);
+  h->peerWin.release();
+  h->peerState.release();
   if (h->comm) nccl().commDestroy(h->comm);
   h->cgPglob.release();
   h->cgState.release();
@@ -2190,6 +2274,95 @@ int ikb_comm_init(ikb_handle hh, const void* id128, int rank, int nranks) {
   IKB_CUDA(h, cudaStreamSynchronize(h->stream));
   mine.release();
   all.release();
+  return IKB_OK;
+}
+
+int ikb_comm_ipc_export(ikb_handle hh, void* handles128) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (!handles128) return fail(h, IKB_EINVAL, "null handle buffer");
+  if (!h->comm) return fail(h, IKB_ESTATE, "ikb_comm_init first");
+  if (!h->peerEnabled || h->nranks > PEER_MAXR) return fail(h, IKB_ENOTIMPL, "peer-memory transport disabled or too many ranks");
+  if (h->cgPglob.n < (size_t)h->nDof) {
+    IKB_CUDA(h, h->cgPglob.alloc((size_t)h->nDof));
+    IKB_CUDA(h, cudaMemsetAsync(h->cgPglob.p, 0, h->cgPglob.bytes(), h->stream));
+  }
+  if (!h->peerWin.p) {
+    IKB_CUDA(h, h->peerWin.alloc(256));
+    IKB_CUDA(h, cudaMemsetAsync(h->peerWin.p, 0, h->peerWin.bytes(), h->stream));
+  }
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaIpcMemHandle_t hp, hw;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  IKB_CUDA(h, cudaIpcGetMemHandle(&hp, h->cgPglob.p));
+  IKB_CUDA(h, cudaIpcGetMemHandle(&hw, h->peerWin.p));
+  std::memcpy(handles128, &hp, 64);
+  std::memcpy(static_cast<char*>(handles128) + 64, &hw, 64);
+  return IKB_OK;
+}
+
+static void closePeers(Handle* h) {
+  for (void* p : h->peerOpened) cudaIpcCloseMemHandle(p);
+  h->peerOpened.clear();
+  h->peerReady = false;
+  if (h->peerGraph) cudaGraphExecDestroy(h->peerGraph);
+  h->peerGraph = nullptr;
+}
+
+int ikb_comm_ipc_import(ikb_handle hh, const void* all, int* ok) {
+  Handle* h = H(hh);
+  if (checkHandle(h)) return IKB_EINVAL;
+  if (ok) *ok = 0;
+  closePeers(h);
+  if (!all) return IKB_OK;  // back to the NCCL transport
+  if (!h->comm || !h->peerWin.p || h->nranks > PEER_MAXR) return fail(h, IKB_ESTATE, "ikb_comm_ipc_export first");
+  if (!h->peerCommHost) h->peerCommHost = new PeerComm();
+  PeerComm& PC = *reinterpret_cast<PeerComm*>(h->peerCommHost);
+  std::memset(&PC, 0, sizeof(PC));
+  PC.rank = h->rank;
+  PC.nranks = h->nranks;
+  const char* rec = static_cast<const char*>(all);
+  for (int s = 0; s < h->nranks; ++s) {
+    if (s == h->rank) {
+      PC.peerP[s] = h->cgPglob.p;
+      PC.peerW[s] = h->peerWin.p;
+      continue;
+    }
+    cudaIpcMemHandle_t hp, hw;
+    std::memcpy(&hp, rec + (size_t)s * 128, 64);
+    std::memcpy(&hw, rec + (size_t)s * 128 + 64, 64);
+    void *pp = nullptr, *pw = nullptr;
+    if (cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pw, hw, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      if (pp) cudaIpcCloseMemHandle(pp);
+      closePeers(h);
+      return IKB_OK;  // *ok stays 0: the caller falls back to NCCL on every rank
+    }
+    h->peerOpened.push_back(pp);
+    h->peerOpened.push_back(pw);
+    PC.peerP[s] = static_cast<double*>(pp);
+    PC.peerW[s] = static_cast<unsigned long long*>(pw);
+  }
+  // who reads which of my rows, and whose rows my boundary rows read
+  const int D = h->dim;
+  const int64_t* me = h->peerRanges.data() + 4 * h->rank;
+  for (int s = 0; s < h->nranks; ++s) {
+    if (s == h->rank) continue;
+    const int64_t* pr = h->peerRanges.data() + 4 * s;
+    int64_t sb, se, rb, re;
+    haloIntervals(me[0], me[1], me[2], me[3], pr[0], pr[1], pr[2], pr[3], sb, se, rb, re);
+    if (se > sb) {
+      PC.sendPeer[PC.nSend] = s;
+      PC.sendBegin[PC.nSend] = (long long)D * sb;
+      PC.sendEnd[PC.nSend] = (long long)D * se;
+      PC.nSend++;
+    }
+    if (re > rb) PC.recvPeer[PC.nRecv++] = s;
+  }
+  h->peerFirstInterior = h->peerEndInterior = -1;
+  h->peerReady = true;
+  if (ok) *ok = 1;
   return IKB_OK;
 }
 

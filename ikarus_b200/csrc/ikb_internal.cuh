@@ -186,6 +186,17 @@ struct Handle {
   int64_t colBegin = 0, colEnd = 0;          // node range touched by the uploaded elements (owned + ghost)
   std::vector<int64_t> peerRanges;           // [nranks][4] = ownBegin, ownEnd, needBegin, needEnd (nodes)
   DevBuf<double> cgPglob;                    // search direction, global length (owned + halo filled)
+  // peer-memory transport of the distributed PCG (ikb_pcg_peer.cuh)
+  bool peerReady = false;
+  bool peerEnabled = true;                   // IKB_PCG_PEER=0: NCCL transport
+  DevBuf<unsigned long long> peerWin;        // my control window (exported by IPC)
+  std::vector<void*> peerOpened;             // pointers opened with cudaIpcOpenMemHandle (closed on destroy)
+  void* peerCommHost = nullptr;              // PeerComm (host copy, passed by value to the kernels)
+  unsigned long long peerEpoch = 0;
+  int64_t peerFirstInterior = -1, peerEndInterior = -1;
+  DevBuf<uint8_t> peerState;
+  cudaGraphExec_t peerGraph = nullptr;
+  const void* peerGraphKey[2] = {nullptr, nullptr};
 
   PatternView view() const {
     PatternView P;

@@ -77,6 +77,83 @@ __global__ void cg2_init_kernel(CgState* st, const double* rzDev, const double* 
   *arrive = 0u;
 }
 
+// One node-row of y = A x: the D scalar rows of node g share their column set.  Leaves the row sums in lane 0.
+// COHERENT: x entries may have been written by another GPU while this kernel runs (halo of a row-block partition):
+// read them from L2 (ld.global.cg) instead of through the non-coherent path.
+template <int D, bool COHERENT>
+__device__ __forceinline__ void spmvNodeRow(const PatternView& P, const double* __restrict__ vals, const double* x,
+                                            int64_t g, int lane, double (&s)[D]) {
+  const int32_t b0 = P.nbrPtr[g];
+  const int nnb = P.nbrPtr[g + 1] - b0;
+  const int len = nnb * D;
+  int64_t start[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    s[i] = 0.0;
+    start[i] = rawRowStart(P, g, i, nnb);
+  }
+  auto loadX = [&](int64_t dof) -> double { return COHERENT ? __ldcg(x + dof) : __ldg(x + dof); };
+  if (nnb <= 32) {
+    // Fast path (rows of up to 96 entries: every Q1 mesh).  The column nodes of the node-row come from ONE coalesced
+    // load and are handed out by shuffle, and the lane passes are unrolled, so all matrix loads and x gathers of the
+    // node-row are in flight together instead of one dependent index -> x chain per pass.  Same per-lane summation
+    // order as the generic loop below.
+    constexpr int U = 3;
+    const int32_t myCol = lane < nnb ? __ldg(P.nbrIdx + b0 + lane) : 0;
+    double av[U][D], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = lane + 32 * u;
+      const bool valid = j < len;
+#pragma unroll
+      for (int i = 0; i < D; ++i) av[u][i] = valid ? __ldcs(vals + start[i] + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      xv[u] = 0.0;
+      if (32 * u < len) {  // warp-uniform
+        const int j = lane + 32 * u;
+        const bool valid = j < len;
+        int slot, k;
+        if (P.layout == LAYOUT_INTERLEAVED) {
+          slot = j / D;
+          k = j - slot * D;
+        } else {
+          k = j / nnb;
+          slot = j - k * nnb;
+        }
+        const int32_t col = __shfl_sync(0xffffffffu, myCol, valid ? slot : 0);
+        if (valid) xv[u] = loadX(dofOf(P.layout, D, P.nNodes, col, k));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = fma(av[u][i], xv[u], s[i]);
+  } else
+    for (int j = lane; j < len; j += 32) {
+      int slot, k;
+      if (P.layout == LAYOUT_INTERLEAVED) {
+        slot = j / D;
+        k = j - slot * D;
+      } else {
+        k = j / nnb;
+        slot = j - k * nnb;
+      }
+      // the matrix is streamed exactly once: keep it out of L1 (__ldcs) so the gathered x stays resident there
+      double av[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) av[i] = __ldcs(vals + start[i] + j);
+      const double xv = loadX(dofOf(P.layout, D, P.nNodes, __ldg(P.nbrIdx + b0 + slot), k));
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = fma(av[i], xv, s[i]);
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], w);
+}
+
 template <int D>
 __global__ void __launch_bounds__(256, 6) spmv_node_dot_kernel(PatternView P, const double* __restrict__ vals,
                                                             const double* __restrict__ x, double* __restrict__ y,
@@ -88,75 +165,8 @@ __global__ void __launch_bounds__(256, 6) spmv_node_dot_kernel(PatternView P, co
   const int64_t warpsTotal = (int64_t)gridDim.x * 8;
   double dot = 0.0;
   for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < P.nRowNodes; g += warpsTotal) {
-    const int32_t b0 = P.nbrPtr[g];
-    const int nnb = P.nbrPtr[g + 1] - b0;
-    const int len = nnb * D;
     double s[D];
-    int64_t start[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      s[i] = 0.0;
-      start[i] = rawRowStart(P, g, i, nnb);
-    }
-    if (nnb <= 32) {
-      // Fast path (rows of up to 96 entries: every Q1 mesh).  The column nodes of the node-row come from ONE coalesced
-      // load and are handed out by shuffle, and the lane passes are unrolled, so all matrix loads and x gathers of the
-      // node-row are in flight together instead of one dependent index -> x chain per pass.  Same per-lane summation
-      // order as the generic loop below.
-      constexpr int U = 3;
-      const int32_t myCol = lane < nnb ? __ldg(P.nbrIdx + b0 + lane) : 0;
-      double av[U][D], xv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = lane + 32 * u;
-        const bool valid = j < len;
-#pragma unroll
-        for (int i = 0; i < D; ++i) av[u][i] = valid ? __ldcs(vals + start[i] + j) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        xv[u] = 0.0;
-        if (32 * u < len) {  // warp-uniform
-          const int j = lane + 32 * u;
-          const bool valid = j < len;
-          int slot, k;
-          if (P.layout == LAYOUT_INTERLEAVED) {
-            slot = j / D;
-            k = j - slot * D;
-          } else {
-            k = j / nnb;
-            slot = j - k * nnb;
-          }
-          const int32_t col = __shfl_sync(0xffffffffu, myCol, valid ? slot : 0);
-          if (valid) xv[u] = __ldg(x + dofOf(P.layout, D, P.nNodes, col, k));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int i = 0; i < D; ++i) s[i] = fma(av[u][i], xv[u], s[i]);
-    } else
-      for (int j = lane; j < len; j += 32) {
-        int slot, k;
-        if (P.layout == LAYOUT_INTERLEAVED) {
-          slot = j / D;
-          k = j - slot * D;
-        } else {
-          k = j / nnb;
-          slot = j - k * nnb;
-        }
-        // the matrix is streamed exactly once: keep it out of L1 (__ldcs) so the gathered x stays resident there
-        double av[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) av[i] = __ldcs(vals + start[i] + j);
-        const double xv = __ldg(x + dofOf(P.layout, D, P.nNodes, __ldg(P.nbrIdx + b0 + slot), k));
-#pragma unroll
-        for (int i = 0; i < D; ++i) s[i] = fma(av[i], xv, s[i]);
-      }
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int w = 16; w > 0; w >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], w);
+    spmvNodeRow<D, false>(P, vals, x, g, lane, s);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < D; ++i) {

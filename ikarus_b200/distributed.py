@@ -25,7 +25,7 @@ def halo_intervals(mine, peer):
     return tuple(int(v) for v in out)
 
 
-def init_communicator(asm: SparseFlatAssembler, dist):
+def init_communicator(asm: SparseFlatAssembler, dist, peer_memory=True):
     """Create the library's NCCL communicator: rank 0 makes the id, torch.distributed broadcasts it."""
     import torch
 
@@ -41,6 +41,37 @@ def init_communicator(asm: SparseFlatAssembler, dist):
     dist.broadcast(t, 0)
     buf = t.cpu().numpy().copy()
     asm._check(asm._lib.ikb_comm_init(asm._h, capi.ptr(buf), rank, world))
+    if peer_memory and world <= 8:
+        _open_peer_memory(asm, dist, rank, world)
+
+
+def _open_peer_memory(asm, dist, rank, world):
+    """All-gather the CUDA IPC handles of every rank's search-direction vector and control window, so that the PCG
+    kernels can store halo entries and partial sums straight into the neighbours' memory over NVLink."""
+    import torch
+
+    mine = np.zeros(128, dtype=np.uint8)
+    ok_local = asm._lib.ikb_comm_ipc_export(asm._h, capi.ptr(mine)) == 0
+    dev = dist.get_backend() == "nccl"
+    t = torch.from_numpy(mine)
+    t = t.cuda() if dev else t
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    flag = torch.tensor([1 if ok_local else 0], dtype=torch.int32)
+    flag = flag.cuda() if dev else flag
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return False
+    allh = np.concatenate([g.cpu().numpy() for g in gathered]).astype(np.uint8)
+    ok = C.c_int(0)
+    asm._check(asm._lib.ikb_comm_ipc_import(asm._h, capi.ptr(allh), C.byref(ok)))
+    flag = torch.tensor([ok.value], dtype=torch.int32)
+    flag = flag.cuda() if dev else flag
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:  # some rank could not open a peer: everybody stays on the NCCL transport
+        asm._check(asm._lib.ikb_comm_ipc_import(asm._h, None, C.byref(ok)))
+        return False
+    return True
 
 
 class DistributedNewton:

@@ -220,6 +220,14 @@ int ikb_comm_init(ikb_handle h, const void* id128, int rank, int nranks);
 int ikb_halo_intervals(const int64_t* mine4, const int64_t* peer4, int64_t* out4);
 /* exchange the interface node layers of a global-length resident array ("solution" | "correction") */
 int ikb_halo_exchange(ikb_handle h, const char* what);
+/* Peer-memory transport of the distributed PCG (one process per GPU on one NVLink/NVSwitch node; new, the reference
+ * has no distributed code).  After ikb_comm_init every rank exports two CUDA IPC handles (its search-direction
+ * vector and its control window, 64 bytes each), the caller all-gathers the 128-byte records of all ranks in rank order
+ * and hands them to every rank.  The PCG then stores halo entries and partial dot products directly into the peers'
+ * memory from inside its kernels: no NCCL call and no host round trip per iteration.  Optional: without it (or when
+ * `ok` comes back 0 because IPC is unavailable) ikb_pcg_solve uses ncclSend/Recv + ncclAllReduce. */
+int ikb_comm_ipc_export(ikb_handle h, void* handles128 /* 128 bytes */);
+int ikb_comm_ipc_import(ikb_handle h, const void* all_handles /* nranks x 128 bytes */, int* ok);
 
 /* ---- introspection for benchmarks ------------------------------------------------ */
 int ikb_stream(ikb_handle h, void** cuda_stream);

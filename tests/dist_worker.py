@@ -145,6 +145,26 @@ def run_nccl():
         single._check(single._lib.ikb_get_scalar(single._h, C.byref(es)))
         part._check(part._lib.ikb_get_scalar(part._h, C.byref(ep)))
         assert abs(es.value - ep.value) <= 1e-12 * abs(es.value), (es.value, ep.value)
+    # the two transports of the distributed PCG (NVLink peer memory: no NCCL inside the iteration; NCCL send/recv +
+    # all-reduce) solve the same system: same iteration count up to the last-digit difference of the summation order
+    # of the dot products, same solution
+    part_nccl = make(slab, (slab.node_begin, slab.node_end))
+    ikd.init_communicator(part_nccl, dist, peer_memory=False)
+    sols, its = [], []
+    for a in (part, part_nccl):
+        a._check(a._lib.ikb_set_solution(a._h, capi.ptr(d)))
+        a._check(a._lib.ikb_set_parameter(a._h, 0.4))
+        a._check(a._lib.ikb_assemble(a._h, capi.MATRIX | capi.VECTOR, capi.DBC_FULL))
+        x = np.zeros(hi - lo)
+        it, rel = C.c_int(), C.c_double()
+        for _ in range(2):  # twice: the second solve runs on a new epoch of the peer windows
+            a._check(a._lib.ikb_pcg_solve(a._h, capi.DBC_FULL, None, capi.ptr(x), 1e-12, 5000, C.byref(it), C.byref(rel)))
+        assert rel.value <= 1e-12 and it.value > 5
+        sols.append(x.copy())
+        its.append(it.value)
+    assert abs(its[0] - its[1]) <= 2, its
+    assert np.abs(sols[0] - sols[1]).max() <= 1e-9 * np.abs(sols[1]).max()
+    del part_nccl
     # Newton on both: identical iteration counts, same solution
     z = np.zeros(n)
     for a in (single, part):
