@@ -1044,6 +1044,8 @@ int ikb_destroy(ikb_handle hh) {
   if (h->evSweepJoin) cudaEventDestroy(h->evSweepJoin);
   h->gatherTab.release();
   if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
+  if (h->tcgGraph) cudaGraphExecDestroy(h->tcgGraph);
+  h->tcgState.release();
   h->T0inv.release();
   if (h->hostScal) cudaFreeHost(h->hostScal);
   if (h->evVec) cudaEventDestroy(h->evVec);
@@ -2002,6 +2004,8 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
     if (!h->cgGraph || h->cgGraphKey[0] != h->vals[dbc].p || h->cgGraphKey[1] != h->cgP.p ||
         h->cgGraphKey[2] != h->nbrIdx.p) {
       if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
+  if (h->tcgGraph) cudaGraphExecDestroy(h->tcgGraph);
+  h->tcgState.release();
       h->cgGraph = nullptr;
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -2136,7 +2140,69 @@ int ikb_tcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, ikb_tcg_
   bool solved = rhsNorm <= tiny;  // x = 0 (:87-92)
   const double threshold = std::max(tol * tol * rhsNorm * rhsNorm, tiny);
   if (!solved && resNorm * resNorm < threshold) solved = true;  // :94-99
-  if (!solved) {
+  if (dbc == IKB_DBC_FULL && !solved) {
+    // Sync-free path (tcg2_* kernels): the whole loop of the reference, stopping rules included, runs on the device;
+    // batches of iterations are replayed from a CUDA graph and the host reads the state once per batch.
+    if (!h->tcgState.p) IKB_CUDA(h, h->tcgState.alloc(256));
+    TcgState* st = reinterpret_cast<TcgState*>(h->tcgState.p);
+    tcg2_init_kernel<<<1, 1, 0, h->stream>>>(st, scal + 0, scal + 0, tol, Delta, info->kappa, info->mininner,
+                                             (long long)maxIters, IKB_TCG_MAXIMUM_INNER_ITERATIONS);
+    IKB_LAUNCH_CHECK(h);
+    const PatternView P = h->view();
+    double* pqPartial = h->scratch.p;
+    double* rzPartial = h->scratch.p + MAX_SPMV_BLOCKS;
+    const int batch = 16;
+    const long long maxItersLL = (long long)maxIters;
+    auto enqueueBatch = [&]() {
+      for (int b = 0; b < batch; ++b) {
+        if (h->dim == 3)
+          spmv_node_dot_kernel<3><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                        pqPartial, &st->cg);
+        else
+          spmv_node_dot_kernel<2><<<h->spmvBlocks, tpb, 0, h->stream>>>(P, h->vals[dbc].p, h->cgP.p, h->cgQ.p, h->cgP.p,
+                                                                        pqPartial, &st->cg);
+        tcg2_update_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, pqPartial, h->spmvBlocks, h->cgP.p, h->cgQ.p,
+                                                              h->cgDinv.p, h->cgX.p, h->cgR.p, h->cgZ.p, rzPartial);
+        tcg2_direction_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, st, rzPartial, RED_BLOCKS, maxItersLL, h->cgZ.p,
+                                                                 h->cgP.p);
+      }
+    };
+    if (!h->tcgGraph || h->tcgGraphKey[0] != h->vals[dbc].p || h->tcgGraphKey[1] != h->cgP.p ||
+        h->tcgGraphKey[2] != h->nbrIdx.p || h->tcgGraphMaxIters != maxItersLL) {
+      if (h->tcgGraph) cudaGraphExecDestroy(h->tcgGraph);
+      h->tcgGraph = nullptr;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueueBatch();
+        if (cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && graph) {
+          if (cudaGraphInstantiate(&h->tcgGraph, graph, 0) != cudaSuccess) h->tcgGraph = nullptr;
+          cudaGraphDestroy(graph);
+        }
+      }
+      cudaGetLastError();
+      h->tcgGraphKey[0] = h->vals[dbc].p;
+      h->tcgGraphKey[1] = h->cgP.p;
+      h->tcgGraphKey[2] = h->nbrIdx.p;
+      h->tcgGraphMaxIters = maxItersLL;
+    }
+    TcgState hsT;
+    while (true) {
+      if (h->tcgGraph) {
+        IKB_CUDA(h, cudaGraphLaunch(h->tcgGraph, h->stream));
+      } else {
+        enqueueBatch();
+      }
+      h->launches += 3 * batch;
+      IKB_CUDA(h, cudaGetLastError());
+      IKB_CUDA(h, cudaMemcpyAsync(&hsT, st, sizeof(TcgState), cudaMemcpyDeviceToHost, h->stream));
+      IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (hsT.cg.done) break;
+    }
+    if (hsT.cg.done == 2) return fail(h, IKB_ECUDA, "tCG produced NaN");
+    i = hsT.i;
+    stop = hsT.stop;
+    resNorm = std::sqrt(hsT.cg.rr);
+  } else if (!solved) {
     double e_Pd = 0.0, e_Pe = 0.0, d_Pd = absNew;
     double* partial = h->scratch.p + MAX_SPMV_BLOCKS;
     i = 1;

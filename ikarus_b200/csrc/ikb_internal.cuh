@@ -179,6 +179,10 @@ struct Handle {
   DevBuf<uint8_t> cgState;     // CgState + arrival counter of the sync-free PCG
   cudaGraphExec_t cgGraph = nullptr;  // one captured batch of PCG iterations
   const void* cgGraphKey[3] = {nullptr, nullptr, nullptr};
+  DevBuf<uint8_t> tcgState;           // TcgState of the sync-free truncated CG
+  cudaGraphExec_t tcgGraph = nullptr;
+  const void* tcgGraphKey[3] = {nullptr, nullptr, nullptr};
+  long long tcgGraphMaxIters = -1;
 
   // NCCL (element-partitioned runs)
   void* comm = nullptr;

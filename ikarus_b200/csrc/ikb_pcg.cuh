@@ -481,6 +481,156 @@ __global__ void __launch_bounds__(256) tcg_update_kernel(int64_t n, double alpha
   }
 }
 // p = z + beta p
+// ---------------------------------------------------------------------------------------------------
+// Sync-free Steihaug-Toint truncated CG (linearalgebra/truncatedconjugategradient.hh:68-168 of the reference) in the
+// style of the cg2_* kernels: three kernels per iteration, every decision of the reference's loop (negative curvature,
+// trust-region boundary, kappa/theta rule, residual threshold, iteration cap) taken on the device from sums that every
+// block folds in the same order; the host reads the state once per batch of iterations.
+struct TcgState {
+  CgState cg;  // rz[0] = absNew (r.z), rr = |r|^2, threshold, iter = completed CG steps, done, maxIter (read by the SpMV)
+  double e_Pd, e_Pe, d_Pd, alpha, rhsNorm, Delta, kappa;
+  int stop, mininner, i, pad;  // i = the reference's loop counter (starts at 1)
+  unsigned int arrive[2];
+};
+
+__global__ void tcg2_init_kernel(TcgState* st, const double* absNewDev, const double* bbDev, double tol, double Delta,
+                                 double kappa, int mininner, long long maxIters, int stopInit) {
+  const double tiny = 2.2250738585072014e-308;
+  const double rhsNorm = sqrt(bbDev[1]);
+  st->cg.rz[0] = absNewDev[0];
+  st->cg.rz[1] = 0.0;
+  st->cg.rr = bbDev[1];
+  const double thr = tol * tol * rhsNorm * rhsNorm;
+  st->cg.threshold = thr > tiny ? thr : tiny;
+  st->cg.iter = 0;
+  st->cg.maxIter = 0x7fffffff;
+  st->e_Pd = 0.0;
+  st->e_Pe = 0.0;
+  st->d_Pd = absNewDev[0];
+  st->alpha = 0.0;
+  st->rhsNorm = rhsNorm;
+  st->Delta = Delta;
+  st->kappa = kappa;
+  st->stop = stopInit;
+  st->mininner = mininner;
+  st->arrive[0] = st->arrive[1] = 0u;
+  // x = 0 solves it (:87-99: zero iterations), or the loop condition 1 < maxIters fails at once
+  const bool solved = rhsNorm <= tiny || rhsNorm * rhsNorm < st->cg.threshold;
+  st->i = solved ? 0 : 1;
+  st->cg.done = (solved || maxIters <= 1) ? 1 : 0;
+}
+
+// d_Hd = fold(p.q); either the boundary step x += tau p (negative curvature / trust region exceeded, :122-134) or
+// x += alpha p, r -= alpha q, z = Minv r with the block partials of r.z and r.r
+__global__ void __launch_bounds__(256, 4)
+    tcg2_update_kernel(int64_t n, TcgState* st, const double* __restrict__ pqPartial, int npq, const double* __restrict__ p,
+                       const double* __restrict__ q, const double* __restrict__ minv, double* x, double* r, double* z,
+                       double* partial) {
+  if (st->cg.done) return;
+  __shared__ double sh[256];
+  __shared__ double sh1[256];
+  const double d_Hd = blockFold(pqPartial, npq, sh);
+  const double absNew = st->cg.rz[0];
+  const double alpha = absNew / d_Hd;
+  const double e_Pd = st->e_Pd, e_Pe = st->e_Pe, d_Pd = st->d_Pd, Delta = st->Delta;
+  const double e_Pe_new = e_Pe + 2.0 * alpha * e_Pd + alpha * alpha * d_Pd;
+  const bool boundary = d_Hd <= 0 || e_Pe_new >= Delta * Delta;
+  const double step = boundary ? (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta * Delta - e_Pe))) / d_Pd : alpha;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(step, p[i], x[i]);
+    if (!boundary) {
+      const double ri = fma(-alpha, q[i], r[i]);
+      r[i] = ri;
+      const double zi = minv[i] * ri;
+      z[i] = zi;
+      s0 = fma(ri, zi, s0);
+      s1 = fma(ri, ri, s1);
+    }
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, w);
+    s1 += __shfl_down_sync(0xffffffffu, s1, w);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = s0;
+    sh1[threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t0 += sh[w];
+      t1 += sh1[w];
+    }
+    partial[blockIdx.x] = t0;
+    partial[gridDim.x + blockIdx.x] = t1;
+    __threadfence();
+    if (atomicAdd(&st->arrive[0], 1u) == gridDim.x - 1) {  // everybody has read the old state
+      st->arrive[0] = 0u;
+      st->alpha = alpha;
+      if (boundary) {
+        st->stop = d_Hd <= 0 ? 0 /* NEGATIVE_CURVATURE */ : 1 /* EXCEEDED_TRUST_REGION */;
+        __threadfence();
+        st->cg.done = 1;
+      } else {
+        st->e_Pe = e_Pe_new;
+      }
+    }
+  }
+}
+
+// stopping rules after the residual update (:142-151), then beta, the recurrences of e_Pd / d_Pd and p = z + beta p
+__global__ void __launch_bounds__(256)
+    tcg2_direction_kernel(int64_t n, TcgState* st, const double* __restrict__ partial, int np, long long maxIters,
+                          const double* __restrict__ z, double* p) {
+  if (st->cg.done) return;
+  __shared__ double sh[256];
+  const double absNewNext = blockFold(partial, np, sh);
+  const double rr = blockFold(partial + np, np, sh);
+  const double resNorm = sqrt(rr);
+  const int i = st->i;
+  const double rhsNorm = st->rhsNorm, kappa = st->kappa;
+  int stopNow = -1;  // -1: continue
+  if (!(resNorm == resNorm))
+    stopNow = 100;  // NaN
+  else if (i >= st->mininner && resNorm <= rhsNorm * fmin(rhsNorm, kappa))
+    stopNow = kappa < rhsNorm ? 2 /* REACHED_KAPPA_LINEAR */ : 3 /* REACHED_THETA_SUPERLINEAR */;
+  else if (resNorm < st->cg.threshold)  // the reference compares the NORM with the squared-norm threshold (:151)
+    stopNow = st->stop;
+  const double absOld = st->cg.rz[0];
+  const double beta = absNewNext / absOld;
+  if (stopNow < 0) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+      p[k] = fma(beta, p[k], z[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&st->arrive[1], 1u) == gridDim.x - 1) {
+      st->arrive[1] = 0u;
+      st->cg.rr = rr;
+      if (stopNow >= 0) {
+        st->stop = stopNow;
+        __threadfence();
+        st->cg.done = stopNow == 100 ? 2 : 1;
+      } else {
+        const double alpha = st->alpha, d_Pd = st->d_Pd;
+        st->e_Pd = beta * (st->e_Pd + alpha * d_Pd);
+        st->d_Pd = absNewNext + beta * beta * d_Pd;
+        st->cg.rz[0] = absNewNext;
+        st->cg.iter = st->cg.iter + 1;
+        st->i = i + 1;
+        if ((long long)(i + 1) >= maxIters) {
+          __threadfence();
+          st->cg.done = 1;  // loop condition i < maxIters (:113)
+        }
+      }
+    }
+  }
+}
+
 __global__ void tcg_direction_kernel(int64_t n, double beta, const double* __restrict__ z, double* p) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = fma(beta, p[i], z[i]);
