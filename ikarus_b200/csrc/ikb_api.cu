@@ -12,6 +12,7 @@
 #include "ikb_elem_q2.cuh"
 #include "ikb_fused.cuh"
 #include "ikb_gather.cuh"
+#include "ikb_gather_async.cuh"
 #include "ikb_internal.cuh"
 #include "ikb_pattern.cuh"
 #include "ikb_pcg.cuh"
@@ -63,6 +64,25 @@ void joinSolution(Handle* h) {
   h->piecesPending = false;
 }
 
+// the Q1 element kernel of the handle's kind over the element range described by A
+cudaError_t launchQ1Kernel(Handle* h, const ElemArgs& A) {
+  cudaError_t e = cudaErrorInvalidValue;
+  if (h->dim == 3 && h->elemMma && A.Lap && h->form != FORM_SVK) {
+    // Hex8 with the contraction on the FP64 tensor cores (ikb_elem_h8mma.cuh); IKB_ELEM=fma selects the FMA kernel
+    if (h->form == FORM_LE) e = launchElemH8Mma<FORM_LE>(A, h->stream, h->h8MinBlocks);
+    if (h->form == FORM_NH) e = launchElemH8Mma<FORM_NH>(A, h->stream, h->h8MinBlocks);
+  } else if (h->dim == 3) {
+    if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
+    if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
+    if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
+  } else {
+    if (h->form == FORM_LE) e = launchElemQ1<2, FORM_LE>(A, h->stream);
+    if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
+    if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
+  }
+  return e;
+}
+
 int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const double* Uoverride = nullptr,
                    double* alphaOverride = nullptr) {
   ElemArgs A;
@@ -102,19 +122,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
         A.Est = h->Est.p + b;
         if (c) h->launches++;
       }
-      if (h->dim == 3 && h->elemMma && A.Lap && h->form != FORM_SVK) {
-        // Hex8 with the contraction on the FP64 tensor cores (ikb_elem_h8mma.cuh); IKB_ELEM=fma selects the FMA kernel
-        if (h->form == FORM_LE) e = launchElemH8Mma<FORM_LE>(A, h->stream, h->h8MinBlocks);
-        if (h->form == FORM_NH) e = launchElemH8Mma<FORM_NH>(A, h->stream, h->h8MinBlocks);
-      } else if (h->dim == 3) {
-        if (h->form == FORM_LE) e = launchElemQ1<3, FORM_LE>(A, h->stream);
-        if (h->form == FORM_SVK) e = launchElemQ1<3, FORM_SVK>(A, h->stream);
-        if (h->form == FORM_NH) e = launchElemQ1<3, FORM_NH>(A, h->stream);
-      } else {
-        if (h->form == FORM_LE) e = launchElemQ1<2, FORM_LE>(A, h->stream);
-        if (h->form == FORM_SVK) e = launchElemQ1<2, FORM_SVK>(A, h->stream);
-        if (h->form == FORM_NH) e = launchElemQ1<2, FORM_NH>(A, h->stream);
-      }
+      e = launchQ1Kernel(h, A);
       if (e != cudaSuccess) break;
     }
     h->piecesPending = false;
@@ -490,8 +498,26 @@ int launchFused(Handle* h, unsigned what, int dbc) {
   return IKB_OK;
 }
 
-int launchGather(Handle* h, unsigned what, int dbc) {
+// row-pipelined cp.async gather (Q1 kinds, Raw / Full)
+template <int DIM, int MODE, bool IL>
+void launchRowsAsync(Handle* h, const GatherArgs& G, bool idx32, int64_t nRowNodes) {
+  if constexpr (MODE != IKB_DBC_REDUCED) {
+    const unsigned grid = gridFor(nRowNodes, ASYNC_WARPS * ASYNC_ROWS);
+    if (idx32)
+      gather_rows_async_kernel<DIM, MODE, IL, true><<<grid, ASYNC_WARPS * 32, 0, h->stream>>>(G, h->cptr.p, h->csrc.p, h->rowSlow.p);
+    else
+      gather_rows_async_kernel<DIM, MODE, IL, false><<<grid, ASYNC_WARPS * 32, 0, h->stream>>>(G, h->cptr.p, h->csrc.p, h->rowSlow.p);
+  }
+}
+
+// rowFirst/rowEnd/st: a row range of the matrix on another stream (interleaved sweep; pull gather only)
+int launchGather(Handle* h, unsigned what, int dbc, int64_t rowFirst = 0, int64_t rowEnd = -1, cudaStream_t st = nullptr) {
   GatherArgs G = makeGatherArgs(h, what, dbc);
+  G.rowFirst = rowFirst;
+  G.rowEnd = rowEnd;
+  cudaStream_t gst = st ? st : h->stream;
+  const int64_t nRange = (rowEnd < 0 ? (h->rowEnd - h->rowBegin) : rowEnd) - rowFirst;
+  if (nRange <= 0 && !(what & IKB_VECTOR)) return IKB_OK;
   const int rs = h->nn > 8 ? 1 : h->dim;
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   if (h->nBlocks == 0 || nRowNodes == 0) return IKB_OK;
@@ -526,6 +552,17 @@ int launchGather(Handle* h, unsigned what, int dbc) {
     mirror_blocks_kernel<<<gridFor(h->nBlocks, 256), 256, 0, h->stream>>>(G.P, h->mirrorBlk.p);
     IKB_LAUNCH_CHECK(h);
   }
+  // row-pipelined cp.async gather: Q1 kinds, Raw / Full
+  const bool rowsAsync = h->pullAsync && h->gatherPull && h->csrc.p && G.vals && !mirror && h->nn <= 8 && dbc != IKB_DBC_REDUCED;
+  if (rowsAsync && dbc == IKB_DBC_FULL && !h->rowSlowValid) {
+    if (!h->rowSlow.p) IKB_CUDA(h, h->rowSlow.alloc((size_t)nRowNodes));
+    if (h->layout == LAYOUT_INTERLEAVED)
+      row_slow_kernel<true><<<gridFor(nRowNodes, 256), 256, 0, h->stream>>>(G.P, G.flags, h->rowSlow.p);
+    else
+      row_slow_kernel<false><<<gridFor(nRowNodes, 256), 256, 0, h->stream>>>(G.P, G.flags, h->rowSlow.p);
+    IKB_LAUNCH_CHECK(h);
+    h->rowSlowValid = true;
+  }
   G.rowDiag = h->rowDiag.p;
   G.rowLowEnd = h->rowLowEnd.p;
   G.mirrorBlk = h->mirrorBlk.p;
@@ -544,17 +581,19 @@ int launchGather(Handle* h, unsigned what, int dbc) {
     }                                                                                                                \
     if (G.vals && h->gatherPull && h->csrc.p) {                                                                      \
       constexpr bool canMirror = MODE != IKB_DBC_REDUCED;                                                            \
-      if (canMirror && mirror && idx32)                                                                              \
-        gather_pull_kernel<DIM, MODE, IL, true, canMirror><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(      \
+      if (rowsAsync && NN <= 8)                                                                                      \
+        launchRowsAsync<DIM, MODE, IL>(h, G, idx32, nRowNodes);                                                      \
+      else if (canMirror && mirror && idx32)                                                                         \
+        gather_pull_kernel<DIM, MODE, IL, true, canMirror><<<gridFor(nRange, pw), pw * 32, 0, gst>>>(      \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else if (canMirror && mirror)                                                                                  \
-        gather_pull_kernel<DIM, MODE, IL, false, canMirror><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(     \
+        gather_pull_kernel<DIM, MODE, IL, false, canMirror><<<gridFor(nRange, pw), pw * 32, 0, gst>>>(     \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else if (idx32)                                                                                                \
-        gather_pull_kernel<DIM, MODE, IL, true, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(          \
+        gather_pull_kernel<DIM, MODE, IL, true, false><<<gridFor(nRange, pw), pw * 32, 0, gst>>>(          \
             G, h->cptr.p, h->csrc.p);                                                                                \
       else                                                                                                           \
-        gather_pull_kernel<DIM, MODE, IL, false, false><<<gridFor(nRowNodes, pw), pw * 32, 0, h->stream>>>(         \
+        gather_pull_kernel<DIM, MODE, IL, false, false><<<gridFor(nRange, pw), pw * 32, 0, gst>>>(         \
             G, h->cptr.p, h->csrc.p);                                                                                \
       if (G.vec) cudaStreamWaitEvent(h->stream, h->evVec, 0); /* join */                                             \
     } else if (G.vals) {                                                                                             \
@@ -595,6 +634,90 @@ int launchGather(Handle* h, unsigned what, int dbc) {
   if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("gather launch: ") + cudaGetErrorString(e));
   if (!G.vals) h->launches--;  // only the residual kernel was launched (already counted)
   IKB_LAUNCH_CHECK(h);
+  return IKB_OK;
+}
+
+// Chunk tables of the interleaved sweep: element ranges of equal size (whole CTAs of the element kernels) and, per
+// chunk, the end of the prefix of node-rows all of whose elements lie in chunks 0..c.
+int ensureSweepChunks(Handle* h) {
+  if (h->sweepChunksBuilt) return IKB_OK;
+  h->sweepChunksBuilt = true;
+  h->sweepElemEnd.clear();
+  h->sweepRowEnd.clear();
+  const int64_t nRowNodes = h->rowEnd - h->rowBegin;
+  const int K = std::min(h->sweepChunks, 32);
+  if (K < 2 || h->order != 1 || h->easM != 0 || !h->gatherPull || h->pullMirror || h->pullAsync || h->fusedEnabled ||
+      !h->csrc.p || !h->adjPtr.p || nRowNodes == 0 || h->nElem < (int64_t)K * 4096)
+    return IKB_OK;
+  DevBuf<int32_t> dMax;
+  IKB_CUDA(h, dMax.alloc((size_t)nRowNodes));
+  row_max_elem_kernel<<<gridFor(nRowNodes, 256), 256, 0, h->stream>>>(nRowNodes, h->adjPtr.p, h->adjCode.p, h->nn, dMax.p);
+  IKB_LAUNCH_CHECK(h);
+  std::vector<int32_t> maxElem((size_t)nRowNodes);
+  IKB_CUDA(h, cudaMemcpyAsync(maxElem.data(), dMax.p, dMax.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int64_t row = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t end = c + 1 == K ? h->nElem : std::min<int64_t>(h->nElem, (h->nElem * (c + 1) / K + 255) / 256 * 256);
+    while (row < nRowNodes && maxElem[(size_t)row] < end) ++row;
+    h->sweepElemEnd.push_back(end);
+    h->sweepRowEnd.push_back(c + 1 == K ? nRowNodes : row);
+  }
+  for (int c = 0; c < K; ++c)
+    if (!h->evChunk[c]) IKB_CUDA(h, cudaEventCreateWithFlags(&h->evChunk[c], cudaEventDisableTiming));
+  if (!h->stream3) {
+    int prioLo = 0, prioHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);
+    IKB_CUDA(h, cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prioLo));
+    IKB_CUDA(h, cudaEventCreateWithFlags(&h->evSweepFork, cudaEventDisableTiming));
+    IKB_CUDA(h, cudaEventCreateWithFlags(&h->evSweepJoin, cudaEventDisableTiming));
+  }
+  return IKB_OK;
+}
+
+// Interleaved sweep: element kernel of chunk c on the main stream, matrix gather of the rows completed by chunk c on
+// the side stream (beside the element kernel of chunk c+1); the residual gather follows the last chunk as usual.
+// Same kernels, same staged values, same summation order as the back-to-back path: only the launch shape differs.
+int launchInterleaved(Handle* h, unsigned stageWhat, unsigned gatherWhat, int dbc) {
+  ElemArgs A = makeElemArgs(h, stageWhat);
+  const int K = (int)h->sweepElemEnd.size();
+  const int nsol = (int)h->chunkElemEnd.size();
+  int64_t rowDone = 0;
+  for (int c = 0; c < K; ++c) {
+    const int64_t b = c ? h->sweepElemEnd[c - 1] : 0, end = h->sweepElemEnd[c];
+    if (h->piecesPending) {
+      // a pipelined solution upload: this chunk needs the piece that holds the dofs of its last element
+      int sc = 0;
+      while (sc + 1 < nsol && h->chunkElemEnd[sc] < end) ++sc;
+      cudaStreamWaitEvent(h->stream, h->evPiece[sc], 0);
+    }
+    A.elemBegin = b;
+    A.elemCount = end - b;
+    A.X = h->X.p + b;
+    A.elemNode = h->elemNode.p + b;
+    A.Lap = h->Lap.p ? h->Lap.p + b : nullptr;
+    A.Kst = h->Kst.p + (size_t)b * h->npair * h->dim * h->dim;
+    A.Rst = h->Rst.p + (size_t)b * h->nd;
+    A.Est = h->Est.p + b;
+    const cudaError_t e = launchQ1Kernel(h, A);
+    h->launches++;
+    if (e != cudaSuccess) return fail(h, IKB_ECUDA, std::string("element kernel: ") + cudaGetErrorString(e));
+    if (h->sweepRowEnd[c] > rowDone) {
+      cudaEventRecord(h->evChunk[c], h->stream);
+      cudaStreamWaitEvent(h->stream3, h->evChunk[c], 0);
+      const int rc = launchGather(h, IKB_MATRIX, dbc, rowDone, h->sweepRowEnd[c], h->stream3);
+      if (rc) return rc;
+      rowDone = h->sweepRowEnd[c];
+    }
+  }
+  h->piecesPending = false;
+  markSolutionUse(h);
+  if (gatherWhat & IKB_VECTOR) {
+    const int rc = launchGather(h, IKB_VECTOR, dbc);
+    if (rc) return rc;
+  }
+  cudaEventRecord(h->evSweepJoin, h->stream3);
+  cudaStreamWaitEvent(h->stream, h->evSweepJoin, 0);
   return IKB_OK;
 }
 
@@ -966,6 +1089,8 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   if (const char* i64 = std::getenv("IKB_PULL_IDX64")) h->pullIdx64 = std::atoi(i64) != 0;
   if (const char* pm = std::getenv("IKB_PULL_MIRROR")) h->pullMirror = std::atoi(pm) != 0;
   if (const char* w = std::getenv("IKB_PULL_WARPS")) h->pullWarps = std::min(std::max(std::atoi(w), 1), PULL_WARPS_MAX);
+  if (const char* pa = std::getenv("IKB_PULL_ASYNC")) h->pullAsync = std::atoi(pa) != 0;
+  if (const char* ch = std::getenv("IKB_CHUNKS")) h->sweepChunks = std::atoi(ch);
   if (const char* sb = std::getenv("IKB_SPMV_BLOCKS")) h->spmvBlocks = std::min(std::max(std::atoi(sb), 1), MAX_SPMV_BLOCKS);
   int prioLo = 0, prioHi = 0;
   cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi);  // the side stream outranks the main one
@@ -1013,6 +1138,9 @@ int ikb_destroy(ikb_handle hh) {
   h->adjPtr.release();
   h->adjCode.release();
   h->slotTab.release();
+  h->rowSlow.release();
+  h->rowSlowValid = false;
+  h->sweepChunksBuilt = false;
   h->cbelow.release();
   h->freeCnt.release();
   h->freeTot.release();
@@ -1039,6 +1167,8 @@ int ikb_destroy(ikb_handle hh) {
   h->sweepRowWait.release();
   h->sweepCtl.release();
   h->sweepDone.release();
+  for (auto& ev : h->evChunk)
+    if (ev) cudaEventDestroy(ev);
   if (h->stream3) cudaStreamDestroy(h->stream3);
   if (h->evSweepFork) cudaEventDestroy(h->evSweepFork);
   if (h->evSweepJoin) cudaEventDestroy(h->evSweepJoin);
@@ -1151,6 +1281,8 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->meshUploaded = true;
   h->patternBuilt = false;
   h->reducedBuilt = false;
+  h->rowSlowValid = false;
+  h->sweepChunksBuilt = false;
   h->fusedTried = h->fusedOk = false;
   h->stateVersion++;
   h->Lap.release();
@@ -1251,6 +1383,8 @@ int ikb_upload_dirichlet(ikb_handle hh, const uint8_t* flags) {
   IKB_CUDA(h, cudaStreamSynchronize(h->stream));
   h->hasFlags = true;
   h->reducedBuilt = false;
+  h->rowSlowValid = false;
+  h->sweepChunksBuilt = false;
   h->vals[IKB_DBC_REDUCED].release();
   h->vec[IKB_DBC_REDUCED].release();
   h->stateVersion++;
@@ -1267,6 +1401,8 @@ int ikb_set_row_ownership(ikb_handle hh, int64_t nodeBegin, int64_t nodeEnd) {
   h->rowEnd = nodeEnd;
   h->patternBuilt = false;
   h->reducedBuilt = false;
+  h->rowSlowValid = false;
+  h->sweepChunksBuilt = false;
   return IKB_OK;
 }
 
@@ -1397,6 +1533,8 @@ int ikb_build_pattern(ikb_handle hh) {
   tmp.release();
   h->patternBuilt = true;
   h->reducedBuilt = false;
+  h->rowSlowValid = false;
+  h->sweepChunksBuilt = false;
   h->rowDiag.release();
   h->rowLowEnd.release();
   h->mirrorBlk.release();
@@ -1621,6 +1759,23 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
     needStage = 0;
   }
   if (h->stagedVersion == h->stateVersion) needStage &= ~h->stagedWhat;
+  if ((needStage & IKB_MATRIX) && (needGather & IKB_MATRIX)) {
+    if ((rc = ensureSweepChunks(h))) return rc;
+    if (!h->sweepElemEnd.empty()) {
+      if ((rc = ensureStaging(h, needStage))) return rc;
+      if ((needGather & IKB_MATRIX) && !h->vals[dbc].p)
+        IKB_CUDA(h, h->vals[dbc].alloc((size_t)std::max<int64_t>(nnzOf(h, dbc), 1)));
+      if ((needGather & IKB_VECTOR) && !h->vec[dbc].p)
+        IKB_CUDA(h, h->vec[dbc].alloc((size_t)std::max<int64_t>(rowsOf(h, dbc), 1)));
+      if ((rc = launchInterleaved(h, needStage, needGather, dbc))) return rc;
+      h->stagedWhat = (h->stagedVersion == h->stateVersion ? h->stagedWhat : 0) | needStage;
+      h->stagedVersion = h->stateVersion;
+      if (needGather & IKB_MATRIX) h->valsVersion[dbc] = h->stateVersion;
+      if (needGather & IKB_VECTOR) h->vecVersion[dbc] = h->stateVersion;
+      needStage = 0;
+      needGather = 0;
+    }
+  }
   if (needStage) {
     if ((rc = ensureStaging(h, needStage))) return rc;
     const unsigned stageWhat = needStage;

@@ -35,6 +35,7 @@ struct GatherArgs {
   const int64_t* redRowStart;
   const int32_t* cbelow;
   int64_t redVecOffset;  // index of the first local free row in the reduced vector
+  int64_t rowFirst = 0, rowEnd = -1;  // pull gather: local node-rows [rowFirst, rowEnd) (rowEnd < 0: all of them)
   int pullStageMax;      // pull gather: chunks with at most this many codes are staged in shared memory (<= PULL_CAP)
   // mirrored pull (Raw/Full): a row computes its blocks (g, g') with g' >= g (and those whose column node belongs to
   // another rank) and stores each off-diagonal one a second time, transposed, as block (g', g) of row g'
@@ -462,9 +463,18 @@ __global__ void __launch_bounds__(32 * PULL_WARPS_MAX, MIRROR ? 12 : 16)
     gather_pull_kernel(GatherArgs G, const int32_t* __restrict__ cptr, const uint32_t* __restrict__ csrc) {
   __shared__ uint32_t codeBuf[PULL_WARPS_MAX][PULL_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (g >= G.P.nRowNodes) return;
+  const int64_t g = G.rowFirst + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= (G.rowEnd < 0 ? G.P.nRowNodes : G.rowEnd)) return;
   pullRow<D, DBC, INTERLEAVED, IDX32, false, MIRROR>(G, cptr, csrc, g, codeBuf[warp], lane);
+}
+
+// highest element touching each node-row (the adjacency lists ascend by element); -1 for rows without elements
+__global__ void row_max_elem_kernel(int64_t nRowNodes, const int32_t* __restrict__ adjPtr, const uint32_t* __restrict__ adjCode,
+                                    int n, int32_t* maxElem) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nRowNodes) return;
+  const int32_t a0 = adjPtr[g], a1 = adjPtr[g + 1];
+  maxElem[g] = a1 > a0 ? (int32_t)(adjCode[a1 - 1] / (uint32_t)n) : -1;
 }
 
 // one-time maps of the mirrored pull

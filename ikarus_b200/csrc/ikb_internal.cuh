@@ -123,6 +123,17 @@ struct Handle {
   bool pullIdx64 = false;       // force the 64-bit offset path of the pull gather (IKB_PULL_IDX64, test hook)
   bool elemMma = true;          // Hex8 NeoHooke/LinearElastic: tangent contraction by DMMA (IKB_ELEM=fma: FMA kernel)
   int h8MinBlocks = 4;          // register budget of the DMMA kernel as resident CTAs per SM (IKB_H8_MINB, tuning)
+  bool pullAsync = false;       // IKB_PULL_ASYNC=1: row-pipelined cp.async gather for Q1 kinds, Raw/Full (ikb_gather_async.cuh; measured slower)
+  DevBuf<uint8_t> rowSlow;      // [nRowNodes] row or one of its column nodes constrained
+  bool rowSlowValid = false;
+  // Interleaved sweep (Q1 kinds, pull gather): the element list is cut into sweepChunks chunks; the rows that are
+  // complete after chunk c (a prefix of the row list) are gathered on a side stream while chunk c+1 is evaluated, so
+  // the staged K_e of a chunk is read back while it still sits in L2.  Opt-in (IKB_CHUNKS=n): measured slower than the two
+  // back-to-back kernels on C2 (0.340 ms with 4 chunks, 0.347 with 8, 0.326 back to back).
+  int sweepChunks = 0;
+  std::vector<int64_t> sweepElemEnd, sweepRowEnd;  // per chunk: end of its element range, end of the complete row prefix
+  bool sweepChunksBuilt = false;
+  cudaEvent_t evChunk[32] = {};
   bool gatherPull = true;       // matrix gather through the per-block contribution lists (IKB_GATHER=tile: warp tile gather)
   // reduced-mode structures
   bool reducedBuilt = false;

@@ -291,6 +291,30 @@ def test_pipelined_solution_upload_is_bit_identical():
     dev._check(lib.ikb_get_vector(h, int(ik.DBCOption.Full), capi.ptr(r1)))
     dev._check(lib.ikb_get_matrix_values(h, int(ik.DBCOption.Full), capi.ptr(v1)))
     assert np.array_equal(r0, r1) and np.array_equal(v0, v1)
+    # Interleaved sweep (IKB_CHUNKS=n, opt-in): element kernel chunk by chunk, the rows completed by a chunk gathered on a
+    # side stream beside the next chunk -- same kernels, same staged values: same bits, also behind a pipelined upload
+    import os
+    os.environ["IKB_CHUNKS"] = "5"
+    try:
+        chunked = device_assembler(mesh, kind, mat, flags, "interleaved")
+    finally:
+        del os.environ["IKB_CHUNKS"]
+    lib2, h2 = chunked._lib, chunked._h
+    for upload in (lib2.ikb_set_solution, None):
+        chunked._check(lib2.ikb_set_solution(h2, capi.ptr(np.zeros(n))))
+        chunked._check(lib2.ikb_assemble(h2, 6, int(ik.DBCOption.Full)))
+        if upload:
+            chunked._check(upload(h2, capi.ptr(d)))
+        else:
+            chunked._check(lib2.ikb_set_solution_range(h2, capi.ptr(d), 0, n))
+        chunked._check(lib2.ikb_assemble(h2, 6, int(ik.DBCOption.Full)))
+        chunked._check(lib2.ikb_get_vector(h2, int(ik.DBCOption.Full), capi.ptr(r1)))
+        chunked._check(lib2.ikb_get_matrix_values(h2, int(ik.DBCOption.Full), capi.ptr(v1)))
+        assert np.array_equal(r0, r1) and np.array_equal(v0, v1)
+    n0 = chunked.launchCount()
+    chunked._check(lib2.ikb_invalidate(h2))
+    chunked._check(lib2.ikb_assemble(h2, 6, int(ik.DBCOption.Full)))
+    assert chunked.launchCount() - n0 >= 7  # the chunked path really ran: 5 element launches, up to 5 + 1 gathers
 
 
 UNSTRUCTURED = [
@@ -355,7 +379,8 @@ def test_gather_variants_bit_identical(case, layout, monkeypatch):
     req = ik.FERequirements(d, 0.4)
     modes = (ik.DBCOption.Raw, ik.DBCOption.Full, ik.DBCOption.Reduced)
     base = [dev.matrix(req, ik.MatrixAffordance.stiffness, m).data.copy() for m in modes]
-    variants = [{"IKB_GATHER": "tile"}, {"IKB_PULL_STAGE_MAX": "0"}, {"IKB_PULL_STAGE_MAX": "5"}, {"IKB_PULL_IDX64": "1"},
+    # (IKB_PULL_ASYNC=1: the row-pipelined cp.async form for Q1 kinds in Raw/Full mode)
+    variants = [{"IKB_PULL_ASYNC": "1"}, {"IKB_GATHER": "tile"}, {"IKB_PULL_STAGE_MAX": "0"}, {"IKB_PULL_STAGE_MAX": "5"}, {"IKB_PULL_IDX64": "1"},
                 {"IKB_PULL_IDX64": "1", "IKB_PULL_STAGE_MAX": "7"}]
     for env in variants:
         with monkeypatch.context() as mp:

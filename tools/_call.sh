@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_trust_region.py tests/test_cpp_wrapper.py -x -q -m gpu 2>&1 | tail -5
-python bench.py --steps 50 --warmup 5 --no-c5 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['trust_region_inner'], d['newton_step'])"
+timeout 1700 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+python bench.py --steps 200 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json
+python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 300 gpurun_out/bench_ref.json

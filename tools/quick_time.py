@@ -35,6 +35,20 @@ for ph in ("fused", "elements", "gather", "spmv", "dfma_peak", "dmma_peak"):
         print(f"{ph}: {ms:.4f} ms  -> {fl/ms/1e9:.2f} TFLOP/s FP64")
     else:
         print(f"{ph}: {ms:.4f} ms  -> {mesh.n_elem/ms/1e3:.1f} Melem/s")
+# whole K+R sweep through ikb_assemble (what bench.py times), wall clock around a synchronised batch
+from ikarus_b200 import _capi as capi
+lib, h = dev._lib, dev._h
+for rep in range(2):
+    lib.ikb_sync(h)
+    t = time.time()
+    for _ in range(50):
+        lib.ikb_invalidate(h)
+        dev._check(lib.ikb_assemble(h, capi.MATRIX | capi.VECTOR, capi.DBC_FULL))
+    lib.ikb_sync(h)
+    t = (time.time() - t) / 50
+print(f"step: {t*1e3:.4f} ms  -> {mesh.n_elem/t/1e6:.1f} Melem/s (IKB_CHUNKS={os.environ.get('IKB_CHUNKS', 'default')})")
+if os.environ.get("QT_NO_PCG"):
+    sys.exit(0)
 ls = ik.DeviceLinearSolver(1e-10)
 t = time.time(); x = ls(-R, A); t = time.time() - t
 print(f"pcg: {ls.lastIterations} its relres {ls.lastRelRes:.2e} in {t*1e3:.1f} ms -> {t*1e3/max(ls.lastIterations,1):.3f} ms/it")
