@@ -8,6 +8,7 @@ from .assembler import (AffordanceCollection, DBCOption, DenseFlatAssembler, Dev
                         makeDenseFlatAssembler, makeSparseFlatAssembler)
 from .fe import (DirichletValues, FEContainer, Materials, eas, linearElastic, makeFE, neumannBoundaryLoad,  # noqa: F401
                  nonLinearElastic, planeStrain, planeStress, skills, toLamesFirstParameterAndShearModulus, volumeLoad)
+from .io import ResultFunction, makeResultFunction  # noqa: F401
 from .solvers import (ControlInformation, DeviceLinearSolver, DeviceTruncatedCG, LoadControl,  # noqa: F401
                       LoadControlConfig, NewtonRaphson, NewtonRaphsonConfig, NonLinearSolverInformation, NRSettings,
                       PreConditioner, TrustRegion, TRSettings, obtainForcesDueToIDBC)

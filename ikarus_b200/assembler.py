@@ -163,6 +163,8 @@ class _FlatAssemblerBase:
         self._check(self._lib.ikb_build_pattern(self._h))
         self._fext_lambda = None
         self._last_d = None
+        self._user_fext, self._user_scales = None, True
+        self._loads_proportional = True
         self._refresh_loads(1.0, force=True)
 
     # ------------------------------------------------------------------ plumbing
@@ -189,21 +191,44 @@ class _FlatAssemblerBase:
             pass
 
     def _refresh_loads(self, lam, force=False):
-        """Volume loads are host callbacks f(x, lambda) (loads/volume.hh:26); all reference tests are
-        lambda-proportional, so sample once at lambda = 1 and let the device scale by lambda."""
-        if not self._fes.loads or not force:
+        """Volume and Neumann loads are host callbacks f(x, lambda) (loads/volume.hh:26, loads/traction.hh:29).  They are
+        sampled on the host with the reference's rules (FEContainer.sample_external_load).  A load that is proportional
+        to the load factor -- every reference test -- is sampled once at lambda = 1 and scaled on the device; any other
+        dependence on lambda is re-sampled whenever the load factor changes and uploaded unscaled
+        (R_e -= N f(x, lambda) detJ w, E_e -= u . f(x, lambda) detJ w: volume.hh:67-106, traction.hh:70-138)."""
+        if not self._fes.loads:
             return
-        self._fext = self._fes.sample_external_load(1.0)
-        f2 = self._fes.sample_external_load(2.0)
-        if not np.allclose(f2, 2.0 * self._fext, rtol=1e-12, atol=1e-300):
-            raise NotImplementedInReference("volume load is not proportional to the load factor")
-        self._check(self._lib.ikb_set_external_load(self._h, capi.ptr(self._fext), 1))
+        if force:
+            self._fext = self._fes.sample_external_load(1.0)
+            f2 = self._fes.sample_external_load(2.0)
+            f0 = self._fes.sample_external_load(0.0)
+            scale = np.abs(self._fext).max(initial=0.0)
+            self._loads_proportional = bool(np.allclose(f2, 2.0 * self._fext, rtol=1e-12, atol=1e-14 * scale)
+                                            and np.allclose(f0, 0.0, rtol=0.0, atol=1e-14 * scale))
+            self._fext_lambda = None
+            if self._loads_proportional:
+                self._check(self._lib.ikb_set_external_load(self._h, capi.ptr(self._fext), 1))
+                return
+        if not self._loads_proportional and lam != self._fext_lambda:
+            f = self._fes.sample_external_load(lam)
+            if self._user_fext is not None:
+                f = f + (lam if self._user_scales else 1.0) * self._user_fext
+            self._fext_now = f  # (kept alive until the copy has run)
+            self._check(self._lib.ikb_set_external_load(self._h, capi.ptr(f), 0))
+            self._check(self._lib.ikb_sync(self._h))
+            self._fext_lambda = lam
 
     def setExternalLoad(self, fext, scalesWithLambda=True):
-        """Extra lambda-proportional nodal load vector (what the reference tests add through an
+        """Extra nodal load vector, lambda-proportional by default (what the reference tests add through an
         AssemblerManipulator vector callback, tests/src/testcantileverbeam.hh:56-80)."""
         f = capi.as_f64(fext)
+        self._user_fext, self._user_scales = f.copy(), bool(scalesWithLambda)
+        if self._fes.loads and not self._loads_proportional:
+            self._fext_lambda = None  # re-sampled together with the skills' loads at the next bind
+            return
         if self._fes.loads:
+            if not scalesWithLambda:
+                raise NotImplementedInReference("a constant nodal load next to lambda-proportional load skills")
             f = f + self._fext
         self._fext_user = f
         self._check(self._lib.ikb_set_external_load(self._h, capi.ptr(f), int(scalesWithLambda)))
@@ -217,6 +242,7 @@ class _FlatAssemblerBase:
             self._check(self._lib.ikb_sync(self._h))
             self._last_d = d.copy()
         self._check(self._lib.ikb_set_parameter(self._h, req.parameter()))
+        self._refresh_loads(req.parameter())
 
     # ------------------------------------------------------------------ FlatAssemblerBase
     def size(self):

@@ -22,18 +22,38 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <functional>
+#include <iterator>
+#include <limits>
 #include <memory>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../ikb200.h"
 #include "hosttypes.hh"
+
+// DeviceResultFunction derives from Dune::VTKFunction (as io/resultfunction.hh:57 does) where dune-grid is present
+#if !defined(IKB_HAVE_DUNE_VTK)
+  #if IKB_HAVE_IKARUS && defined(__has_include)
+    #if __has_include(<dune/grid/io/file/vtk/function.hh>)
+      #define IKB_HAVE_DUNE_VTK 1
+    #endif
+  #endif
+  #if !defined(IKB_HAVE_DUNE_VTK)
+    #define IKB_HAVE_DUNE_VTK 0
+  #endif
+#endif
+#if IKB_HAVE_DUNE_VTK
+  #include <dune/common/fvector.hh>
+  #include <dune/grid/io/file/vtk/function.hh>
+#endif
 
 namespace Ikarus::B200 {
 
@@ -274,6 +294,11 @@ public:
     check(ikb_upload_mesh(h_, corners.data(), dofs.data()));
     check(ikb_upload_dirichlet(h_, flags.data()));
     check(ikb_build_pattern(h_));
+    dim_     = desc.dim;
+    order_   = desc.order;
+    nElem_   = nElem;
+    corners_ = std::move(corners);  // kept for the host-side load sampling
+    dofs_    = std::move(dofs);
   }
   ~DeviceSparseFlatAssembler() {
     if (h_)
@@ -533,9 +558,180 @@ public:
         });
   }
 #endif
-  /** lambda-proportional external nodal loads sampled on the host (loads/volume.hh, loads/traction.hh). */
+  // ---- results at local positions ---------------------------------------------------------------------
+  /** Number of components of result type rt (IKB_RESULT_*): dim(dim+1)/2 in Voigt form, 6 for the *Full types. */
+  int resultComponents(int rt) const {
+    return (rt == IKB_RESULT_LINEAR_STRESS_FULL || rt == IKB_RESULT_PK2_STRESS_FULL) ? 6 : dim_ * (dim_ + 1) / 2;
+  }
+  /** `fe.calculateAt<RT>(req, local)` of EVERY element at nPoints local positions at once (mechanics/
+   *  nonlinearelastic.hh:237-271, linearelastic.hh, enhancedassumedstrains.hh:127-187), evaluated on the device:
+   *  out[(e*nPoints + q)*ncomp + c], Voigt order.  local: nPoints x dim reference coordinates in [0,1]^dim. */
+  std::vector<double> calculateAt(int rt, const FERequirement& req, const double* local, int nPoints) {
+    push(req);
+    std::vector<double> out(static_cast<std::size_t>(nElem_) * nPoints * resultComponents(rt));
+    check(ikb_calculate_at(h_, rt, local, nPoints, out.data()));
+    check(ikb_sync(h_));
+    return out;
+  }
+  int worldDimension() const { return dim_; }
+  std::int64_t numberOfElements() const { return nElem_; }
+
+  // ---- external loads (mechanics/loads/volume.hh, loads/traction.hh) -----------------------------------
+  /** f(x, lambda): the reference's `std::function<Eigen::Vector<double, worldDim>(const FieldVector&, const double&)>`
+   *  (loads/volume.hh:26, loads/traction.hh:29) on plain arrays; the first dim entries are used. */
+  using LoadFunction = std::function<std::array<double, 3>(const std::array<double, 3>& x, double lambda)>;
+
+  /** volumeLoad<dim>(f) (loads/volume.hh:67-106): R_a -= N_a f(x, lambda) detJ w, E -= u . f(x, lambda) detJ w with the
+   *  element's own Gauss rule (order + 1 points per direction). */
+  void addVolumeLoad(LoadFunction f) {
+    volumeLoads_.push_back(std::move(f));
+    loadsSampled_ = false;
+  }
+  /** neumannBoundaryLoad(&patch, t) (loads/traction.hh:70-138): the faces of the patch as (element index in the
+   *  container, DUNE face id: 2k -> xi_k = 0, 2k+1 -> xi_k = 1); face rule of order = basis order (traction.hh:122). */
+  void addNeumannBoundaryLoad(std::vector<std::pair<std::int64_t, int>> faces, LoadFunction t) {
+    neumannLoads_.push_back({std::move(faces), std::move(t)});
+    loadsSampled_ = false;
+  }
+  /** Extra nodal load vector, proportional to the load factor by default (what the reference's tests add through an
+   *  AssemblerManipulator vector callback, tests/src/testcantileverbeam.hh:56-80). */
   void setExternalLoad(const VectorType& fext, bool scalesWithLambda = true) {
-    check(ikb_set_external_load(h_, fext.data(), scalesWithLambda ? 1 : 0));
+    userLoad_.assign(fext.data(), fext.data() + size());
+    userScales_   = scalesWithLambda;
+    loadsSampled_ = false;
+    if (volumeLoads_.empty() && neumannLoads_.empty())
+      check(ikb_set_external_load(h_, userLoad_.data(), scalesWithLambda ? 1 : 0));
+  }
+  /** The nodal load vector of the load skills at load factor lambda, integrated on the host (any dependence on lambda). */
+  std::vector<double> sampleLoads(double lambda) const {
+    std::vector<double> fext(size(), 0.0);
+    const int dim = dim_, n1 = order_ + 1, nc = 1 << dim;
+    int nn = 1;
+    for (int k = 0; k < dim; ++k)
+      nn *= n1;
+    auto lagrange = [](int order, double xi, double* v) {
+      if (order == 1) {
+        v[0] = 1.0 - xi;
+        v[1] = xi;
+      } else {
+        v[0] = 2.0 * (xi - 0.5) * (xi - 1.0);
+        v[1] = 4.0 * xi * (1.0 - xi);
+        v[2] = 2.0 * xi * (xi - 0.5);
+      }
+    };
+    auto gauss01 = [](int n, double* x, double* w) {
+      if (n == 1) {
+        x[0] = 0.5, w[0] = 1.0;
+      } else if (n == 2) {
+        const double a = 0.5 / std::sqrt(3.0);
+        x[0] = 0.5 - a, x[1] = 0.5 + a, w[0] = w[1] = 0.5;
+      } else {
+        const double a = 0.5 * std::sqrt(0.6);
+        x[0] = 0.5 - a, x[1] = 0.5, x[2] = 0.5 + a, w[0] = w[2] = 5.0 / 18.0, w[1] = 8.0 / 18.0;
+      }
+    };
+    // shape functions of the basis, geometry (multilinear over the corners) and its Jacobian at xi of element e
+    auto at = [&](std::int64_t e, const double* xi, double* N, std::array<double, 3>& x, double Jt[3][3]) {
+      double v[3][3];
+      for (int k = 0; k < dim; ++k)
+        lagrange(order_, xi[k], v[k]);
+      for (int a = 0; a < nn; ++a) {
+        double p = 1.0;
+        for (int k = 0, q = a; k < dim; ++k, q /= n1)
+          p *= v[k][q % n1];
+        N[a] = p;
+      }
+      x = {0.0, 0.0, 0.0};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+          Jt[i][j] = 0.0;
+      const double* X = corners_.data() + static_cast<std::size_t>(e) * nc * dim;
+      for (int c = 0; c < nc; ++c) {
+        double Ng = 1.0;
+        for (int k = 0; k < dim; ++k)
+          Ng *= ((c >> k) & 1) ? xi[k] : 1.0 - xi[k];
+        for (int j = 0; j < dim; ++j)
+          x[j] += Ng * X[c * dim + j];
+        for (int i = 0; i < dim; ++i) {
+          double dN = ((c >> i) & 1) ? 1.0 : -1.0;
+          for (int k = 0; k < dim; ++k)
+            if (k != i)
+              dN *= ((c >> k) & 1) ? xi[k] : 1.0 - xi[k];
+          for (int j = 0; j < dim; ++j)
+            Jt[i][j] += dN * X[c * dim + j];  // Jt[i][j] = dx_j / dxi_i
+        }
+      }
+    };
+    auto scatter = [&](std::int64_t e, const double* N, const std::array<double, 3>& f, double weight) {
+      const std::int64_t* dofs = dofs_.data() + static_cast<std::size_t>(e) * nn * dim;
+      for (int a = 0; a < nn; ++a)
+        for (int k = 0; k < dim; ++k)
+          fext[static_cast<std::size_t>(dofs[a * dim + k])] += N[a] * f[k] * weight;
+    };
+    double N[27], Jt[3][3];
+    std::array<double, 3> x{};
+    if (!volumeLoads_.empty()) {
+      double gx[3], gw[3];
+      gauss01(n1, gx, gw);
+      int npts = 1;
+      for (int k = 0; k < dim; ++k)
+        npts *= n1;
+      for (std::int64_t e = 0; e < nElem_; ++e)
+        for (int g = 0; g < npts; ++g) {
+          double xi[3] = {0, 0, 0}, w = 1.0;
+          for (int k = 0, q = g; k < dim; ++k, q /= n1) {
+            xi[k] = gx[q % n1];
+            w *= gw[q % n1];
+          }
+          at(e, xi, N, x, Jt);
+          const double detJ =
+              dim == 2 ? std::abs(Jt[0][0] * Jt[1][1] - Jt[0][1] * Jt[1][0])
+                       : std::abs(Jt[0][0] * (Jt[1][1] * Jt[2][2] - Jt[1][2] * Jt[2][1]) - Jt[0][1] * (Jt[1][0] * Jt[2][2] - Jt[1][2] * Jt[2][0]) +
+                                  Jt[0][2] * (Jt[1][0] * Jt[2][1] - Jt[1][1] * Jt[2][0]));
+          std::array<double, 3> f{0.0, 0.0, 0.0};
+          for (const auto& fn : volumeLoads_) {
+            const auto v = fn(x, lambda);
+            for (int k = 0; k < dim; ++k)
+              f[k] += v[k];
+          }
+          scatter(e, N, f, detJ * w);
+        }
+    }
+    for (const auto& nl : neumannLoads_) {
+      const int np = order_ / 2 + 1;
+      double gx[3], gw[3];
+      gauss01(np, gx, gw);
+      int npts = 1;
+      for (int k = 0; k + 1 < dim; ++k)
+        npts *= np;
+      for (const auto& [e, face] : nl.faces) {
+        const int kf = face / 2, side = face % 2;
+        int dirs[2] = {0, 0}, nd = 0;
+        for (int j = 0; j < dim; ++j)
+          if (j != kf)
+            dirs[nd++] = j;
+        for (int g = 0; g < npts; ++g) {
+          double xi[3] = {0, 0, 0}, w = 1.0;
+          xi[kf] = side;
+          for (int t = 0, q = g; t < nd; ++t, q /= np) {
+            xi[dirs[t]] = gx[q % np];
+            w *= gw[q % np];
+          }
+          at(e, xi, N, x, Jt);
+          double area;
+          if (dim == 2) {
+            area = std::hypot(Jt[dirs[0]][0], Jt[dirs[0]][1]);
+          } else {
+            const double* a = Jt[dirs[0]];
+            const double* b = Jt[dirs[1]];
+            const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+            area = std::sqrt(cx * cx + cy * cy + cz * cz);
+          }
+          scatter(e, N, nl.t(x, lambda), w * area);
+        }
+      }
+    }
+    return fext;
   }
   ikb_handle handle() const { return h_; }
 
@@ -555,6 +751,17 @@ private:
       lastD_.assign(p, p + size());
     }
     check(ikb_set_parameter(h_, req.parameter()));
+    // load skills: f(x, lambda) is evaluated at the requirement's load factor, like the reference does at every call
+    if ((!volumeLoads_.empty() || !neumannLoads_.empty()) && (!loadsSampled_ || sampledLambda_ != req.parameter())) {
+      const double lambda = req.parameter();
+      loadNow_            = sampleLoads(lambda);
+      for (std::size_t i = 0; i < userLoad_.size(); ++i)
+        loadNow_[i] += (userScales_ ? lambda : 1.0) * userLoad_[i];
+      check(ikb_set_external_load(h_, loadNow_.data(), 0));
+      check(ikb_sync(h_));
+      loadsSampled_  = true;
+      sampledLambda_ = lambda;
+    }
   }
 public:
   /** The device state was changed behind the wrapper's back (ikb_update_solution, ikb_set_solution on handle()). */
@@ -582,6 +789,21 @@ private:
   std::size_t vertexCount_{0};
   bool fusedSweep_{true};
   std::vector<double> lastD_;
+  // host copies of the mesh and the load skills
+  int dim_{0}, order_{0};
+  std::int64_t nElem_{0};
+  std::vector<double> corners_;
+  std::vector<std::int64_t> dofs_;
+  struct NeumannLoad
+  {
+    std::vector<std::pair<std::int64_t, int>> faces;
+    LoadFunction t;
+  };
+  std::vector<LoadFunction> volumeLoads_;
+  std::vector<NeumannLoad> neumannLoads_;
+  std::vector<double> userLoad_, loadNow_;
+  bool userScales_{true}, loadsSampled_{false};
+  double sampledLambda_{0.0};
   ikb_handle h_{nullptr};
   ScalarType scal_{0.0};
   VectorType vec_[3];
@@ -594,6 +816,118 @@ private:
 template <typename FEC, typename DV>
 auto makeDeviceSparseFlatAssembler(FEC&& fes, const DV& dirichletValues, int device = -1) {
   return std::make_shared<DeviceSparseFlatAssembler<FEC, DV>>(std::forward<FEC>(fes), dirichletValues, device);
+}
+
+/** io/resultfunction.hh:19-37: the default user function returns the requested component unchanged. */
+struct DefaultResultUserFunction
+{
+  template <typename R, typename FiniteElement>
+  double operator()(const R& resultArray, const double* /*pos*/, const FiniteElement& /*fe*/, int comp) const {
+    return resultArray[comp];
+  }
+};
+
+/**
+ * \brief Mirror of Ikarus::ResultFunction (io/resultfunction.hh:57-157): evaluates a result type of the bound
+ * requirement at local positions of single elements, for a VTK writer.
+ * \details The reference calls `fe.calculateAt<RT>(requirement(), local)` for one element at a time; a writer asks for
+ * the same few local positions (the element vertices) on every element, so here the first request for a position
+ * evaluates ALL elements on the device (ikb_calculate_at) and the following ones are served from that table.  The
+ * table is dropped when the solution or the load factor of the bound requirement changes.
+ * With Ikarus and dune-grid present (IKB_HAVE_DUNE_VTK) the class derives from Dune::VTKFunction<GridView> and `evaluate(comp, entity, local)` maps
+ * the entity through `gridView().indexSet().index(e)` exactly like resultfunction.hh:87-90.
+ * \tparam AS DeviceSparseFlatAssembler; RT: IKB_RESULT_* code of the result type; UF: user function
+ * `(resultArray, pos, fe, comp) -> double` with optional `ncomps()` / `name()` (resultfunction.hh:100-121).
+ */
+template <typename AS, typename UserFunction = DefaultResultUserFunction>
+class DeviceResultFunction
+#if IKB_HAVE_DUNE_VTK
+    : public Dune::VTKFunction<typename AS::GridView>
+#endif
+{
+public:
+  using Assembler = AS;
+
+  DeviceResultFunction(std::shared_ptr<AS> assembler, int resultType, UserFunction userFunction = {})
+      : assembler_{std::move(assembler)},
+        rt_{resultType},
+        userFunction_{std::move(userFunction)} {}
+
+  /** resultfunction.hh:143-148 with the element given by its index in the container */
+  double evaluate(int comp, std::int64_t elementIndex, const double* local) const {
+    const int nc        = assembler_->resultComponents(rt_);
+    const double* table = tableFor(local);
+    const double* r     = table + static_cast<std::size_t>(elementIndex) * nc;
+    auto it             = std::begin(assembler_->finiteElements());
+    std::advance(it, elementIndex);
+    return userFunction_(r, local, *it, comp);
+  }
+#if IKB_HAVE_DUNE_VTK
+  using GridView = typename AS::GridView;
+  using Entity   = typename GridView::template Codim<0>::Entity;
+  using ctype    = typename GridView::ctype;
+  double evaluate(int comp, const Entity& e, const Dune::FieldVector<ctype, GridView::dimension>& local) const override {
+    double xi[3] = {0, 0, 0};
+    for (int k = 0; k < GridView::dimension; ++k)
+      xi[k] = local[k];
+    return evaluate(comp, static_cast<std::int64_t>(assembler_->gridView().indexSet().index(e)), xi);
+  }
+  [[nodiscard]] int ncomps() const override { return ncompsImpl(); }
+  [[nodiscard]] std::string name() const override { return nameImpl(); }
+#else
+  [[nodiscard]] int ncomps() const { return ncompsImpl(); }
+  [[nodiscard]] std::string name() const { return nameImpl(); }
+#endif
+
+private:
+  int ncompsImpl() const {
+    if constexpr (requires { userFunction_.ncomps(); })
+      return userFunction_.ncomps();
+    else
+      return assembler_->resultComponents(rt_);
+  }
+  std::string nameImpl() const {
+    if constexpr (requires { userFunction_.name(); })
+      return userFunction_.name();
+    else {
+      static const char* names[] = {"linearStress", "PK2Stress", "linearStressFull", "PK2StressFull", "kirchhoffStress", "cauchyStress"};
+      return names[rt_];
+    }
+  }
+  const double* tableFor(const double* local) const {
+    const auto& req = assembler_->requirement();
+    const auto& d   = req.globalSolution();
+    // a new state of the bound requirement invalidates every table
+    if (lambda_ != req.parameter() || lastD_.size() != static_cast<std::size_t>(d.size()) ||
+        !std::equal(lastD_.begin(), lastD_.end(), d.data())) {
+      tables_.clear();
+      lastD_.assign(d.data(), d.data() + d.size());
+      lambda_ = req.parameter();
+    }
+    const int dim = assembler_->worldDimension();
+    std::array<double, 3> key{0, 0, 0};
+    for (int k = 0; k < dim; ++k)
+      key[k] = local[k];
+    for (const auto& t : tables_)
+      if (t.first == key)
+        return t.second.data();
+    tables_.emplace_back(key, assembler_->calculateAt(rt_, req, key.data(), 1));
+    return tables_.back().second.data();
+  }
+
+  std::shared_ptr<AS> assembler_;
+  int rt_;
+  UserFunction userFunction_;
+  mutable std::vector<std::pair<std::array<double, 3>, std::vector<double>>> tables_;
+  mutable std::vector<double> lastD_;
+  mutable double lambda_{std::numeric_limits<double>::quiet_NaN()};
+};
+
+/** makeResultFunction<RT>(assembler, ...) (io/resultfunction.hh:172-178) with the result type as IKB_RESULT_* code */
+template <typename AS, typename UserFunction = DefaultResultUserFunction>
+auto makeResultFunction(std::shared_ptr<AS> assembler, int resultType, UserFunction&& userFunction = {}) {
+  return std::make_shared<DeviceResultFunction<AS, std::remove_cvref_t<UserFunction>>>(std::move(assembler), resultType,
+                                                                                       std::forward<UserFunction>(userFunction));
 }
 
 /**

@@ -244,6 +244,78 @@ int main(int argc, char** argv) {
     CHECK(std::isfinite(m.scalar(req, ScalarAffordance::mechanicalPotentialEnergy)));
   }
 
+  // Load skills through the wrapper (loads/volume.hh:67-106, loads/traction.hh:70-138): a volume load and a traction on
+  // the face x = nx*h with a non-proportional dependence on the load factor.  At d = 0 the internal forces vanish, so
+  // R = -fext(lambda): totals against the exact integrals, nodal values against the wrapper's own sampling.
+  {
+    auto fes2 = makeMesh(nx, ny, nz, 0.5, IKB_MAT_NEOHOOKE, IKB_STRAIN_GREEN_LAGRANGE, 0);
+    auto a2   = makeDeviceSparseFlatAssembler(fes2, dv);
+    a2->addVolumeLoad([](const std::array<double, 3>& x, double lam) { return std::array<double, 3>{0.0, 0.0, -(lam * lam + 1.0) * x[0]}; });
+    std::vector<std::pair<std::int64_t, int>> faces;
+    for (std::int64_t e = 0; e < (std::int64_t)fes2.size(); ++e)
+      if (e % nx == nx - 1)
+        faces.push_back({e, 1});  // face xi_0 = 1 of the last element column
+    a2->addNeumannBoundaryLoad(faces, [](const std::array<double, 3>&, double lam) { return std::array<double, 3>{std::cos(lam), 0.0, 0.0}; });
+    HostRequirement r2;
+    r2.d.assign(n, 0.0);
+    for (double lam : {0.0, 1.5}) {
+      r2.lambda = lam;
+      const std::vector<double> R = a2->vector(r2, VectorAffordance::forces, DBCOption::Raw);
+      const std::vector<double> f = a2->sampleLoads(lam);
+      double sx = 0, sz = 0, dmax = 0;
+      for (std::size_t i = 0; i < n; ++i) {
+        dmax = std::max(dmax, std::abs(R[i] + f[i]));
+        if (i % 3 == 0)
+          sx += f[i];
+        if (i % 3 == 2)
+          sz += f[i];
+      }
+      // box 2 x 1 x 1: int x dV = 2, face area 1
+      CHECK(dmax <= 1e-13);
+      CHECK(std::abs(sz + (lam * lam + 1.0) * 2.0) <= 1e-12 && std::abs(sx - std::cos(lam)) <= 1e-12);
+      const double E = a2->scalar(r2, ScalarAffordance::mechanicalPotentialEnergy);
+      CHECK(std::abs(E) <= 1e-13);  // d = 0
+    }
+  }
+
+  // ResultFunction mirror (io/resultfunction.hh:57-157): PK2 stress of single elements at local positions, served from
+  // one device evaluation of all elements per position; a user function (von Mises like) with its own ncomps/name.
+  {
+    auto rf = makeResultFunction(asmb, IKB_RESULT_PK2_STRESS);
+    CHECK(rf->ncomps() == 6 && rf->name() == "PK2Stress");
+    const double centre[3] = {0.5, 0.5, 0.5}, corner[3] = {0.0, 1.0, 0.0};
+    const std::vector<double> all = asmb->calculateAt(IKB_RESULT_PK2_STRESS, req, centre, 1);
+    CHECK(all.size() == fes.size() * 6);
+    for (std::int64_t e : {std::int64_t(0), std::int64_t(5), std::int64_t(fes.size() - 1)})
+      for (int c = 0; c < 6; ++c)
+        CHECK(rf->evaluate(c, e, centre) == all[e * 6 + c]);
+    CHECK(rf->evaluate(0, 3, corner) != rf->evaluate(0, 3, centre));
+    struct Trace
+    {
+      double operator()(const double* r, const double*, const HostFE&, int) const { return r[0] + r[1] + r[2]; }
+      int ncomps() const { return 1; }
+      std::string name() const { return "trace"; }
+    };
+    auto tr = makeResultFunction(asmb, IKB_RESULT_PK2_STRESS, Trace{});
+    CHECK(tr->ncomps() == 1 && tr->name() == "trace");
+    CHECK(std::abs(tr->evaluate(0, 2, centre) - (all[12] + all[13] + all[14])) <= 1e-12 * std::abs(all[12]));
+    // a new state of the bound requirement drops the cached tables
+    const double before = rf->evaluate(0, 1, centre);
+    req.d[n - 1] += 1e-3;
+    const double after = rf->evaluate(0, (std::int64_t)fes.size() - 1, centre);
+    CHECK(after != all[(fes.size() - 1) * 6]);
+    req.d[n - 1] -= 1e-3;
+    CHECK(rf->evaluate(0, 1, centre) == before);
+    // the linear result type is rejected for the nonlinear element like supportsResultType does
+    bool rejected = false;
+    try {
+      makeResultFunction(asmb, IKB_RESULT_LINEAR_STRESS)->evaluate(0, 0, centre);
+    } catch (const NotImplemented&) {
+      rejected = true;
+    }
+    CHECK(rejected);
+  }
+
   // Newton iteration with the device PCG callable, as NewtonRaphson::solve does (newtonraphson.hh:196-257)
   DevicePCG<A> ls{asmb, 1e-13};
   double rnorm = 0;

@@ -103,3 +103,47 @@ def test_assembler_manipulator_style_callbacks():
     K = dev.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Full)
     assert K[0, 0] == 7.0
     assert dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy) == 1.0  # zero energy at d = 0, plus callback
+
+
+@pytest.mark.gpu
+def test_loads_with_general_dependence_on_the_load_factor():
+    """loads/volume.hh:67-106 and loads/traction.hh:70-138 evaluate f(x, lambda) at every call, whatever its dependence
+    on lambda; the device mirror re-samples a non-proportional load whenever the load factor changes.  R and E against
+    the oracle with the load vector of the respective lambda; a proportional extra nodal load rides along."""
+    import ikarus_b200 as ik
+    import ikarus_oracle as o
+
+    mesh = o.structured_mesh((4, 3), (2.0, 1.5))
+    lam_, mu_ = o.lame_from_E_nu(100.0, 0.3)
+    mat = o.Material("neohooke", lam_, mu_, plane_strain=True)
+    kind = o.ElementKind(2, 1, "gl")
+    flags = o.fix_nodes(mesh, o.boundary_nodes(mesh, 0, 0.0))
+    faces = [(e, 1) for e in range(mesh.n_elem) if abs(mesh.corner_coords[e][:, 0].max() - 2.0) < 1e-12]
+    vol = lambda x, lam: np.array([0.0, -(lam * lam + 1.0) * (1.0 + x[0])])
+    trac = lambda x, lam: np.array([np.sin(lam), 0.25 * x[1]])
+    p = ik.fe.LamesFirstParameterAndShearModulus(mat.lam, mat.mu)
+    sk = ik.skills(ik.nonLinearElastic(ik.planeStrain(ik.Materials.NeoHooke(p))), ik.volumeLoad(vol),
+                   ik.neumannBoundaryLoad(faces, trac))
+    n = mesh.n_nodes * 2
+    fes = ik.makeFE(dict(dim=2, order=1, n_dof=n), sk, mesh.corner_coords, mesh.elem_dofs("interleaved"))
+    dv = ik.DirichletValues(n)
+    dv.container()[:] = flags
+    dev = ik.makeSparseFlatAssembler(fes, dv)
+    point = np.zeros(n)
+    point[-1] = 0.3
+    dev.setExternalLoad(point)  # lambda-proportional nodal load on top of the skills' loads
+    d = 0.01 * np.random.default_rng(3).uniform(-1, 1, n)
+    d[flags] = 0.0
+    for lam in (0.7, 1.9, 0.0):
+        fext = fes.sample_external_load(lam) + lam * point
+        ref = o.FlatAssembler(mesh, kind, mat, flags, fext=fext)
+        req = ik.FERequirements(d, lam)
+        for mode, name in ((ik.DBCOption.Raw, "raw"), (ik.DBCOption.Full, "full"), (ik.DBCOption.Reduced, "reduced")):
+            R = dev.vector(req, ik.VectorAffordance.forces, mode)
+            Rr = ref.vector(d, 1.0, name)
+            assert np.abs(R - Rr).max() <= 1e-12 * np.abs(Rr).max(), (lam, name)
+        E = dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+        Er = ref.scalar(d, 1.0)
+        assert abs(E - Er) <= 1e-12 * max(abs(Er), 1.0), lam
+    # the load at lambda = 0 is not zero: this is what "not proportional" means
+    assert np.abs(fes.sample_external_load(0.0)).max() > 0.1

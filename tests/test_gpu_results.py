@@ -97,3 +97,46 @@ def test_results_match_oracle(case, layout):
             ref = o.stress_at(kind, mat, mesh.corner_coords, u, xi, alpha=alpha, result=name)
             assert S[:, q].shape == ref.shape, (rt, S.shape, ref.shape)
             assert np.abs(S[:, q] - ref).max() <= 1e-11 * np.abs(ref).max(), (rt, q)
+
+
+def test_result_function_mirror_reproduces_the_vertex_stress_table():
+    """io/resultfunction.hh:57-157: ResultFunction::evaluate(comp, element, local) = fe.calculateAt<RT>(req, local)[comp]
+    (through the user function).  On the reference's cube (tests/src/resultcollection.hh:150-163) every vertex value of
+    the table comes out of evaluate(); vertexData() is what a vertex-data writer samples; a user function with its own
+    ncomps()/name() replaces the component access; a new state of the bound requirement drops the cached tables."""
+    mesh = _unit(3)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    d = np.zeros(24)
+    d[6:9] = 1.0
+    exp = np.array(GOLDEN["cube_vertex_stress"]["values"], float)
+    verts = np.array([[(v >> k) & 1 for k in range(3)] for v in range(8)], float)
+    dev = device_assembler(mesh, o.ElementKind(3, 1, "linear"), o.Material("linear", lam, mu), np.zeros(24, dtype=bool))
+    req = ik.FERequirements(d, 0.0)
+    with pytest.raises(Exception):
+        ik.makeResultFunction(dev, RT.linearStress).evaluate(0, 0, verts[0])  # unbound assembler (resultfunction.hh:151)
+    dev.bind(req, ik.elastoStatics, ik.DBCOption.Full)
+    rf = ik.makeResultFunction(dev, RT.linearStress)
+    assert rf.ncomps() == 6 and rf.name() == "linearStress"
+    for v in range(8):
+        for c in range(6):
+            assert abs(rf.evaluate(c, 0, verts[v]) - exp[v, c]) <= 1e-7
+    assert np.allclose(rf.vertexData()[0], exp, atol=1e-7)
+
+    class VonMises:
+        def __call__(self, s, pos, fe, comp):
+            return np.sqrt(0.5 * ((s[0] - s[1])**2 + (s[1] - s[2])**2 + (s[2] - s[0])**2) + 3.0 * (s[3]**2 + s[4]**2 + s[5]**2))
+
+        def ncomps(self):
+            return 1
+
+        def name(self):
+            return "VonMises"
+
+    vm = ik.makeResultFunction(dev, RT.linearStress, VonMises())
+    assert vm.ncomps() == 1 and vm.name() == "VonMises"
+    s = exp[3]
+    ref = np.sqrt(0.5 * ((s[0] - s[1])**2 + (s[1] - s[2])**2 + (s[2] - s[0])**2) + 3.0 * (s[3]**2 + s[4]**2 + s[5]**2))
+    assert abs(vm.evaluate(0, 0, verts[3]) - ref) <= 1e-7 * ref
+    # the requirement is held by reference (assembler/interface.hh:210-222): changing d changes what evaluate() returns
+    d[6:9] = 2.0
+    assert abs(rf.evaluate(0, 0, verts[0]) - 2.0 * exp[0, 0]) <= 2e-7
