@@ -318,6 +318,9 @@ class ElementKind:
     strain: str = "gl"
     eas_m: int = 0
     quad_n: int | None = None  # points per direction; default = order+1 (rule of order 2*order)
+    # which measure the EAS parameters enhance (mechanics/strainenhancements/easfunctions/*.hh): "strain" = LinearStrain /
+    # GreenLagrangeStrain (E4..E21), "dg" = DisplacementGradient, "dgt" = DisplacementGradientTransposed (H4 / H9)
+    eas_function: str = "strain"
 
     @property
     def nodes(self):
@@ -374,6 +377,10 @@ def element_quantities(kind: ElementKind, mat: Material, X, u, alpha=None, want=
     Also returns the EAS blocks (D, L, Rtilde) when eas_m > 0.
     """
     d, nn, nd, m = kind.dim, kind.nodes, kind.ndof, kind.eas_m
+    if m and kind.eas_function in ("dg", "dgt"):
+        if kind.strain != "gl":
+            raise NotImplementedError("EAS::DisplacementGradient enhances a nonlinear element")
+        return _element_quantities_dg(kind, mat, X, u, np.zeros((X.shape[0], m)) if alpha is None else alpha, want)
     s = d * (d + 1) // 2
     ne = X.shape[0]
     pts, wts = kind.rule()
@@ -447,6 +454,97 @@ def element_quantities(kind: ElementKind, mat: Material, X, u, alpha=None, want=
         En = np.full(ne, np.nan)  # EAS elements expose no potential (:302-310)
     out.update(K=K, R=R, E=En)
     return out
+
+
+def eas_Hhat(dim, m, xi):
+    """Reference-element ansatz of the displacement-gradient enhancement: H4 / H9
+    (strainenhancements/easvariants/displacementgradient.hh:76-163): mode p = dim*i + j is (2 xi_j - 1) e_i (x) e_j."""
+    if (dim, m) not in ((2, 4), (3, 9)):
+        raise NotImplementedError(f"EAS variant H{m} in {dim}D")
+    H = np.zeros((m, dim, dim))
+    for i in range(dim):
+        for j in range(dim):
+            H[dim * i + j, i, j] = 2.0 * xi[j] - 1.0
+    return H
+
+
+def _element_quantities_dg(kind: ElementKind, mat: Material, X, u, alpha, want):
+    """EnhancedAssumedStrains with EAS::DisplacementGradient (mechanics/enhancedassumedstrains.hh:258-434 over
+    strainenhancements/easfunctions/displacementgradient.hh:40-282): the enhanced displacement gradient is
+        H = H_c + sum_p alpha_p Htilde_p,  Htilde_p = (detJ0/detJ) J0^-T Hhat_p J0^-1     (helperfunctions.hh:27-36)
+    and E = (H + H^T + H^T H)/2.  Every derivative the reference writes out is an instance of one rule: for a variation
+    dF of the deformation gradient (e_c (x) grad N_a for a nodal dof, Htilde_p for an enhanced one)
+        E,I  = sym(F^T dF_I)  (Voigt, engineering shear)        (:107-165, both wrtCoeff)
+        E,IJ : S = tr(S dF_I^T dF_J)                               (:190-245, wrtCoeff 0, 1, 2)
+    so K_uu, L, D and R, Rtilde are blocks of one generalised tangent / residual."""
+    d, nn, nd, m = kind.dim, kind.nodes, kind.ndof, kind.eas_m
+    transposed = kind.eas_function == "dgt"
+    ne = X.shape[0]
+    pts, wts = kind.rule()
+    G = nd + m
+    Kg = np.zeros((ne, G, G))
+    Rg = np.zeros((ne, G))
+    Jt0, Jt0inv, detJ0 = _geometry(kind, X, np.full(d, 0.5))
+    I = np.eye(d)
+    vp = voigt_pairs(d)
+    if transposed:
+        # compatible gradient and shape-function gradients at the element centre (centerPosition, :327-333)
+        _, dN0 = shape_functions(d, kind.order, np.full(d, 0.5))
+        gradN0 = np.einsum("eji,ai->eaj", Jt0inv, dN0)
+        Fc0 = I + np.einsum("eac,eaj->ecj", u, gradN0)
+    for xi, w in zip(pts, wts):
+        _, dN = shape_functions(d, kind.order, xi)
+        Jt, Jtinv, detJ = _geometry(kind, X, xi)
+        gradN = np.einsum("eji,ai->eaj", Jtinv, dN)
+        Hc = np.einsum("eac,eaj->ecj", u, gradN)
+        Hh = eas_Hhat(d, m, xi)
+        # jacobianInverseTransposed(center) maps reference to physical gradients: it is Jt0inv here
+        Ht = np.einsum("e,eik,pkl,ejl->epij", detJ0 / detJ, Jt0inv, Hh, Jt0inv)
+        Hsum = np.einsum("epij,ep->eij", Ht, alpha)
+        gN = gradN
+        if transposed:
+            # H = H_c + F_c0 Htilde^T (displacementgradienttransposed.hh:343-360); a nodal variation then sees the
+            # gradient g_a + Htilde g_a^0 (dNtilde, :133-141)
+            H = Hc + np.einsum("eik,ejk->eij", Fc0, Hsum)
+            gN = gradN + np.einsum("ejk,eak->eaj", Hsum, gradN0)
+        else:
+            H = Hc + Hsum
+        F = I + H
+        Em = 0.5 * (H + np.swapaxes(H, -1, -2) + np.einsum("eki,ekj->eij", H, H))
+        psi, S, C = mat.evaluate(to_voigt(Em, strain=True))
+        Sm = from_voigt(S, strain=False)
+        # variations of F: nodal dofs (a, c) -> e_c (x) grad N_a, then the enhanced modes
+        dF = np.zeros((ne, G, d, d))
+        for a in range(nn):
+            for c in range(d):
+                dF[:, a * d + c, c, :] = gN[:, a, :]
+        dF[:, nd:] = np.einsum("eik,epjk->epij", Fc0, Ht) if transposed else Ht
+        if transposed:
+            # the one non-vanishing second variation: d_alpha_p d_u(a,c) F = e_c (x) (Htilde_p g_a^0); its work with
+            # P = F S is the dNXHtilde part of E,ad (:297-318)
+            P = np.einsum("eik,ekj->eij", F, Sm)
+            hg = np.einsum("epjk,eak->epaj", Ht, gradN0)
+            mixed = np.einsum("ecj,epaj,e->epac", P, hg, w * detJ).reshape(ne, m, nd)
+            Kg[:, nd:, :nd] += mixed
+            Kg[:, :nd, nd:] += np.swapaxes(mixed, -1, -2)
+        FtdF = np.einsum("eki,egkj->egij", F, dF)
+        Bg = np.zeros((ne, G, len(vp)))
+        for q, (i, j) in enumerate(vp):
+            Bg[:, :, q] = FtdF[:, :, i, i] if i == j else FtdF[:, :, i, j] + FtdF[:, :, j, i]
+        wd = w * detJ
+        Kg += np.einsum("egp,epq,ehq,e->egh", Bg, C, Bg, wd, optimize=True)
+        Kg += np.einsum("eij,egki,ehkj,e->egh", Sm, dF, dF, wd, optimize=True)
+        Rg += np.einsum("egp,ep,e->eg", Bg, S, wd)
+    K, R = Kg[:, :nd, :nd], Rg[:, :nd]
+    Dm, Lf, Rt = Kg[:, nd:, nd:], Kg[:, nd:, :nd], Rg[:, nd:]
+    Dinv = np.linalg.inv(Dm)
+    Kc = K - np.einsum("emi,emn,enj->eij", Lf, Dinv, Lf, optimize=True)  # enhancedassumedstrains.hh:292-296
+    iu = np.triu_indices(nd)
+    Ks = np.zeros_like(Kc)
+    Ks[:, iu[0], iu[1]] = Kc[:, iu[0], iu[1]]
+    Ks = Ks + np.swapaxes(np.triu(Ks, 1), -1, -2)
+    Rc = R - np.einsum("emi,emn,en->ei", Lf, Dinv, Rt, optimize=True)  # :341-345
+    return dict(K=Ks, R=Rc, E=np.full(ne, np.nan), D=Dm.copy(), L=Lf.copy(), Rtilde=Rt.copy())
 
 
 def eas_update_alpha(kind, mat, X, u, alpha, du):
