@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libikb200.so")
 
-IKB_ABI_VERSION = 2
+IKB_ABI_VERSION = 3
 OK, EINVAL, ECUDA, ESTATE, ENOTIMPL, EMATERIAL, ENCCL = 0, -1, -2, -3, -4, -5, -6
 STRAIN_LINEAR, STRAIN_GL = 0, 1
 MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE = 0, 1, 2
@@ -19,7 +19,7 @@ class Desc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("dim", C.c_int32), ("order", C.c_int32), ("strain", C.c_int32),
                 ("material", C.c_int32), ("plane_strain", C.c_int32), ("eas_m", C.c_int32), ("device", C.c_int32),
                 ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64),
-                ("reduce_tol", C.c_double)]
+                ("reduce_tol", C.c_double), ("eas_function", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TcgInfo(C.Structure):
@@ -31,6 +31,7 @@ class TcgInfo(C.Structure):
 
 
 PRECOND_IDENTITY, PRECOND_DIAGONAL = 0, 1
+EAS_STRAIN, EAS_DISPLACEMENT_GRADIENT, EAS_DISPLACEMENT_GRADIENT_TRANSPOSED = 0, 1, 2
 
 # every symbol include/ikb200.h declares (tests check that the library exports all of them)
 SYMBOLS = {

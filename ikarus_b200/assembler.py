@@ -146,11 +146,12 @@ class _FlatAssemblerBase:
         mat = fes.solid.material
         desc = capi.Desc(capi.IKB_ABI_VERSION, fes.dim, fes.order, fes.solid.strain, mat.code, int(mat.reduced),
                          fes.numberOfInternalVariables(), device, mat.params.lambda_, mat.params.mu, len(fes), self._n,
-                         float(mat.reduce_tol))
+                         float(mat.reduce_tol), fes.eas.function if fes.eas else 0, 0)
         self._h = C.c_void_p()
         rc = self._lib.ikb_create(C.byref(self._h), C.byref(desc))
         if rc == capi.ENOTIMPL:
-            raise NotImplementedInReference("EAS is only supported for Q1 and H1 elements with m in {4,5,7} / {9,21}")
+            raise NotImplementedInReference("EAS is only supported for Q1 and H1 elements with m in {4,5,7} / {9,21} "
+                                            "(displacement-gradient forms: nonlinear element, m = 4 / 9)")
         if rc != 0:
             raise ValueError(f"ikb_create failed with code {rc}")
         self._check(self._lib.ikb_upload_mesh(self._h, capi.ptr(fes.corner_coords), capi.ptr(fes.elem_dofs)))

@@ -7,6 +7,7 @@
 
 #include "ikb_dist.cuh"
 #include "ikb_elem_eas.cuh"
+#include "ikb_elem_easdg.cuh"
 #include "ikb_elem_h8mma.cuh"
 #include "ikb_elem_q1.cuh"
 #include "ikb_elem_q2.cuh"
@@ -43,7 +44,17 @@ cudaError_t launchEasForm(Handle* h, const EasArgs& EA) {
   return launchElemEas<D, FORM_NH, M>(EA, h->stream);
 }
 
+// displacement-gradient enhancement (ikb_elem_easdg.cuh)
+template <int D>
+cudaError_t launchEasDg(Handle* h, const EasArgs& EA) {
+  const bool tr = h->easFunction == IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED;
+  if (h->form == FORM_SVK) return tr ? launchElemEasDg<D, FORM_SVK, true>(EA, h->stream) : launchElemEasDg<D, FORM_SVK, false>(EA, h->stream);
+  if (h->form == FORM_NH) return tr ? launchElemEasDg<D, FORM_NH, true>(EA, h->stream) : launchElemEasDg<D, FORM_NH, false>(EA, h->stream);
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launchEas(Handle* h, const EasArgs& EA) {
+  if (h->easFunction != IKB_EAS_STRAIN) return h->dim == 2 ? launchEasDg<2>(h, EA) : launchEasDg<3>(h, EA);
   if (h->dim == 2) {
     if (h->easM == 4) return launchEasForm<2, 4>(h, EA);
     if (h->easM == 5) return launchEasForm<2, 5>(h, EA);
@@ -1044,6 +1055,13 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   const bool easOk = m == 0 || (desc->order == 1 && ((desc->dim == 2 && (m == 4 || m == 5 || m == 7)) ||
                                                      (desc->dim == 3 && (m == 9 || m == 21))));
   if (!easOk) return IKB_ENOTIMPL;  // Dune::NotImplemented in the reference (enhancedassumedstrains.hh:250-256)
+  if (desc->eas_function < IKB_EAS_STRAIN || desc->eas_function > IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED) return IKB_EINVAL;
+  if (m && desc->eas_function != IKB_EAS_STRAIN) {
+    // H4 / H9 on the nonlinear element (enhancedassumedstrains.hh:85-90; easvariants.hh); plane stress is served for
+    // the strain enhancements only
+    if (form == FORM_LE) return IKB_EINVAL;
+    if (m != desc->dim * desc->dim || desc->plane_strain == IKB_REDUCE_PLANE_STRESS) return IKB_ENOTIMPL;
+  }
 
   int dev = desc->device;
   if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return IKB_ECUDA;
@@ -1060,6 +1078,7 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   h->npair = h->nn * (h->nn + 1) / 2;
   h->form = form;
   h->easM = m;
+  h->easFunction = m ? desc->eas_function : IKB_EAS_STRAIN;
   h->nElem = desc->n_elem;
   h->nDof = desc->n_dof;
   h->nNodes = desc->n_dof / desc->dim;
@@ -1949,6 +1968,8 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
   const bool linearType = resultType == IKB_RESULT_LINEAR_STRESS || resultType == IKB_RESULT_LINEAR_STRESS_FULL;
   if (linearType != (h->form == FORM_LE))  // supportsResultType (linearelastic.hh / nonlinearelastic.hh)
     return fail(h, IKB_ENOTIMPL, "The requested result type is not supported by this element");
+  if (h->easM && h->easFunction != IKB_EAS_STRAIN)
+    return fail(h, IKB_ENOTIMPL, "results at local positions are not built for the displacement-gradient enhancements");
   int rc;
   if ((rc = ensureSolution(h))) return rc;
   joinSolution(h);

@@ -1,0 +1,577 @@
+// EAS with an enhanced DISPLACEMENT GRADIENT: EAS::DisplacementGradient and EAS::DisplacementGradientTransposed with the
+// H4 (Quad4) / H9 (Hex8) ansatz.
+//
+// Replaces EnhancedAssumedStrains::calculateMatrixImpl / calculateVectorImpl / updateStateImpl
+// (ikarus/finiteelements/mechanics/enhancedassumedstrains.hh:225-248, 258-348, 378-434) over
+// strainenhancements/easfunctions/displacementgradient.hh:40-282, displacementgradienttransposed.hh:40-360 and the
+// ansatz of strainenhancements/easvariants/displacementgradient.hh:76-163 (helperfunctions.hh:27-36).
+//
+// The enhanced deformation gradient is  F = I + H_c + sum_p alpha_p Ht_p   (transposed form: I + H_c + F_c0 (sum_p
+// alpha_p Ht_p)^T with F_c0 the compatible F at the element centre),  Ht_p = (detJ0/detJ) J0^-T Hhat_p J0^-1  and
+// Hhat_(D i + j) = (2 xi_j - 1) e_i (x) e_j, i.e. Ht_p is the rank-one matrix s t_j (J0^-T e_i)(J0^-T e_j)^T.
+// Every derivative the reference spells out is an instance of one rule.  For a variation dF_I of F -- e_c (x) g_a for a
+// nodal dof (g_a = grad N_a, plus Ht g_a^0 in the transposed form), Ht_p (resp. F_c0 Ht_p^T) for an enhanced one:
+//     E,I = sym(F^T dF_I),      E,IJ : S = tr(S dF_I^T dF_J)  (+ P : d_I d_J F, non-zero only for the (alpha, d) pairs of
+//     the transposed form: d_p d_(a,c) F = e_c (x) Ht_p g_a^0),
+// so K_uu, L, D and R, Rtilde are blocks of ONE generalised tangent over the G = N D + D^2 generalised dofs, with the
+// isotropic moduli in the factored form of ikb_elem_q1.cuh:  B_I : CC : B_J = l' (X:B_I)(X:B_J) + 2 m' tr(X B_I X B_J).
+//
+// One warp per element.  Per Gauss point every lane evaluates the kinematics and the material (redundantly: a few
+// hundred flops), writes the record of its own generalised dof(s) -- B, X B X, X:B, dF, dF S -- to shared memory, and
+// the G(G+1)/2 dof pairs are accumulated in registers, 18 pairs per lane for Hex8.  The enhanced block is then
+// eliminated in shared memory (Gauss-Jordan with partial pivoting on [D | L | Rtilde]; the reference inverts D), the
+// condensed K_e leaves in the symmetric-packed staging form of the other element kernels.  This is the first, plain
+// formulation of the variant (parity first); it moves about 2 MB through shared memory per Hex8 element.
+#pragma once
+#include "ikb_elem_eas.cuh"
+
+namespace ikb {
+
+template <int D, bool TR>
+struct DgCfg {
+  static constexpr int N = 1 << D, ND = N * D, M = D * D, G = ND + M;
+  static constexpr int SYM = D * (D + 1) / 2;
+  static constexpr int NP = G * (G + 1) / 2;     // generalised dof pairs I <= J
+  static constexpr int NS = (NP + 31) / 32;      // pairs per lane
+  // record of a generalised dof at a Gauss point
+  static constexpr int O_B = 0, O_XBX = SYM, O_T = 2 * SYM, O_DF = 2 * SYM + 1, O_DFS = O_DF + D * D;
+  static constexpr int O_MA = O_DFS + D * D, O_MB = O_MA + D * D;  // transposed form: the mixed second variation
+  static constexpr int REC0 = TR ? O_MB + D * D : O_MA;
+  static constexpr int REC = REC0 | 1;           // odd stride: lanes on different dofs hit different banks
+  static constexpr int GS = G | 1;               // row stride of the generalised tangent
+  static constexpr int O_REC = 0, O_KG = O_REC + G * REC, O_RG = O_KG + G * GS, O_X = O_RG + G, O_U = O_X + ND,
+                       O_AL = O_U + ND, O_DU = O_AL + M, O_RHS = O_DU + ND;
+  static constexpr int WARP_DOUBLES = (O_RHS + M + 1) / 2 * 2;
+  static constexpr int WARPS = 4;
+  static constexpr size_t SMEM = (size_t)WARPS * WARP_DOUBLES * 8;
+};
+
+// symmetric index (i,j) -> 0..SYM-1, row-major upper packing
+template <int D>
+__device__ __forceinline__ constexpr int symI(int i, int j) {
+  return symIdx<D>(i, j);
+}
+
+template <int D, int FORM, bool TR>
+__global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(EasArgs EA) {
+  static_assert(FORM == FORM_SVK || FORM == FORM_NH, "the displacement gradient enhances the nonlinear element");
+  using C = DgCfg<D, TR>;
+  constexpr int N = C::N, ND = C::ND, M = C::M, G = C::G, SYM = C::SYM, REC = C::REC, GS = C::GS;
+  constexpr unsigned FULL = 0xffffffffu;
+  const ElemArgs& A = EA.E;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * C::WARPS + warp;
+  if (e >= A.nElem) return;
+  double* ws = smem + (size_t)warp * C::WARP_DOUBLES;
+  double* rec = ws + C::O_REC;
+  double* Kg = ws + C::O_KG;
+  double* Rg = ws + C::O_RG;
+  double* Xs = ws + C::O_X;
+  double* us = ws + C::O_U;
+  double* al = ws + C::O_AL;
+  double* dus = ws + C::O_DU;
+  double* rhs = ws + C::O_RHS;
+
+  // ---- element data
+  for (int t = lane; t < ND; t += 32) {
+    const int a = t / D, c = t - a * D;
+    Xs[t] = __ldg(A.X + (size_t)t * A.nElem + e);  // corner a, coordinate c (relative to corner 0)
+    const int64_t node = __ldg(A.elemNode + (size_t)a * A.nElem + e);
+    const int64_t dof = dofOf(A.layout, D, A.nNodes, node, c);
+    us[t] = __ldg(A.U + dof);
+    dus[t] = EA.updateMode ? __ldg(EA.dU + dof) : 0.0;
+  }
+  for (int t = lane; t < M; t += 32) al[t] = EA.alpha[(size_t)e * M + t];
+  __syncwarp();
+
+  // the pairs of this lane: t = lane + 32 s  ->  (I, J), I <= J, rows of G - I pairs each
+  uint16_t pairIJ[C::NS];
+  {
+    int I = 0, off = 0;  // off = index of pair (I, I)
+#pragma unroll
+    for (int s = 0; s < C::NS; ++s) {
+      const int t = lane + 32 * s;
+      while (I < G - 1 && t >= off + (G - I)) {
+        off += G - I;
+        ++I;
+      }
+      const int J = I + (t - off);
+      pairIJ[s] = (t < C::NP) ? (uint16_t)(I | (J << 8)) : (uint16_t)0xffff;
+    }
+  }
+  double acc[C::NS];
+#pragma unroll
+  for (int s = 0; s < C::NS; ++s) acc[s] = 0.0;
+  double rI[2] = {0.0, 0.0};  // R_gen of dofs lane and lane + 32
+
+  // ---- element centre: J0^-T, detJ0, (transposed form) grad N^0 and F_c0
+  double JI0[D][D], detJ0;
+  double Fc0[D][D];
+  {
+    double Jt[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) Jt[i][k] = 0.0;
+    const double half = (D == 3) ? 0.25 : 0.5;  // dN_c/dxi_i at the centre: +-0.5^(D-1)
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double dn = ((c >> i) & 1) ? half : -half;
+#pragma unroll
+        for (int k = 0; k < D; ++k) Jt[i][k] = fma(dn, Xs[c * D + k], Jt[i][k]);
+      }
+    detJ0 = fabs(invSmall<D>(Jt, JI0));
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int j = 0; j < D; ++j) Fc0[c][j] = (c == j) ? 1.0 : 0.0;
+    if constexpr (TR) {
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        double g0[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) s = fma(JI0[j][i], ((a >> i) & 1) ? half : -half, s);
+          g0[j] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c)
+#pragma unroll
+          for (int j = 0; j < D; ++j) Fc0[c][j] = fma(us[a * D + c], g0[j], Fc0[c][j]);
+      }
+    }
+  }
+
+  // ---- Gauss points
+#pragma unroll 1
+  for (int g = 0; g < N; ++g) {
+    const double lo = 0.5 - 0.28867513459481287, hi = 0.5 + 0.28867513459481287;
+    double xi[D], om[D], tt[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      xi[k] = ((g >> k) & 1) ? hi : lo;
+      om[k] = 1.0 - xi[k];
+      tt[k] = 2.0 * xi[k] - 1.0;
+    }
+    double Jt[D][D], Hx[D][D];  // Hx[c][i] = sum_a u_a[c] dN_a/dxi_i
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) Jt[i][k] = Hx[i][k] = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double dn = ((c >> i) & 1) ? 1.0 : -1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+          if (k != i) dn *= ((c >> k) & 1) ? xi[k] : om[k];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          Jt[i][k] = fma(dn, Xs[c * D + k], Jt[i][k]);
+          Hx[k][i] = fma(dn, us[c * D + k], Hx[k][i]);
+        }
+      }
+    double Ji[D][D];
+    const double detJ = fabs(invSmall<D>(Jt, Ji));
+    double wd = detJ;
+#pragma unroll
+    for (int k = 0; k < D; ++k) wd *= 0.5;
+    const double sc = detJ0 / detJ;
+    // compatible gradient H_c[c][j] = sum_i Hx[c][i] Ji[j][i]; enhanced part Ht = sc J0^-T (alpha_(i,j) t_j) J0^-1
+    double H[D][D], Hs[D][D];
+    {
+      double T1[D][D];  // (alpha_(i,j) t_j) J0^-1 :  T1[i][l] = sum_j alpha_(Di+j) t_j JI0[l][j]
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) s = fma(al[D * i + j] * tt[j], JI0[l][j], s);
+          T1[i][l] = s;
+        }
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) s = fma(JI0[k][i], T1[i][l], s);
+          Hs[k][l] = sc * s;
+        }
+#pragma unroll
+      for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) s = fma(Hx[c][i], Ji[j][i], s);
+          if constexpr (TR) {
+            // H = H_c + F_c0 Hs^T
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(Fc0[c][k], Hs[j][k], s);
+          } else {
+            s += Hs[c][j];
+          }
+          H[c][j] = s;
+        }
+    }
+    double F[D][D], Cm[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) F[i][j] = H[i][j] + (i == j ? 1.0 : 0.0);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(F[k][i], F[k][j], s);
+        Cm[i][j] = s;
+      }
+    // material: S, X, l', m'  (svk.hh; neohooke.hh:79-142 with C = 2E + I; plane strain: the 3D law at zero
+    // out-of-plane strain, vanishingstrain.hh)
+    double Sm[D][D], Xm[D][D], lp, mp;
+    if constexpr (FORM == FORM_SVK) {
+      double tr = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) tr += 0.5 * (Cm[i][i] - 1.0);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          const double E = 0.5 * (Cm[i][j] - (i == j ? 1.0 : 0.0));
+          Sm[i][j] = 2.0 * A.mu * E + (i == j ? A.lambda * tr : 0.0);
+          Xm[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+      lp = A.lambda;
+      mp = A.mu;
+    } else {
+      const double detC = invSmall<D>(Cm, Xm);
+      if (!(detC > 0.0) && lane == 0) atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+      const double lnJ = 0.5 * log(detC);
+      lp = A.lambda;
+      mp = A.mu - A.lambda * lnJ;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) Sm[i][j] = (i == j ? A.mu : 0.0) - mp * Xm[i][j];
+    }
+
+    // ---- record(s) of this lane's generalised dof(s)
+    __syncwarp();  // the pair loop of the previous Gauss point has read the records
+#pragma unroll
+    for (int rnd = 0; rnd < (G + 31) / 32; ++rnd) {
+      const int I = lane + 32 * rnd;
+      if (I < G) {
+        double dF[D][D], mA[D][D], mB[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) dF[i][j] = mA[i][j] = mB[i][j] = 0.0;
+        if (I < ND) {
+          const int a = I / D, c = I - a * D;
+          double dn[D], gph[D];
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double v = ((a >> i) & 1) ? 1.0 : -1.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+              if (k != i) v *= ((a >> k) & 1) ? xi[k] : om[k];
+            dn[i] = v;
+          }
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fma(Ji[j][i], dn[i], s);
+            gph[j] = s;
+          }
+          if constexpr (TR) {
+            const double half = (D == 3) ? 0.25 : 0.5;
+            double g0[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              double s = 0.0;
+#pragma unroll
+              for (int i = 0; i < D; ++i) s = fma(JI0[j][i], ((a >> i) & 1) ? half : -half, s);
+              g0[j] = s;
+            }
+            // g_a + Hs g_a^0 (dNtilde, displacementgradienttransposed.hh:133-141); mA = e_c (x) g_a^0
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+#pragma unroll
+              for (int k = 0; k < D; ++k) gph[j] = fma(Hs[j][k], g0[k], gph[j]);
+            }
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+              for (int j = 0; j < D; ++j) mA[r][j] = (r == c) ? g0[j] : 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int j = 0; j < D; ++j) dF[r][j] = (r == c) ? gph[j] : 0.0;
+        } else {
+          const int p = I - ND, i0 = p / D, j0 = p - i0 * D;
+          double Ht[D][D];
+          const double f = sc * (j0 == 0 ? tt[0] : (j0 == 1 ? tt[1] : tt[D - 1]));
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+              double ki = 0.0, lj = 0.0;
+#pragma unroll
+              for (int q = 0; q < D; ++q) {
+                ki = (q == i0) ? JI0[k][q] : ki;
+                lj = (q == j0) ? JI0[l][q] : lj;
+              }
+              Ht[k][l] = f * ki * lj;
+            }
+          if constexpr (TR) {
+            // dF = F_c0 Ht^T;  mB = P Ht with P = F S (the work of d_p d_(a,c) F = e_c (x) Ht g_a^0)
+            double P[D][D];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                double s = 0.0, pp = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                  s = fma(Fc0[r][k], Ht[j][k], s);
+                  pp = fma(F[r][k], Sm[k][j], pp);
+                }
+                dF[r][j] = s;
+                P[r][j] = pp;
+              }
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+              for (int k = 0; k < D; ++k) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) s = fma(P[r][j], Ht[j][k], s);
+                mB[r][k] = s;
+              }
+          } else {
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+              for (int j = 0; j < D; ++j) dF[r][j] = Ht[r][j];
+          }
+        }
+        // B = sym(F^T dF), X B X, X:B, dF S
+        double FtdF[D][D], Bm[D][D], XB[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(F[k][i], dF[k][j], s);
+            FtdF[i][j] = s;
+          }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) Bm[i][j] = 0.5 * (FtdF[i][j] + FtdF[j][i]);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(Xm[i][k], Bm[k][j], s);
+            XB[i][j] = s;
+          }
+        double* r = rec + I * REC;
+        double tI = 0.0, rS = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = i; j < D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(XB[i][k], Xm[k][j], s);
+            r[C::O_B + symI<D>(i, j)] = Bm[i][j];
+            r[C::O_XBX + symI<D>(i, j)] = s;
+          }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          tI += XB[i][i];
+#pragma unroll
+          for (int j = 0; j < D; ++j) rS = fma(Bm[i][j], Sm[i][j], rS);
+        }
+        r[C::O_T] = tI;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(dF[i][k], Sm[k][j], s);
+            r[C::O_DF + i * D + j] = dF[i][j];
+            r[C::O_DFS + i * D + j] = s;
+            if constexpr (TR) {
+              r[C::O_MA + i * D + j] = mA[i][j];
+              r[C::O_MB + i * D + j] = mB[i][j];
+            }
+          }
+        rI[rnd] = fma(wd, rS, rI[rnd]);
+      }
+    }
+    __syncwarp();
+
+    // ---- pairs
+    const double c1 = wd * lp, c2 = 2.0 * wd * mp;
+#pragma unroll
+    for (int s = 0; s < C::NS; ++s) {
+      const unsigned pj = pairIJ[s];
+      if (pj != 0xffffu) {
+        const double* a = rec + (pj & 0xffu) * REC;
+        const double* b = rec + (pj >> 8) * REC;
+        double mat = 0.0, geo = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = i; j < D; ++j) {
+            const double v = a[C::O_B + symI<D>(i, j)] * b[C::O_XBX + symI<D>(i, j)];
+            mat += (i == j) ? v : 2.0 * v;
+          }
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) geo = fma(a[C::O_DF + q], b[C::O_DFS + q], geo);
+        if constexpr (TR) {
+#pragma unroll
+          for (int q = 0; q < D * D; ++q)
+            geo = fma(a[C::O_MA + q], b[C::O_MB + q], fma(a[C::O_MB + q], b[C::O_MA + q], geo));
+        }
+        acc[s] += c1 * a[C::O_T] * b[C::O_T] + c2 * mat + wd * geo;
+      }
+    }
+  }
+
+  // ---- generalised tangent and residual to shared memory
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < C::NS; ++s) {
+    const unsigned pj = pairIJ[s];
+    if (pj != 0xffffu) {
+      const int I = pj & 0xffu, J = pj >> 8;
+      Kg[I * GS + J] = acc[s];
+      Kg[J * GS + I] = acc[s];
+    }
+  }
+#pragma unroll
+  for (int rnd = 0; rnd < (G + 31) / 32; ++rnd)
+    if (lane + 32 * rnd < G) Rg[lane + 32 * rnd] = rI[rnd];
+  __syncwarp();
+  // right-hand side of the enhanced block: Rtilde, in update mode Rtilde + L du (enhancedassumedstrains.hh:243)
+  if (lane < M) {
+    double s = Rg[ND + lane];
+    if (EA.updateMode)
+      for (int j = 0; j < ND; ++j) s = fma(Kg[(ND + lane) * GS + j], dus[j], s);
+    rhs[lane] = s;
+  }
+  __syncwarp();
+
+  // ---- [D | L | rhs] -> [I | D^-1 L | D^-1 rhs]: Gauss-Jordan with partial pivoting on the rows ND.. of Kg.  The
+  // columns ND.. of the rows below ND keep L^T for the condensation.
+  for (int k = 0; k < M; ++k) {
+    int piv = k;
+    double best = fabs(Kg[(ND + k) * GS + ND + k]);
+    for (int r = k + 1; r < M; ++r) {
+      const double v = fabs(Kg[(ND + r) * GS + ND + k]);
+      if (v > best) {
+        best = v;
+        piv = r;
+      }
+    }
+    __syncwarp();
+    if (piv != k) {
+      for (int c = lane; c <= G; c += 32) {
+        double* x = (c < G) ? &Kg[(ND + k) * GS + c] : &rhs[k];
+        double* y = (c < G) ? &Kg[(ND + piv) * GS + c] : &rhs[piv];
+        const double t = *x;
+        *x = *y;
+        *y = t;
+      }
+      __syncwarp();
+    }
+    const double ip = 1.0 / Kg[(ND + k) * GS + ND + k];
+    double f[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) f[r] = Kg[(ND + r) * GS + ND + k];
+    __syncwarp();
+    for (int c = lane; c <= G; c += 32) {
+      double* rowk = (c < G) ? &Kg[(ND + k) * GS + c] : &rhs[k];
+      const double pk = *rowk * ip;
+      *rowk = pk;
+#pragma unroll
+      for (int r = 0; r < M; ++r)
+        if (r != k) {
+          double* x = (c < G) ? &Kg[(ND + r) * GS + c] : &rhs[r];
+          *x = fma(-f[r], pk, *x);
+        }
+    }
+    __syncwarp();
+  }
+
+  if (EA.updateMode) {
+    if (lane < M) EA.alpha[(size_t)e * M + lane] -= rhs[lane];
+    return;
+  }
+
+  // ---- condensation: K_uu -= L^T (D^-1 L) on the upper triangle, R_u -= L^T (D^-1 Rtilde)
+  // (enhancedassumedstrains.hh:292-296, 341-345)
+  for (int t = lane; t < ND * (ND + 1) / 2; t += 32) {
+    int I = 0, off = 0;
+    while (t >= off + (ND - I)) {
+      off += ND - I;
+      ++I;
+    }
+    const int J = I + (t - off);
+    double s = Kg[I * GS + J];
+#pragma unroll
+    for (int p = 0; p < M; ++p) s = fma(-Kg[I * GS + ND + p], Kg[(ND + p) * GS + J], s);
+    Kg[I * GS + J] = s;
+  }
+  if (lane < ND && (A.what & IKB_VECTOR)) {
+    double s = Rg[lane];
+#pragma unroll
+    for (int p = 0; p < M; ++p) s = fma(-Kg[lane * GS + ND + p], rhs[p], s);
+    A.Rst[(size_t)e * ND + lane] = s;
+  }
+  __syncwarp();
+  if (A.what & IKB_MATRIX) {
+    // symmetric-packed staging: pair p = k*N + a holds block (a, (a+k) mod N), k <= N/2 (k == N/2: a < N/2)
+    constexpr int NPAIR = N * (N + 1) / 2, DD = D * D;
+    double* Ke = A.Kst + (size_t)e * NPAIR * DD;
+    for (int t = lane; t < NPAIR * DD; t += 32) {
+      const int p = t / DD, q = t - p * DD, i = q / D, j = q - i * D;
+      const int k = p / N, a = p - k * N, b = (a + k) & (N - 1);
+      const int I = a * D + i, J = b * D + j;
+      Ke[t] = (I <= J) ? Kg[I * GS + J] : Kg[J * GS + I];
+    }
+  }
+}
+
+template <int D, int FORM, bool TR>
+cudaError_t launchElemEasDg(const EasArgs& A, cudaStream_t st) {
+  using C = DgCfg<D, TR>;
+  cudaError_t e =
+      cudaFuncSetAttribute(elem_easdg_kernel<D, FORM, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((A.E.nElem + C::WARPS - 1) / C::WARPS);
+  if (grid == 0) return cudaSuccess;
+  elem_easdg_kernel<D, FORM, TR><<<grid, 32 * C::WARPS, C::SMEM, st>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace ikb

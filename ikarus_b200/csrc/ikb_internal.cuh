@@ -68,6 +68,7 @@ __host__ __device__ inline int64_t dofOf(int layout, int dim, int64_t nNodes, in
 struct Handle {
   ikb_desc desc{};
   int dim = 0, order = 0, nn = 0, nd = 0, nc = 0, npair = 0, form = 0, easM = 0;
+  int easFunction = 0;  // IKB_EAS_*
   int layout = 0;
   int64_t nElem = 0, nDof = 0, nNodes = 0;
   int device = 0;

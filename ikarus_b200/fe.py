@@ -75,10 +75,21 @@ class _Solid:
     material: _Material
 
 
+# EAS::LinearStrain / GreenLagrangeStrain / DisplacementGradient / DisplacementGradientTransposed
+# (mechanics/strainenhancements/easfunctions/*.hh) -> IKB_EAS_*
+_EAS_FUNCTIONS = {"GreenLagrangeStrain": capi.EAS_STRAIN, "LinearStrain": capi.EAS_STRAIN,
+                  "DisplacementGradient": capi.EAS_DISPLACEMENT_GRADIENT,
+                  "DisplacementGradientTransposed": capi.EAS_DISPLACEMENT_GRADIENT_TRANSPOSED}
+
+
 @dataclass(frozen=True)
 class _EAS:
     m: int
     enhanced: str = "GreenLagrangeStrain"
+
+    @property
+    def function(self):
+        return _EAS_FUNCTIONS[self.enhanced]
 
 
 @dataclass(frozen=True)
@@ -107,9 +118,10 @@ def nonLinearElastic(mat):
 
 
 def eas(numberOfInternalVariables=0, enhanced="GreenLagrangeStrain"):
-    """mechanics/enhancedassumedstrains.hh eas<ES>(m) with ES in {LinearStrain, GreenLagrangeStrain}."""
-    if enhanced not in ("GreenLagrangeStrain", "LinearStrain"):
-        raise NotImplementedError(f"EAS enhancement {enhanced} is outside the device hot path (SURVEY 8f)")
+    """mechanics/enhancedassumedstrains.hh eas<ES>(m) with ES in {LinearStrain, GreenLagrangeStrain, DisplacementGradient,
+    DisplacementGradientTransposed} (the last two with m = dim*dim: H4 / H9)."""
+    if enhanced not in _EAS_FUNCTIONS:
+        raise NotImplementedError(f"unknown EAS enhancement {enhanced}")
     return _EAS(int(numberOfInternalVariables), enhanced)
 
 

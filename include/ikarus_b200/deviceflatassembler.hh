@@ -33,6 +33,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -97,6 +98,8 @@ struct ElementAccess
   static double lambda(const FE& fe) { return fe.lambda; }
   static double mu(const FE& fe) { return fe.mu; }
   static int numberOfInternalVariables(const FE& fe) { return fe.easM; }
+  /** IKB_EAS_*: the ES of eas<ES>(m) (mechanics/enhancedassumedstrains.hh:69) */
+  static int easFunction(const FE& fe) { return fe.easFunction; }
   /** FEHelper::globalIndices(fe, dofs) (finiteelements/fehelper.hh:194-197), flat index [0] */
   static void globalIndices(const FE& fe, std::vector<std::int64_t>& dofs) {
     dofs.insert(dofs.end(), fe.dofs.begin(), fe.dofs.end());
@@ -169,6 +172,22 @@ struct ElementAccess<FE>
       return fe.numberOfInternalVariables();
     else
       return 0;
+  }
+  static int easFunction(const FE&) {
+    if constexpr (requires { typename FE::EnhancedStrainFunction; }) {
+      using ES = typename FE::EnhancedStrainFunction;
+      if constexpr (requires { ES::name(); }) {
+        // EAS::DisplacementGradient / DisplacementGradientTransposed (strainenhancements/easfunctions/
+        // displacementgradient.hh:256, displacementgradienttransposed.hh:322)
+        constexpr std::string_view n = "Displacement Gradient (Transposed)";
+        const std::string name = ES::name();
+        if (name == n)
+          return IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED;
+        if (name == n.substr(0, 21))
+          return IKB_EAS_DISPLACEMENT_GRADIENT;
+      }
+    }
+    return IKB_EAS_STRAIN;
   }
   static void globalIndices(const FE& fe, std::vector<std::int64_t>& dofs) {
     std::vector<typename FE::GlobalIndex> ids;
@@ -250,6 +269,7 @@ public:
         desc.plane_strain = A::reduction(fe);
         desc.reduce_tol   = A::reductionTolerance(fe);
         desc.eas_m        = A::numberOfInternalVariables(fe);
+        desc.eas_function = A::easFunction(fe);
         desc.lambda       = A::lambda(fe);
         desc.mu           = A::mu(fe);
       }

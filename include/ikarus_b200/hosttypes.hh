@@ -130,6 +130,7 @@ struct HostSparseMatrix
 struct HostFE
 {
   int dim{3}, order{1}, strain{1}, material{2}, easM{0};
+  int easFunction{0};  // IKB_EAS_*
   bool planeStrain{false}, planeStress{false};
   double reduceTol{1e-12};
   double lambda{0.0}, mu{0.0};

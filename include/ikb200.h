@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IKB_ABI_VERSION 2
+#define IKB_ABI_VERSION 3
 
 typedef struct ikb_handle_s* ikb_handle;
 
@@ -52,6 +52,9 @@ enum { IKB_DBC_RAW = 0, IKB_DBC_REDUCED = 1, IKB_DBC_FULL = 2 };
 enum { IKB_SCALAR = 1, IKB_VECTOR = 2, IKB_MATRIX = 4 };
 
 enum { IKB_REDUCE_NONE = 0, IKB_REDUCE_PLANE_STRAIN = 1, IKB_REDUCE_PLANE_STRESS = 2 };
+/* EAS::LinearStrain / EAS::GreenLagrangeStrain (by the element's strain tag), EAS::DisplacementGradient,
+ * EAS::DisplacementGradientTransposed */
+enum { IKB_EAS_STRAIN = 0, IKB_EAS_DISPLACEMENT_GRADIENT = 1, IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED = 2 };
 
 typedef struct ikb_desc {
   int32_t abi_version;  /* IKB_ABI_VERSION */
@@ -61,13 +64,18 @@ typedef struct ikb_desc {
   int32_t material;     /* IKB_MAT_* */
   int32_t plane_strain; /* 2D only, IKB_REDUCE_*: Materials::planeStrain(mat) (materials/vanishingstrain.hh) or
                            Materials::planeStress(mat, tol) (materials/vanishingstress.hh) */
-  int32_t eas_m;        /* eas<...>(m): 0 | 4,5,7 (2D Q1) | 9,21 (3D Q1)  (easvariants/linearandglstrains.hh) */
+  int32_t eas_m;        /* eas<...>(m): 0 | 4,5,7 (2D Q1) | 9,21 (3D Q1)  (easvariants/linearandglstrains.hh);
+                           4 (2D) | 9 (3D) with a displacement-gradient eas_function */
   int32_t device;       /* CUDA ordinal, -1 = current device */
   double lambda;        /* Lame's first parameter (physicshelper.hh:53-57) */
   double mu;            /* shear modulus */
   int64_t n_elem;       /* elements owned by this handle */
   int64_t n_dof;        /* global dofs = basis.flat().size() */
   double reduce_tol;    /* planeStress: tolerance of the stress reduction (VanishingStress ctor, default 1e-12) */
+  int32_t eas_function; /* IKB_EAS_*: what eas<ES>(m) enhances (the headers under strainenhancements/easfunctions); the
+                           displacement-gradient forms take m = dim*dim (H4 / H9, easvariants/displacementgradient.hh)
+                           and a nonlinear element */
+  int32_t reserved_;
 } ikb_desc;
 
 /* ---- lifetime ------------------------------------------------------------------- */

@@ -17,7 +17,9 @@ def device_assembler(mesh, kind, mat, flags, layout="interleaved", fext=None, de
     solid = ik.linearElastic(m) if kind.strain == "linear" else ik.nonLinearElastic(m)
     sk = [solid]
     if kind.eas_m:
-        sk.append(ik.eas(kind.eas_m))
+        fn = {"strain": "GreenLagrangeStrain" if kind.strain == "gl" else "LinearStrain", "dg": "DisplacementGradient",
+              "dgt": "DisplacementGradientTransposed"}[getattr(kind, "eas_function", "strain")]
+        sk.append(ik.eas(kind.eas_m, fn))
     if volume is not None:
         sk.append(ik.fe.volumeLoad(volume))
     n_dof = mesh.n_nodes * mesh.dim

@@ -139,3 +139,82 @@ def test_cantilever_with_device_pcg_matches_golden_iterations():
     info = ik.LoadControl(nr, ik.LoadControlConfig(20, 0.0, 1.0)).run(req)
     assert info.success and info.totalIterations == 80
     assert abs(np.abs(req.globalSolution()).max() - GOLDEN["cantilever_eas"]["cases"][0]["max_abs_d"]) < 1e-8
+
+
+# ---------------------------------------------------------------- displacement-gradient enhancements (H4 / H9)
+DG_CASES = [(3, "neohooke", "dg"), (3, "svk", "dg"), (3, "neohooke", "dgt"), (3, "svk", "dgt"),
+            (2, "neohooke", "dg"), (2, "svk", "dgt")]
+
+
+@pytest.mark.parametrize("dim,matk,fn", DG_CASES, ids=lambda v: str(v))
+def test_displacement_gradient_matrix_vector_and_alpha_update(dim, matk, fn):
+    """EAS::DisplacementGradient / DisplacementGradientTransposed with H4 / H9 (easfunctions/displacementgradient.hh,
+    displacementgradienttransposed.hh, easvariants/displacementgradient.hh:76-163) on distorted meshes with alpha != 0:
+    condensed K and R in the three Dirichlet modes and the internal-variable update against the oracle, which is
+    pinned on the reference's eight cantilever known answers."""
+    cells = (3, 2, 2) if dim == 3 else (4, 3)
+    mesh = distorted(o.structured_mesh(cells, tuple(float(c) for c in cells)), 0.15, 4)
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material(matk, lam, mu, dim == 2)
+    kind = o.ElementKind(dim, 1, "gl", dim * dim, eas_function=fn)
+    flags = o.fix_nodes(mesh, o.boundary_nodes(o.structured_mesh(cells, tuple(float(c) for c in cells)), 0, 0.0))
+    rng = np.random.default_rng(8)
+    n = flags.shape[0]
+    d = 0.03 * rng.uniform(-1, 1, n)
+    alpha = 0.01 * rng.uniform(-1, 1, (mesh.n_elem, kind.eas_m))
+    ref = o.FlatAssembler(mesh, kind, mat, flags)
+    dev = device_assembler(mesh, kind, mat, flags)
+    ref.alpha = alpha.copy()
+    dev.setInternalVariables(alpha)
+    req = ik.FERequirements(d, 0.0)
+    for mode, dbc in (("raw", ik.DBCOption.Raw), ("full", ik.DBCOption.Full), ("reduced", ik.DBCOption.Reduced)):
+        K = dev.matrix(req, ik.MatrixAffordance.stiffness, dbc)
+        outer, inner = ref.pattern(mode)
+        assert np.array_equal(K.indptr, outer) and np.array_equal(K.indices, inner)
+        rows = np.repeat(np.arange(outer.shape[0] - 1), np.diff(outer))
+        Kref = ref.matrix_values(d, 0.0, mode)
+        assert entry_error(K.data, Kref, rows) <= TOL_8D, mode
+        assert _row_scaled_error(K.data, Kref, rows) <= TOL, mode
+        R = dev.vector(req, ik.VectorAffordance.forces, dbc)
+        Rr = ref.vector(d, 0.0, mode)
+        assert np.abs(R - Rr).max() <= TOL_8D * np.abs(Rr).max(), mode
+    Kd = dev.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Raw).toarray()
+    assert np.array_equal(Kd, Kd.T)
+    corr = 0.01 * rng.uniform(-1, 1, n)
+    dev.updateInternalVariables(req, corr)
+    ref.update_eas(d, corr)
+    assert np.abs(dev.internalVariables() - ref.alpha).max() <= 1e-11 * max(1.0, np.abs(ref.alpha).max())
+    with pytest.raises(NotImplementedError):
+        dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+
+
+@pytest.mark.parametrize(
+    "dim,matk,m,fn,iters,maxd",
+    # tests/src/testcantileverbeamEAS.cpp:34-57, 72-95 (tests/golden/reference_known_answers.json)
+    [(c["dim"], c["material"], c["eas"], c["function"], c["newton_iterations"], c["max_abs_d"])
+     for c in GOLDEN["cantilever_eas_displacement_gradient"]["cases"]],
+)
+def test_reference_cantilever_displacement_gradient_on_device(dim, matk, m, fn, iters, maxd):
+    """The reference's known answers for the displacement-gradient enhancements (80 Newton iterations, max|d| to 1e-10)
+    with the device assembler behind NewtonRaphson + LoadControl, as in tests/src/testcantileverbeam.hh:83-198."""
+    mesh, kind, mat, flags, fext = cantilever(dim, matk, m)
+    kind.eas_function = fn
+    dev = device_assembler(mesh, kind, mat, flags, fext=fext)
+    req = ik.FERequirements(np.zeros(flags.shape[0]), 0.0)
+    dev.bind(req, ik.AffordanceCollection(vector=ik.VectorAffordance.forces, matrix=ik.MatrixAffordance.stiffness),
+             ik.DBCOption.Full)
+    nr = ik.NewtonRaphson(dev, ik.NewtonRaphsonConfig(ik.NRSettings(tol=1e-10)))
+    info = ik.LoadControl(nr, ik.LoadControlConfig(20, 0.0, 1.0)).run(req)
+    assert info.success and info.totalIterations == iters
+    assert abs(np.abs(req.globalSolution()).max() - maxd) < 1e-10
+
+
+def test_displacement_gradient_descriptor_rules():
+    """m must be dim*dim (H4 / H9), the element nonlinear (enhancedassumedstrains.hh:85-90)."""
+    mesh = o.structured_mesh((2, 2, 2), (1.0, 1.0, 1.0))
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    flags = np.zeros(mesh.n_nodes * 3, dtype=bool)
+    with pytest.raises(NotImplementedError):
+        device_assembler(mesh, o.ElementKind(3, 1, "gl", 21, eas_function="dg"), o.Material("neohooke", lam, mu), flags)
+    with pytest.raises(Exception):
+        device_assembler(mesh, o.ElementKind(3, 1, "linear", 9, eas_function="dg"), o.Material("linear", lam, mu), flags)

@@ -57,6 +57,11 @@ if "C4" in which:
 if "C4b" in which:
     n = int(os.environ.get("C4_N", "96"))
     run(f"C4' Hex8+EAS9 NeoHooke nu=0.499 {n}^3", (n, n, n), (1.0, 1.0, 1.0), 1, ik.skills(ik.nonLinearElastic(ik.Materials.NeoHooke(lame(1000.0, 0.499))), ik.eas(9)), 3, 44, 0.05, eas_m=9, flop=102045, alpha_seed=None)
+if "C4dg" in which:
+    # the displacement-gradient enhancements (H9) on the C4 mesh: first, plain formulation (ikb_elem_easdg.cuh)
+    n = int(os.environ.get("C4_N", "96"))
+    for fn in ("DisplacementGradient", "DisplacementGradientTransposed"):
+        run(f"C4'' Hex8+H9 {fn} NeoHooke nu=0.499 {n}^3", (n, n, n), (1.0, 1.0, 1.0), 1, ik.skills(ik.nonLinearElastic(ik.Materials.NeoHooke(lame(1000.0, 0.499))), ik.eas(9, fn)), 3, 44, 0.05, eas_m=9, flop=None, alpha_seed=None)
 if "C5slab" in which:
     # one rank's share of C5 (256^3 over 8 GPUs): 256x256x32 elements
     run("C5 slab Hex8 NeoHooke 256x256x32", (256, 256, 32), (1.0, 1.0, 0.125), 1, ik.skills(ik.nonLinearElastic(ik.Materials.NeoHooke(lame(1000.0, 0.3)))), 3, 46, 0.05, flop=59520)
