@@ -1,1 +1,1 @@
-timeout 1200 python -m pytest tests/test_gpu_eas.py -x -q -m gpu 2>&1 | tail -15
+python tools/config_times.py C1 C3 C4 C4b C4dg 2>/dev/null | tee gpurun_out/config_times_r2.jsonl
