@@ -648,6 +648,16 @@ int launchGather(Handle* h, unsigned what, int dbc, int64_t rowFirst = 0, int64_
   return IKB_OK;
 }
 
+// The captured solver graphs hold raw pointers and sizes of the pattern they were captured for; the caches are keyed on
+// pointer values, and a freed-and-reallocated array can come back at the same address: drop them with the pattern.
+void dropSolverGraphs(Handle* h) {
+  if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
+  if (h->tcgGraph) cudaGraphExecDestroy(h->tcgGraph);
+  if (h->peerGraph) cudaGraphExecDestroy(h->peerGraph);
+  h->cgGraph = h->tcgGraph = h->peerGraph = nullptr;
+  h->cgGraphKey[0] = h->tcgGraphKey[0] = h->peerGraphKey[0] = nullptr;
+}
+
 // Chunk tables of the interleaved sweep: element ranges of equal size (whole CTAs of the element kernels) and, per
 // chunk, the end of the prefix of node-rows all of whose elements lie in chunks 0..c.
 int ensureSweepChunks(Handle* h) {
@@ -862,10 +872,19 @@ int distPcg(Handle* h, const double* rhsHost, double* xHost, double relTol, int 
   IKB_CUDA(h, cudaMemsetAsync(h->Corr.p, 0, h->Corr.bytes(), h->stream));
   double* p = h->cgPglob.p + off;
   int rc;
+  {
+    // Agreement before the first data collective: a rank whose state is not ready must not leave on its own -- the
+    // others would wait for it in the all-reduce below for ever.  Every rank contributes a flag and all of them return.
+    double bad = (h->valsVersion[dbc] != h->stateVersion || (!rhsHost && h->vecVersion[dbc] != h->stateVersion)) ? 1.0 : 0.0;
+    IKB_CUDA(h, cudaMemcpyAsync(h->cgScal.p + 5, &bad, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = allReduceSum(h, h->cgScal.p + 5, 1))) return rc;
+    IKB_CUDA(h, cudaMemcpyAsync(&bad, h->cgScal.p + 5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IKB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (bad > 0.0) return fail(h, IKB_ESTATE, "matrix or resident residual not assembled for the current state (on this or another rank)");
+  }
   if (rhsHost) {
     IKB_CUDA(h, cudaMemcpyAsync(h->cgR.p, rhsHost, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   } else {
-    if (h->vecVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "resident residual not assembled");
     vec_scale_kernel<<<RED_BLOCKS, tpb, 0, h->stream>>>(n, -1.0, h->vec[dbc].p, h->cgR.p);
     IKB_LAUNCH_CHECK(h);
   }
@@ -1160,6 +1179,7 @@ int ikb_destroy(ikb_handle hh) {
   h->rowSlow.release();
   h->rowSlowValid = false;
   h->sweepChunksBuilt = false;
+  dropSolverGraphs(h);
   h->cbelow.release();
   h->freeCnt.release();
   h->freeTot.release();
@@ -1302,6 +1322,7 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->reducedBuilt = false;
   h->rowSlowValid = false;
   h->sweepChunksBuilt = false;
+  dropSolverGraphs(h);
   h->fusedTried = h->fusedOk = false;
   h->stateVersion++;
   h->Lap.release();
@@ -1404,6 +1425,7 @@ int ikb_upload_dirichlet(ikb_handle hh, const uint8_t* flags) {
   h->reducedBuilt = false;
   h->rowSlowValid = false;
   h->sweepChunksBuilt = false;
+  dropSolverGraphs(h);
   h->vals[IKB_DBC_REDUCED].release();
   h->vec[IKB_DBC_REDUCED].release();
   h->stateVersion++;
@@ -1422,6 +1444,7 @@ int ikb_set_row_ownership(ikb_handle hh, int64_t nodeBegin, int64_t nodeEnd) {
   h->reducedBuilt = false;
   h->rowSlowValid = false;
   h->sweepChunksBuilt = false;
+  dropSolverGraphs(h);
   return IKB_OK;
 }
 
@@ -1554,6 +1577,7 @@ int ikb_build_pattern(ikb_handle hh) {
   h->reducedBuilt = false;
   h->rowSlowValid = false;
   h->sweepChunksBuilt = false;
+  dropSolverGraphs(h);
   h->rowDiag.release();
   h->rowLowEnd.release();
   h->mirrorBlk.release();
@@ -2103,12 +2127,13 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;
   if (dbc != IKB_DBC_FULL && dbc != IKB_DBC_REDUCED) return fail(h, IKB_EINVAL, "PCG needs the Full or Reduced matrix");
-  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
   if (h->rowBegin != 0 || h->rowEnd != h->nNodes || h->comm) {
     if (!h->comm) return fail(h, IKB_ESTATE, "partitioned handle: call ikb_comm_init before solving");
     if (dbc != IKB_DBC_FULL) return fail(h, IKB_ENOTIMPL, "distributed PCG supports DBCOption::Full");
+    // (the state of this rank is checked inside, together with the other ranks')
     return distPcg(h, rhs, x, relTol, maxIt, itersOut, relResOut);
   }
+  if (h->valsVersion[dbc] != h->stateVersion) return fail(h, IKB_ESTATE, "matrix not assembled for the current state");
   const int64_t n = rowsOf(h, dbc);
   if (itersOut) *itersOut = 0;
   if (relResOut) *relResOut = 0.0;
@@ -2180,8 +2205,6 @@ int ikb_pcg_solve(ikb_handle hh, int dbc, const double* rhs, double* x, double r
     if (!h->cgGraph || h->cgGraphKey[0] != h->vals[dbc].p || h->cgGraphKey[1] != h->cgP.p ||
         h->cgGraphKey[2] != h->nbrIdx.p) {
       if (h->cgGraph) cudaGraphExecDestroy(h->cgGraph);
-  if (h->tcgGraph) cudaGraphExecDestroy(h->tcgGraph);
-  h->tcgState.release();
       h->cgGraph = nullptr;
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

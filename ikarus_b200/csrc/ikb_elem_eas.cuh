@@ -720,13 +720,10 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 template <int D, int FORM, int M>
 cudaError_t launchElemEas(const EasArgs& A, cudaStream_t st) {
   using C = EasCfg<D, FORM, M>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(elem_eas_kernel<D, FORM, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // (the opt-in is per device and context: made at every launch, a handle may live on any GPU of the process)
+  cudaError_t e =
+      cudaFuncSetAttribute(elem_eas_kernel<D, FORM, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((A.E.nElem + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
   elem_eas_kernel<D, FORM, M><<<grid, C::TPB, C::SMEM, st>>>(A);

@@ -539,13 +539,10 @@ __global__ void __launch_bounds__(Q1Cfg<D, FORM>::TPB, (Q1Cfg<D, FORM>::SMEM > 5
 template <int D, int FORM, bool USELAP>
 cudaError_t launchElemQ1Impl(const ElemArgs& A, cudaStream_t st) {
   using C = Q1Cfg<D, FORM>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(elem_q1_kernel<D, FORM, USELAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // (the opt-in is per device and context: made at every launch, a handle may live on any GPU of the process)
+  cudaError_t e = cudaFuncSetAttribute(elem_q1_kernel<D, FORM, USELAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM);
+  if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((A.elemCount + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
   elem_q1_kernel<D, FORM, USELAP><<<grid, C::TPB, C::SMEM, st>>>(A);

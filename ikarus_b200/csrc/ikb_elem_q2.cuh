@@ -396,13 +396,10 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
 template <int D, int FORM>
 cudaError_t launchElemQ2(const ElemArgs& A, cudaStream_t st) {
   using C = Q2Cfg<D, FORM>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(elem_q2_kernel<D, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // (the opt-in is per device and context: made at every launch, a handle may live on any GPU of the process)
+  cudaError_t e =
+      cudaFuncSetAttribute(elem_q2_kernel<D, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((A.nElem + C::EPC - 1) / C::EPC);
   if (grid == 0) return cudaSuccess;
   elem_q2_kernel<D, FORM><<<grid, C::TPB, C::SMEM, st>>>(A);

@@ -107,6 +107,10 @@ int ikb_get_constraints_below(ikb_handle h, int64_t* out);
 int ikb_element_linear_indices(ikb_handle h, int64_t elem, int64_t* out);
 
 /* ---- per-solve state ------------------------------------------------------------ */
+/* Buffer lifetime: ikb_set_solution, ikb_set_solution_range, ikb_set_external_load, ikb_eas_set_alpha and
+ * ikb_update_solution enqueue an asynchronous copy from the caller's buffer and return.  With pageable host memory the
+ * CUDA runtime has staged the data by then; a PINNED (page-locked) buffer is read when the copy actually runs, so it
+ * must stay untouched until ikb_sync(h) -- or any call that returns host data -- has returned. */
 /* FERequirements::globalSolution()/parameter() (finiteelements/ferequirements.hh:222-407) */
 int ikb_set_solution(ikb_handle h, const double* d);
 /* Partial upload: d[0..count) -> resident solution[dof_begin .. dof_begin+count).  An element-partitioned rank only
