@@ -304,6 +304,82 @@ int ikref_assemble(int dim, int material_id, double lam, double mu, int64_t nEle
   return failed;
 }
 
+/*
+ * "cpu_opt" baseline of SURVEY.md 8d: the SAME math as the device kernels (factored NeoHooke tangent of
+ * ikarus_b200/csrc/ikb_elem_q1.cuh -- K_ab = sum_g w [ lam m_a m_b^T + mu' m_b m_a^T + mu (g_a.g_b) I ],
+ * m_a = F^-T g_a, mu' = mu - lam ln J; R_a = sum_g w (mu F - mu' F^-T) g_a), K and R in ONE sweep, the block symmetry
+ * used, OpenMP over all host cores with atomic scatter.  What a tuned CPU implementation of this path would look like;
+ * the faithful port above keeps the reference's loop structure instead.  Hex8 / Quad4-plane-strain NeoHooke only.
+ * Same argument list and result layout as ikref_assemble (linidx column-major over K_e).
+ */
+int ikref_assemble_opt(int dim, int material_id, double lam, double mu, int64_t nElem, const double* corner,
+                       const int64_t* edofs, const int64_t* linidx, const double* d, double* vals, int64_t nnz,
+                       double* R, int64_t nDof, int nthreads) {
+  if (material_id != 2 || !vals || !R) return -1;
+  ikref_cfg c = {dim, material_id, lam, mu};
+  const int n = 1 << dim, nd = n * dim;
+  int failed = 0;
+  memset(R, 0, nDof * sizeof(double));
+  memset(vals, 0, nnz * sizeof(double));
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : failed) if (nthreads > 1)
+  for (int64_t e = 0; e < nElem; ++e) {
+    double u[MAXN * MAXD], Re[MAXN * MAXD], Ke[MAXN * MAXD * MAXN * MAXD];
+    for (int i = 0; i < nd; ++i) u[i] = d[edofs[e * nd + i]];
+    memset(Re, 0, sizeof(Re));
+    memset(Ke, 0, sizeof(double) * nd * nd);
+    for (int g = 0; g < n; ++g) {
+      gp_kin k;
+      kinematics(&c, corner + e * n * dim, u, g, &k);
+      double Fi[MAXD][MAXD], m[MAXN][MAXD], Pm[MAXD][MAXD];
+      const double J = inv_small(dim, k.F, Fi);  /* plane strain: F33 = 1 */
+      if (!(J > 0.0)) {
+        ++failed;
+        continue;
+      }
+      const double lnJ = log(J), mup = mu - lam * lnJ, w = k.wdet;
+      for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j) Pm[i][j] = w * (mu * k.F[i][j] - mup * Fi[j][i]);
+      for (int a = 0; a < n; ++a)
+        for (int i = 0; i < dim; ++i) {
+          double s = 0, r = 0;
+          for (int j = 0; j < dim; ++j) {
+            s += Fi[j][i] * k.gradN[a][j]; /* (F^-T g_a)_i */
+            r += Pm[i][j] * k.gradN[a][j];
+          }
+          m[a][i] = s;
+          Re[a * dim + i] += r;
+        }
+      const double c1 = w * lam, c2 = w * mup, c3 = w * mu;
+      for (int a = 0; a < n; ++a)
+        for (int b = a; b < n; ++b) {
+          double gg = 0;
+          for (int i = 0; i < dim; ++i) gg += k.gradN[a][i] * k.gradN[b][i];
+          for (int i = 0; i < dim; ++i)
+            for (int j = 0; j < dim; ++j)
+              Ke[(a * dim + i) * nd + b * dim + j] += c1 * m[a][i] * m[b][j] + c2 * m[b][i] * m[a][j] + (i == j ? c3 * gg : 0.0);
+        }
+    }
+    for (int a = 0; a < n; ++a)  /* lower block triangle from the upper one */
+      for (int b = 0; b < a; ++b)
+        for (int i = 0; i < dim; ++i)
+          for (int j = 0; j < dim; ++j) Ke[(a * dim + i) * nd + b * dim + j] = Ke[(b * dim + j) * nd + a * dim + i];
+    for (int i = 0; i < nd; ++i) {
+#pragma omp atomic
+      R[edofs[e * nd + i]] += Re[i];
+    }
+    int64_t q = 0;
+    for (int cc = 0; cc < nd; ++cc)
+      for (int r = 0; r < nd; ++r, ++q) {
+#pragma omp atomic
+        vals[linidx[e * nd * nd + q]] += Ke[r * nd + cc];
+      }
+  }
+  return failed;
+}
+
 int ikref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

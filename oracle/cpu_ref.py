@@ -18,6 +18,7 @@ def load():
             subprocess.run(["make", "-s", "-C", _HERE], check=True)
         _lib = C.CDLL(_LIB)
         _lib.ikref_assemble.restype = C.c_int
+        _lib.ikref_assemble_opt.restype = C.c_int
         _lib.ikref_element.restype = C.c_int
         _lib.ikref_max_threads.restype = C.c_int
     return _lib
@@ -55,6 +56,24 @@ def assemble(dim, material, lam, mu, corner, edofs, linidx, d, nnz, want_K=True,
                             C.c_int64(nnz), _p(R), C.c_int64(d.shape[0]), C.c_int(nthreads))
     if rc:
         raise FloatingPointError(f"{rc} elements failed the material check")
+    return vals, R
+
+
+def assemble_opt(dim, material, lam, mu, corner, edofs, linidx, d, nnz, nthreads=1):
+    """The "cpu_opt" baseline: factored NeoHooke math as on the device, one fused K+R sweep, OpenMP."""
+    lib = load()
+    corner = np.ascontiguousarray(corner, float)
+    edofs = np.ascontiguousarray(edofs, np.int64)
+    d = np.ascontiguousarray(d, float)
+    vals, R = np.zeros(nnz), np.zeros(d.shape[0])
+    li = np.ascontiguousarray(linidx, np.int64)
+    rc = lib.ikref_assemble_opt(C.c_int(dim), C.c_int(MATERIAL_ID[material]), C.c_double(lam), C.c_double(mu),
+                                C.c_int64(corner.shape[0]), _p(corner), _p(edofs), _p(li), _p(d), _p(vals),
+                                C.c_int64(nnz), _p(R), C.c_int64(d.shape[0]), C.c_int(nthreads))
+    if rc < 0:
+        raise NotImplementedError("cpu_opt covers NeoHooke with K and R")
+    if rc:
+        raise FloatingPointError(f"{rc} Gauss points failed the material check")
     return vals, R
 
 

@@ -36,6 +36,8 @@ def test_our_arm_record_has_the_contract_keys(name, n, scaling):
         c = d["cpu_baseline"]
         assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference")
         assert d["config"]["workload"].startswith("C2") and d["parity"]["ok"] is True
+        # the optimised CPU baseline (factored math, fused sweep, all cores) beside the faithful port
+        assert d["cpu_baseline_opt"]["value"] > c["value"] and d["cpu_baseline_opt"]["kind"] == "port"
         assert d["c5_single_gpu"]["elements"] == 256**3
     else:
         assert ("C5" in d["config"]["workload"]) == (scaling == "strong")
@@ -53,3 +55,4 @@ def test_reference_arm_record():
     # the whole C2 mesh per step on a stated number of threads, and the single-thread figure of the single-threaded reference
     assert d["config"]["sample_elements_per_step"] == 131072 and d["cpu_baseline"]["cores"] == d["config"]["threads"] > 1
     assert d["cpu_baseline_1thread"]["cores"] == 1
+    assert d["cpu_baseline_opt"]["value"] > d["cpu_baseline"]["value"]
