@@ -1992,8 +1992,6 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
   const bool linearType = resultType == IKB_RESULT_LINEAR_STRESS || resultType == IKB_RESULT_LINEAR_STRESS_FULL;
   if (linearType != (h->form == FORM_LE))  // supportsResultType (linearelastic.hh / nonlinearelastic.hh)
     return fail(h, IKB_ENOTIMPL, "The requested result type is not supported by this element");
-  if (h->easM && h->easFunction != IKB_EAS_STRAIN)
-    return fail(h, IKB_ENOTIMPL, "results at local positions are not built for the displacement-gradient enhancements");
   int rc;
   if ((rc = ensureSolution(h))) return rc;
   joinSolution(h);
@@ -2035,6 +2033,7 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
   A.form = h->form;
   A.planeStrain = h->desc.plane_strain;
   A.easM = h->easM;
+  A.easFunction = h->easFunction;
   A.resultType = resultType;
   A.ncomp = ncomp;
   A.lambda = h->desc.lambda;

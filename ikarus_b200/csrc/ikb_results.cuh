@@ -23,6 +23,7 @@ struct ResultArgs {
   int32_t* errFlag;
   int64_t nElem, nNodes;
   int layout, npts, form, planeStrain, easM, resultType, ncomp;
+  int easFunction = 0;  // IKB_EAS_*
   double lambda, mu, psTol;
 };
 
@@ -140,6 +141,58 @@ __global__ void __launch_bounds__(128) result_at_kernel(ResultArgs A) {
     }
   }
   // strain in Voigt notation (shear doubled)
+  if (A.easM && A.easFunction != IKB_EAS_STRAIN) {
+    // EnhancedStrainFunction::computeDisplacementGradient (easfunctions/displacementgradient.hh:40-64,
+    // displacementgradienttransposed.hh:40-58, 343-360): H = H_c + Ht, resp. H_c + F_c0 Ht^T with
+    // Ht = (detJ0/detJ) J0^-T (alpha_(i,j) (2 xi_j - 1)) J0^-1 (easvariants/displacementgradient.hh, helperfunctions.hh:27-36)
+    if constexpr (ORDER == 1) {
+      double Jt0[D][D], JI0[D][D], Fc0[D][D];
+      const double half = (D == 3) ? 0.25 : 0.5;
+      for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) Jt0[i][k] = 0.0, Fc0[i][k] = (i == k) ? 1.0 : 0.0;
+      for (int c = 0; c < NC; ++c)
+        for (int i = 0; i < D; ++i)
+          for (int k = 0; k < D; ++k) Jt0[i][k] += (((c >> i) & 1) ? half : -half) * A.X[(size_t)(c * D + k) * A.nElem + e];
+      const double detJ0 = fabs(invSmall<D>(Jt0, JI0));
+      if (A.easFunction == IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED) {
+        for (int a = 0; a < NC; ++a) {
+          const int64_t node = A.elemNode[(size_t)a * A.nElem + e];
+          double g0[D];
+          for (int j = 0; j < D; ++j) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i) v += JI0[j][i] * (((a >> i) & 1) ? half : -half);
+            g0[j] = v;
+          }
+          for (int c = 0; c < D; ++c) {
+            const double u = A.U[dofOf(A.layout, D, A.nNodes, node, c)];
+            for (int j = 0; j < D; ++j) Fc0[c][j] += u * g0[j];
+          }
+        }
+      }
+      const double sc = detJ0 / fabs(detJ);
+      double T1[D][D], Hs[D][D];
+      for (int i = 0; i < D; ++i)
+        for (int l = 0; l < D; ++l) {
+          double v = 0.0;
+          for (int j = 0; j < D; ++j) v += A.alpha[(size_t)e * A.easM + D * i + j] * (2.0 * xi[j] - 1.0) * JI0[l][j];
+          T1[i][l] = v;
+        }
+      for (int k = 0; k < D; ++k)
+        for (int l = 0; l < D; ++l) {
+          double v = 0.0;
+          for (int i = 0; i < D; ++i) v += JI0[k][i] * T1[i][l];
+          Hs[k][l] = sc * v;
+        }
+      for (int c = 0; c < D; ++c)
+        for (int j = 0; j < D; ++j) {
+          if (A.easFunction == IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED) {
+            for (int k = 0; k < D; ++k) H[c][j] += Fc0[c][k] * Hs[j][k];
+          } else {
+            H[c][j] += Hs[c][j];
+          }
+        }
+    }
+  }
   const bool gl = A.form != FORM_LE;
   double Ev[S];
   for (int p = 0; p < S; ++p) {
@@ -150,7 +203,7 @@ __global__ void __launch_bounds__(128) result_at_kernel(ResultArgs A) {
       for (int k = 0; k < D; ++k) v += H[k][i] * H[k][j];
     Ev[p] = i == j ? 0.5 * v : v;
   }
-  if (A.easM) {  // E += M(xi) alpha,  M[:, j] = T0inv[:, r_j] p_j(2 xi - 1) / detJ(xi)
+  if (A.easM && A.easFunction == IKB_EAS_STRAIN) {  // E += M(xi) alpha,  M[:, j] = T0inv[:, r_j] p_j(2 xi - 1) / detJ(xi)
     double tt[D];
     for (int k = 0; k < D; ++k) tt[k] = 2.0 * xi[k] - 1.0;
     const double idet = 1.0 / fabs(detJ);

@@ -573,7 +573,21 @@ def stress_at(kind, mat, X, u, xi, alpha=None, result="native"):
     else:
         Em = 0.5 * (H + np.swapaxes(H, -1, -2))
     Ev = to_voigt(Em)
-    if kind.eas_m:
+    if kind.eas_m and kind.eas_function in ("dg", "dgt"):
+        # EnhancedStrainFunction::computeDisplacementGradient with the stored alpha (enhancedassumedstrains.hh:161-170)
+        if alpha is None:
+            alpha = np.zeros((X.shape[0], kind.eas_m))
+        _, Jt0inv, detJ0 = _geometry(kind, X, np.full(d, 0.5))
+        Hsum = np.einsum("e,eik,pkl,ejl,ep->eij", detJ0 / detJ, Jt0inv, eas_Hhat(d, kind.eas_m, xi), Jt0inv, alpha)
+        if kind.eas_function == "dgt":
+            _, dN0 = shape_functions(d, kind.order, np.full(d, 0.5))
+            Fc0 = np.eye(d) + np.einsum("eac,eaj->ecj", u, np.einsum("eji,ai->eaj", Jt0inv, dN0))
+            H = H + np.einsum("eik,ejk->eij", Fc0, Hsum)
+        else:
+            H = H + Hsum
+        Em = 0.5 * (H + np.swapaxes(H, -1, -2) + np.einsum("eki,ekj->eij", H, H))
+        Ev = to_voigt(Em)
+    elif kind.eas_m:
         if alpha is None:
             q = element_quantities(kind, mat, X, u, np.zeros((X.shape[0], kind.eas_m)), want=())
             alpha = -np.linalg.solve(q["D"], np.einsum("emi,ei->em", q["L"], u.reshape(u.shape[0], -1))[..., None])[..., 0]

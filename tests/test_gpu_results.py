@@ -66,18 +66,25 @@ CASES = [
     (3, (2, 2, 2), 1, "linear", "linear", 9),
     (2, (3, 3), 1, "gl", "svk", 7),
     (2, (3, 3), 1, "linear", "linear", 5),
+    # displacement-gradient enhancements (H9 / H4): the stress at the ENHANCED displacement gradient with the stored
+    # alpha (enhancedassumedstrains.hh:161-170); the seventh entry is the EAS function
+    (3, (2, 2, 2), 1, "gl", "neohooke", 9, "dg"),
+    (3, (2, 2, 2), 1, "gl", "svk", 9, "dgt"),
+    (2, (3, 3), 1, "gl", "neohooke", 4, "dgt"),
+    (2, (3, 3), 1, "gl", "svk", 4, "dg"),
 ]
 
 
 @pytest.mark.parametrize("layout", ["interleaved", "lexicographic"])
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-Q{c[2]}-{c[3]}-{c[4]}-eas{c[5]}")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-Q{c[2]}-{c[3]}-{c[4]}-eas{c[5]}{c[6] if len(c) > 6 else ''}")
 def test_results_match_oracle(case, layout):
-    dim, cells, order, strain, matk, m = case
+    dim, cells, order, strain, matk, m = case[:6]
+    fn = case[6] if len(case) > 6 else "strain"
     bbox = tuple(float(c) for c in cells)
     mesh = distorted(o.structured_mesh(cells, bbox, order=order), 0.12, 5)
     lam, mu = o.lame_from_E_nu(1000.0, 0.3)
     mat = o.Material(matk, lam, mu, plane_strain=(dim == 2))
-    kind = o.ElementKind(dim, order, strain, m)
+    kind = o.ElementKind(dim, order, strain, m, eas_function=fn)
     n = mesh.n_nodes * dim
     rng = np.random.default_rng(9)
     d = 0.03 * rng.uniform(-1, 1, n)

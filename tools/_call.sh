@@ -1,2 +1,1 @@
-python bench.py --steps 200 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 400 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 700 gpurun_out/bench_ref.json
+timeout 900 python -m pytest tests/test_gpu_results.py -x -q -m gpu 2>&1 | tail -5
