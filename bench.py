@@ -366,6 +366,28 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
+    # ---- mirror mode (N = 1): the same step with the matrix values fetched to the host as well, which is what an unchanged
+    # host LinearSolver / TrustRegion consumes (ikb_get_matrix_values: the CSR value array in Eigen's order)
+    e2e_mirror = None
+    if world == 1 and not args.no_mirror:
+        rows_c, nnz_c = C.c_int64(), C.c_int64()
+        asm._check(lib.ikb_pattern_nnz(h, DBC, C.byref(rows_c), C.byref(nnz_c)))
+        k_host = torch.empty(nnz_c.value, dtype=torch.float64).pin_memory()
+        msteps = max(3, min(args.steps, 10))
+        for i in range(2 + msteps):
+            if i == 2:
+                lib.ikb_sync(h)
+                t0 = time.perf_counter()
+            asm._check(lib.ikb_set_solution_range(h, C.c_void_p(d_ptr), need_lo, need_hi - need_lo))
+            asm._check(lib.ikb_assemble(h, WHAT, DBC))
+            asm._check(lib.ikb_get_vector(h, DBC, C.c_void_p(r_host.data_ptr())))
+            asm._check(lib.ikb_get_matrix_values(h, DBC, C.c_void_p(k_host.data_ptr())))
+        mirror_ms = (time.perf_counter() - t0) * 1e3 / msteps
+        e2e_mirror = {"value": int(np.prod(W["cells"])) / mirror_ms / 1e3, "unit": UNIT, "ms_per_step": mirror_ms, "steps": msteps,
+                      "d2h_bytes_per_step": 8 * (n_rows + nnz_c.value),
+                      "note": "as e2e, plus the CSR values of K to a pinned host buffer every step (mirror mode: matrix() "
+                              "returns a host Eigen::SparseMatrix); bound by the 8*nnz bytes over PCIe"}
+        del k_host
     # ---- per-kernel durations (CUDA events on the handle's stream, inside the library)
     t_el = asm.timePhase("elements", DBC, 20)
     t_ga = asm.timePhase("gather", DBC, 20)
@@ -478,6 +500,8 @@ def run_ours(args):
                                "ikb_get_vector(host R, owned rows); byte counts are rank 0's times the rank count; "
                                "K stays resident for the device PCG"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if e2e_mirror is not None:
+            out["e2e_mirror"] = e2e_mirror
         if cpu is not None:
             out["cpu_baseline"] = cpu
             fast = cpu_baseline(wl, args.cpu_sample, host_threads(), opt=True)
@@ -537,6 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C5", "C2W"])
+    ap.add_argument("--no-mirror", action="store_true", help="skip the mirror-mode (K values to the host) e2e figure")
     ap.add_argument("--cpu-sample", type=int, default=32768, help="elements in the cpu_baseline sample of the GPU arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
