@@ -18,7 +18,11 @@ struct Q2Cfg {
   static constexpr int NC = 1 << D;
   static constexpr int DD = D * D;
   static constexpr int SYM = D * (D + 1) / 2;
-  static constexpr int NV = (FORM == FORM_LE) ? 1 : 2;
+  // The records keep g_a only.  m_a = A g_a (A = F for SVK, F C^-1 for NeoHooke) is formed in phase 2 from the 3x3 matrix A
+  // of the Gauss point: 9 more FMAs per node pair and Gauss point, but the record shrinks from 2*D*N to D*N doubles -- Hex27
+  // SVK 40.4 -> 24.8 KB per element -- so TWO CTAs fit an SM (8 warps instead of 4; ncu had the FP64 pipe at 45 % with one
+  // warp per scheduler).
+  static constexpr int NV = 1;
   static constexpr int NPAIR = N * (N + 1) / 2;
   static constexpr int KMAX = (N - 1) / 2;         // pair offsets k = 0..KMAX, all threads
   static constexpr int KPASS = (D == 3) ? 7 : 5;   // pair offsets per register pass
@@ -27,7 +31,8 @@ struct Q2Cfg {
   static constexpr int O_A2 = 2, O_WS = 2 + SYM;
   static constexpr int O_WP = (FORM == FORM_LE) ? 2 : (FORM == FORM_NH ? 3 : 2 + 2 * SYM);
   static constexpr int O_PSI = O_WP + DD;
-  static constexpr int NS = O_PSI + 1;
+  static constexpr int O_AM = O_PSI + 1;                                  // A (row-major), nonlinear forms only
+  static constexpr int NS = O_AM + ((FORM == FORM_LE) ? 0 : DD);
   static constexpr int VEC = NV * D * N;
   static constexpr int GPS0 = VEC + NS;
   static constexpr int GPS = GPS0 + (1 - GPS0 % 2);  // odd stride: conflict-free phase-1 stores
@@ -104,8 +109,7 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
     w *= detJ;
 
     double* gp = rec + t * C::GPS;
-    double* vM = gp;
-    double* vG = gp + (C::NV - 1) * D * N;
+    double* vG = gp;
     double* sc = gp + C::VEC;
     double H[D][D];
 #pragma unroll
@@ -262,19 +266,10 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
           for (int k = 0; k < D; ++k) s = fma(F[i][k], Sm[k][j], s);
           sc[C::O_WP + i * D + j] = w * s;
         }
-#pragma unroll 3
-      for (int a = 0; a < N; ++a) {
-        double g[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) g[j] = vG[j * N + a];
+      for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int j = 0; j < D; ++j) s = fma(Am[i][j], g[j], s);
-          vM[i * N + a] = s;
-        }
-      }
+        for (int j = 0; j < D; ++j) sc[C::O_AM + i * D + j] = Am[i][j];
     }
   }
   __syncwarp();
@@ -297,15 +292,29 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
 #pragma unroll 1
     for (int g = 0; g < N; ++g) {
       const double* gp = rec + g * C::GPS;
-      const double* vM = gp;
-      const double* vG = gp + (C::NV - 1) * D * N;
+      const double* vG = gp;
       const double* sc = gp + C::VEC;
       const double c1 = sc[C::O_C1], c2 = sc[C::O_C2];
+      double Am[D][D];
+      if constexpr (FORM != FORM_LE) {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) Am[i][j] = sc[C::O_AM + i * D + j];
+      }
       double ma[D], ga[D], p1[D], p2[D];
 #pragma unroll
+      for (int i = 0; i < D; ++i) ga[i] = vG[i * N + a];
+#pragma unroll
       for (int i = 0; i < D; ++i) {
-        ga[i] = vG[i * N + a];
-        ma[i] = (FORM == FORM_LE) ? ga[i] : vM[i * N + a];
+        if constexpr (FORM == FORM_LE) {
+          ma[i] = ga[i];
+        } else {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) s = fma(Am[i][j], ga[j], s);
+          ma[i] = s;
+        }
         p1[i] = c1 * ma[i];
         p2[i] = c2 * ma[i];
       }
@@ -338,9 +347,17 @@ __global__ void __launch_bounds__(Q2Cfg<D, FORM>::TPB) elem_q2_kernel(ElemArgs A
         if (b >= N) b -= N;
         double mb[D], gb[D];
 #pragma unroll
+        for (int i = 0; i < D; ++i) gb[i] = vG[i * N + b];
+#pragma unroll
         for (int i = 0; i < D; ++i) {
-          gb[i] = vG[i * N + b];
-          mb[i] = (FORM == FORM_LE) ? gb[i] : vM[i * N + b];
+          if constexpr (FORM == FORM_LE) {
+            mb[i] = gb[i];
+          } else {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) s = fma(Am[i][j], gb[j], s);
+            mb[i] = s;
+          }
         }
 #pragma unroll
         for (int i = 0; i < D; ++i)
