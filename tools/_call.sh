@@ -1,2 +1,5 @@
-python tools/config_times.py C3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print('C3', d['elements_ms'], d['gather_ms'], d['K_R_Melem_s'])"
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py tests/test_gpu_idbc.py tests/test_gpu_plane_stress.py tests/test_gpu_baseline_sizes.py -x -q -m gpu -k "Q2 or q2 or hex27 or Hex27 or quad9 or c3 or C3 or idbc or plane" 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_eas.py -x -q -m gpu -k "displacement_gradient" 2>&1 | tail -4
+python tools/config_times.py C4dg 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'][:60], d['elements_ms'], d['K_R_Melem_s'])"
