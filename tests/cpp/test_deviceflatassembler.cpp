@@ -316,6 +316,73 @@ int main(int argc, char** argv) {
     CHECK(rejected);
   }
 
+  // The reference's cantilever known answer for EAS::DisplacementGradient with H9 and NeoHooke
+  // (tests/src/testcantileverbeamEAS.cpp:81, problem tests/src/testcantileverbeam.hh:83-198: 10 x 1 x 1 Hex8 on
+  // 10 x 2 x 2, E = 100, nu = 0.3, x = 0 clamped, unit point loads -lambda e_y at (10,2,2) and (10,2,0), LoadControl with 20
+  // steps to lambda = 1, Newton tolerance 1e-10, alpha updated on CORRECTION_UPDATED before the solution): 80 Newton
+  // iterations, max |d| = 4.763101490723167 -- through the C++ wrapper, the device PCG as linear solver.
+  {
+    const double E = 100, nu = 0.3;
+    const double lam = E * nu / ((1 + nu) * (1 - 2 * nu)), mu = E / (2 * (1 + nu));
+    std::vector<HostFE> cfes;
+    auto cnode = [](int i, int j, int k) { return (std::int64_t)i + 11 * ((std::int64_t)j + 2 * (std::int64_t)k); };
+    for (int i = 0; i < 10; ++i) {
+      HostFE fe;
+      fe.material = IKB_MAT_NEOHOOKE, fe.strain = IKB_STRAIN_GREEN_LAGRANGE, fe.easM = 9;
+      fe.easFunction = IKB_EAS_DISPLACEMENT_GRADIENT, fe.lambda = lam, fe.mu = mu;
+      for (int a = 0; a < 8; ++a) {
+        const int ii = i + (a & 1), jj = (a >> 1) & 1, kk = (a >> 2) & 1;
+        for (int c = 0; c < 3; ++c)
+          fe.dofs.push_back(3 * cnode(ii, jj, kk) + c);
+        fe.corners.push_back(ii * 1.0), fe.corners.push_back(jj * 2.0), fe.corners.push_back(kk * 2.0);
+      }
+      cfes.push_back(fe);
+    }
+    const std::size_t cn = 3 * 11 * 2 * 2;
+    HostDirichletValues cdv(cn);
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < 2; ++j)
+        for (int c = 0; c < 3; ++c)
+          cdv.setSingleDOF(3 * cnode(0, j, k) + c);
+    auto ca  = makeDeviceSparseFlatAssembler(cfes, cdv);
+    using CA = std::remove_cvref_t<decltype(*ca)>;
+    std::vector<double> load(cn, 0.0);
+    load[3 * cnode(10, 1, 1) + 1] = -1.0;
+    load[3 * cnode(10, 1, 0) + 1] = -1.0;
+    ca->setExternalLoad(load);
+    HostRequirement creq;
+    creq.d.assign(cn, 0.0);
+    ca->bind(creq, elastoStatics, DBCOption::Full);
+    DevicePCG<CA> cls{ca, 1e-14};
+    int total = 0;
+    for (int step = 1; step <= 20; ++step) {
+      creq.lambda = step / 20.0;
+      for (int it = 0;; ++it) {
+        CHECK(it < 20);
+        const auto& rx = ca->vector();
+        const auto& Ax = ca->matrix();
+        double nrm   = 0;
+        for (double v : rx)
+          nrm += v * v;
+        if (std::sqrt(nrm) <= 1e-10)
+          break;
+        auto corr = cls(rx, Ax);
+        for (double& v : corr)
+          v = -v;
+        ca->updateInternalVariables(creq, corr);  // CORRECTION_UPDATED comes before the solution update
+        for (std::size_t i = 0; i < cn; ++i)
+          creq.d[i] += corr[i];
+        ++total;
+      }
+    }
+    double maxd = 0;
+    for (double v : creq.d)
+      maxd = std::max(maxd, std::abs(v));
+    std::printf("cantilever H9 DisplacementGradient through the wrapper: %d Newton iterations, max|d| = %.15f\n", total, maxd);
+    CHECK(total == 80);
+    CHECK(std::abs(maxd - 4.763101490723167) < 1e-10);
+  }
+
   // Newton iteration with the device PCG callable, as NewtonRaphson::solve does (newtonraphson.hh:196-257)
   DevicePCG<A> ls{asmb, 1e-13};
   double rnorm = 0;
