@@ -1,1 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_baseline_sizes.py -x -q -m gpu -k "h9" 2>&1 | grep -E "AssertionError|assert |passed|failed" | head -8
+export QT_NO_PCG=1
+python tools/quick_time.py 2>&1 | grep -E "^elements|^step"
+IKB_H8_BULK=0 python tools/quick_time.py 2>&1 | grep -E "^elements|^step"
