@@ -11,4 +11,5 @@ B="python bench.py --steps 5 --warmup 3 --no-cpu --no-c5"
 [ "$PART" = a ] || $NCU --set full -k regex:'spmv_node_dot' -s 40 -c 1 -o gpurun_out/prof_r2_spmv $B > /dev/null 2>&1
 [ "$PART" = a ] || C4_N=48 $NCU --set full -k regex:'elem_eas' -s 2 -c 1 -o gpurun_out/prof_r2_eas python tools/config_times.py C4 > /dev/null 2>&1
 [ "$PART" = a ] || C3_N=24 $NCU --set full -k regex:'elem_q2' -s 2 -c 1 -o gpurun_out/prof_r2_q2 python tools/config_times.py C3 > /dev/null 2>&1
+[ "$PART" = a ] || C4_N=48 $NCU --set full -k regex:'elem_easdg' -s 2 -c 1 -o gpurun_out/prof_r2_easdg python tools/config_times.py C4dg > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep

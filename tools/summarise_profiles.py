@@ -91,5 +91,8 @@ full_capture(f"prof_{tag}_eas.ncu-rep", f"{tag}_ncu_full_eas.csv",
 full_capture(f"prof_{tag}_q2.ncu-rep", f"{tag}_ncu_full_q2.csv",
              "C3_N=24 ncu --set full --clock-control none --import-source on -k regex:'elem_q2' -s 2 -c 1 python tools/config_times.py C3 "
              "(Hex27 SVK, 24^3)")
+full_capture(f"prof_{tag}_easdg.ncu-rep", f"{tag}_ncu_full_easdg.csv",
+             "C4_N=48 ncu --set full --clock-control none -k regex:'elem_easdg' -s 2 -c 1 python tools/config_times.py C4dg "
+             "(Hex8 + H9 EAS::DisplacementGradient NeoHooke nu=0.499, 48^3)")
 if len(traffic) > 1:
     json.dump(traffic, open(os.path.join(pr, f"{tag}_traffic.json"), "w"), indent=1)
