@@ -130,6 +130,29 @@ def tensor4_to_voigt(T):
 # --------------------------------------------------------------------------------------
 
 
+# deviatoric functions of the principal-stretch framework: (W, dW/dlambda_i, "second derivative" dS[i][k] as the
+# reference's secondDerivativeImpl returns it), all of (mu, lambda[..., 3], J)
+def _blatzko():
+    # deviatoric/blatzko.hh:60-92:  W = mu/2 (sum lambda_i^-2 + 2 J - 5)
+    def W(mu, lam, J):
+        return 0.5 * mu * ((1.0 / lam**2).sum(-1) + 2.0 * J - 5.0)
+
+    def dW(mu, lam, J):
+        return mu * (-1.0 / lam**3 + J[..., None] / lam)
+
+    def d2S(mu, lam, J):
+        dS = J[..., None, None] / (lam[..., :, None] * lam[..., None, :])
+        diag = (1.0 / lam**2) * (1.0 / lam**2 - J[..., None]) + 3.0 / lam**4
+        idx = np.arange(3)
+        dS[..., idx, idx] = diag
+        return mu * dS
+
+    return W, dW, d2S
+
+
+_DEVIATORIC = {"blatzko": _blatzko()}
+
+
 def lame_from_E_nu(E, nu):
     """physicshelper.hh:276-281."""
     lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
@@ -181,7 +204,46 @@ class Material:
             iljk = np.einsum("...il,...jk->...ijkl", invC, invC)
             T = lam * dy + (2.0 * (mu - lam * logJ))[..., None, None, None, None] * 0.5 * (ikjl + iljk)
             return psi, to_voigt(Sm, strain=False), tensor4_to_voigt(T)
+        if self.kind in _DEVIATORIC:
+            return self._hyperelastic(E6)
         raise NotImplementedError(self.kind)
+
+    def _hyperelastic(self, E6):
+        """Materials::Hyperelastic<Deviatoric<DF>, Volumetric<VF>> in principal stretches
+        (materials/hyperelastic/interface.hh:99-232, deviatoric/interface.hh:77-115, materialhelpers.hh:138-164), input
+        C = 2E + I:  lambda_i = sqrt(eig_i(C)), N = eigenvectors,
+            S   = sum_i (W,i / lambda_i) N_i (x) N_i  +  J U'(J) C^-1
+            L_iikk = dS(i,k) / (lambda_i lambda_k),   L_ikik = (S_i - S_k) / (lambda_i^2 - lambda_k^2)
+                     [ 0.5 (L_iiii - L_iikk) when Dune::FloatCmp::eq(lambda_i, lambda_k, 1e-8) ]
+            CC  = sum_ik L_iikk N_iN_i (x) N_kN_k + sum_{i != k} L_ikik N_iN_k (x) (N_iN_k + N_kN_i)
+                  + J ((U' + J U'') C^-1 (x) C^-1 - 2 U' sym(C^-1 (.) C^-1))
+        Here mu is the deviatoric parameter (makeBlatzKo(mu), factory.hh:34-39); the volumetric function is VF0 (none)."""
+        W, dW, d2S = _DEVIATORIC[self.kind]
+        Cm = 2.0 * from_voigt(E6, strain=True) + np.eye(3)
+        ev, N = np.linalg.eigh(Cm)  # ascending, like Eigen::SelfAdjointEigenSolver
+        lam = np.sqrt(ev)
+        J = lam.prod(-1)
+        if np.any(J <= 0.0) or np.any(ev <= 0.0):
+            raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
+        mu = self.mu
+        psi = W(mu, lam, J)
+        Sp = dW(mu, lam, J) / lam  # principal PK2 stresses
+        dS = d2S(mu, lam, J)       # [.., i, k]
+        L1 = dS / (lam[..., :, None] * lam[..., None, :])  # L_iikk
+        lam2 = lam * lam
+        num = Sp[..., :, None] - Sp[..., None, :]
+        den = lam2[..., :, None] - lam2[..., None, :]
+        # Dune::FloatCmp::eq(a, b, 1e-8), relativeWeak: |a - b| <= 1e-8 * max(|a|, |b|)
+        close = np.abs(lam[..., :, None] - lam[..., None, :]) <= 1e-8 * np.maximum(np.abs(lam[..., :, None]), np.abs(lam[..., None, :]))
+        diagL = np.diagonal(L1, axis1=-2, axis2=-1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            L2 = np.where(close, 0.5 * (diagL[..., :, None] - L1), num / np.where(den == 0.0, 1.0, den))
+        Sm = np.einsum("...i,...ai,...bi->...ab", Sp, N, N)
+        T = np.einsum("...ik,...ai,...bi,...ck,...dk->...abcd", L1, N, N, N, N)
+        off = 1.0 - np.eye(3)
+        T = T + np.einsum("...ik,ik,...ai,...bk,...ci,...dk->...abcd", L2, off, N, N, N, N)
+        T = T + np.einsum("...ik,ik,...ai,...bk,...ck,...di->...abcd", L2, off, N, N, N, N)
+        return psi, to_voigt(Sm, strain=False), tensor4_to_voigt(T)
 
     def _reduce_stress(self, Ev):
         """VanishingStress::reduceStress (vanishingstress.hh:150-199): Newton-Raphson (tol, at most 100 iterations,

@@ -38,6 +38,44 @@ def test_A1_A2_cantilever_displacement_gradient(dim, mat, m, fn, iters, maxd):
     assert abs(np.abs(d).max() - maxd) < 1e-10
 
 
+@pytest.mark.parametrize(
+    "dim,m,fn,iters,maxd",
+    # tests/src/testcantileverbeamEAS.cpp: the Blatz-Ko rows (principal-stretch hyperelastic framework)
+    [(c["dim"], c["eas"], c["function"], c["newton_iterations"], c["max_abs_d"])
+     for c in GOLDEN["cantilever_eas_blatzko"]["cases"]],
+)
+def test_A1_A2_cantilever_blatzko(dim, m, fn, iters, maxd):
+    """Materials::Hyperelastic<Deviatoric<BlatzKo>, Volumetric<VF0>> (materials/hyperelastic/interface.hh,
+    deviatoric/interface.hh, deviatoric/blatzko.hh) under all three enhancement types."""
+    mesh, kind, _, flags, fext = cantilever(dim, "neohooke", m)
+    kind.eas_function = fn
+    mat = o.Material("blatzko", 0.0, 40.0, plane_strain=(dim == 2))
+    asm = o.FlatAssembler(mesh, kind, mat, flags, fext=fext)
+    d, lam, info = o.load_control(asm, np.zeros(asm.n), 20, 0.0, 1.0, tol=1e-10, dbc="full")
+    assert info["success"] and info["total_iterations"] == iters
+    assert abs(np.abs(d).max() - maxd) < 1e-10
+
+
+def test_blatzko_law_is_hyperelastic():
+    """S = dpsi/dE and CC = dS/dE by central differences (Voigt, engineering shear), CC symmetric, stress-free reference
+    state with the degenerate-eigenvalue branch of deviatoric/interface.hh:98-106."""
+    mat = o.Material("blatzko", 0.0, 40.0)
+    E = 0.1 * np.random.default_rng(0).uniform(-1, 1, (6, 6))
+    psi, S, C = mat.evaluate(E)
+    h = 1e-6
+    for q in range(6):
+        Ep, Em = E.copy(), E.copy()
+        Ep[:, q] += h
+        Em[:, q] -= h
+        pp, Sp, _ = mat.evaluate(Ep)
+        pm, Sm, _ = mat.evaluate(Em)
+        assert np.abs((pp - pm) / (2 * h) - S[:, q]).max() <= 1e-7 * np.abs(S).max()
+        assert np.abs((Sp - Sm) / (2 * h) - C[:, :, q]).max() <= 1e-7 * np.abs(C).max()
+    assert np.abs(C - np.swapaxes(C, -1, -2)).max() <= 1e-12 * np.abs(C).max()
+    p0, S0, C0 = mat.evaluate(np.zeros((1, 6)))
+    assert np.abs(S0).max() == 0.0 and np.allclose(np.diag(C0[0]), [120, 120, 120, 40, 40, 40])
+
+
 def test_displacement_gradient_tangent_is_the_derivative_of_the_condensed_residual():
     """K = dR/dd for the condensed system when alpha follows d (the static condensation eliminates alpha exactly to
     first order): finite differences on a distorted element with alpha != 0, both variants, 2D and 3D."""
