@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libikb200.so")
 IKB_ABI_VERSION = 3
 OK, EINVAL, ECUDA, ESTATE, ENOTIMPL, EMATERIAL, ENCCL = 0, -1, -2, -3, -4, -5, -6
 STRAIN_LINEAR, STRAIN_GL = 0, 1
-MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE = 0, 1, 2
+MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE, MAT_BLATZKO = 0, 1, 2, 3
 DBC_RAW, DBC_REDUCED, DBC_FULL = 0, 1, 2
 SCALAR, VECTOR, MATRIX = 1, 2, 4
 

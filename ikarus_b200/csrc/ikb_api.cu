@@ -48,13 +48,31 @@ cudaError_t launchEasForm(Handle* h, const EasArgs& EA) {
 template <int D>
 cudaError_t launchEasDg(Handle* h, const EasArgs& EA) {
   const bool tr = h->easFunction == IKB_EAS_DISPLACEMENT_GRADIENT_TRANSPOSED;
-  if (h->form == FORM_SVK) return tr ? launchElemEasDg<D, FORM_SVK, true>(EA, h->stream) : launchElemEasDg<D, FORM_SVK, false>(EA, h->stream);
-  if (h->form == FORM_NH) return tr ? launchElemEasDg<D, FORM_NH, true>(EA, h->stream) : launchElemEasDg<D, FORM_NH, false>(EA, h->stream);
+  if (h->form == FORM_SVK) return tr ? launchElemEasDg<D, FORM_SVK, ENH_DGT>(EA, h->stream) : launchElemEasDg<D, FORM_SVK, ENH_DG>(EA, h->stream);
+  if (h->form == FORM_NH) return tr ? launchElemEasDg<D, FORM_NH, ENH_DGT>(EA, h->stream) : launchElemEasDg<D, FORM_NH, ENH_DG>(EA, h->stream);
+  if (h->form == FORM_PS) return tr ? launchElemEasDg<D, FORM_PS, ENH_DGT>(EA, h->stream) : launchElemEasDg<D, FORM_PS, ENH_DG>(EA, h->stream);
+  return cudaErrorInvalidValue;
+}
+
+// principal-stretch laws: the plain element (m = 0) and the strain enhancements run through the generalised-tangent
+// kernel as well (ikb_elem_easdg.cuh, ENH_STRAIN)
+cudaError_t launchPsStrain(Handle* h, const EasArgs& EA) {
+  if (h->dim == 2) {
+    if (h->easM == 0) return launchElemEasDg<2, FORM_PS, ENH_STRAIN, 0>(EA, h->stream);
+    if (h->easM == 4) return launchElemEasDg<2, FORM_PS, ENH_STRAIN, 4>(EA, h->stream);
+    if (h->easM == 5) return launchElemEasDg<2, FORM_PS, ENH_STRAIN, 5>(EA, h->stream);
+    if (h->easM == 7) return launchElemEasDg<2, FORM_PS, ENH_STRAIN, 7>(EA, h->stream);
+  } else {
+    if (h->easM == 0) return launchElemEasDg<3, FORM_PS, ENH_STRAIN, 0>(EA, h->stream);
+    if (h->easM == 9) return launchElemEasDg<3, FORM_PS, ENH_STRAIN, 9>(EA, h->stream);
+    if (h->easM == 21) return launchElemEasDg<3, FORM_PS, ENH_STRAIN, 21>(EA, h->stream);
+  }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launchEas(Handle* h, const EasArgs& EA) {
   if (h->easFunction != IKB_EAS_STRAIN) return h->dim == 2 ? launchEasDg<2>(h, EA) : launchEasDg<3>(h, EA);
+  if (h->form == FORM_PS) return launchPsStrain(h, EA);
   if (h->dim == 2) {
     if (h->easM == 4) return launchEasForm<2, 4>(h, EA);
     if (h->easM == 5) return launchEasForm<2, 5>(h, EA);
@@ -116,7 +134,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
   A.planeStress = h->desc.plane_strain == IKB_REDUCE_PLANE_STRESS;
   A.psTol = h->desc.reduce_tol > 0.0 ? h->desc.reduce_tol : 1e-12;
   cudaError_t e = cudaErrorInvalidValue;
-  if (h->order == 1 && h->easM == 0) {
+  if (h->order == 1 && h->easM == 0 && h->form != FORM_PS) {
     // a pipelined solution upload is consumed chunk by chunk: chunk c waits for piece c of d only
     const int nch = h->piecesPending ? Handle::SOL_CHUNKS : 1;
     for (int c = 0; c < nch; ++c) {
@@ -667,7 +685,7 @@ int ensureSweepChunks(Handle* h) {
   h->sweepRowEnd.clear();
   const int64_t nRowNodes = h->rowEnd - h->rowBegin;
   const int K = std::min(h->sweepChunks, 32);
-  if (K < 2 || h->order != 1 || h->easM != 0 || !h->gatherPull || h->pullMirror || h->pullAsync || h->fusedEnabled ||
+  if (K < 2 || h->order != 1 || h->easM != 0 || h->form == FORM_PS || !h->gatherPull || h->pullMirror || h->pullAsync || h->fusedEnabled ||
       !h->csrc.p || !h->adjPtr.p || nRowNodes == 0 || h->nElem < (int64_t)K * 4096)
     return IKB_OK;
   DevBuf<int32_t> dMax;
@@ -1065,8 +1083,12 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     form = FORM_SVK;
   else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_NEOHOOKE)
     form = FORM_NH;
+  else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_BLATZKO)
+    form = FORM_PS;
   else
     return IKB_EINVAL;  // the reference statically rejects these strain/material pairings too
+  // principal-stretch laws: Q1 family (plain, strain- and displacement-gradient-enhanced), 3D or plane strain
+  if (form == FORM_PS && (desc->order != 1 || desc->plane_strain == IKB_REDUCE_PLANE_STRESS)) return IKB_ENOTIMPL;
   if (desc->dim == 2 && desc->plane_strain != IKB_REDUCE_PLANE_STRAIN && desc->plane_strain != IKB_REDUCE_PLANE_STRESS)
     return IKB_EINVAL;  // 2D needs a reduced material
   if (desc->dim == 3 && desc->plane_strain) return IKB_EINVAL;
@@ -1292,7 +1314,7 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->chunkElemEnd.clear();
   h->chunkDofEnd.clear();
   h->piecesPending = false;
-  if (h->order == 1 && h->easM == 0 && layout == LAYOUT_INTERLEAVED && ne >= (int64_t)Handle::SOL_CHUNKS * 8192) {
+  if (h->order == 1 && h->easM == 0 && h->form != FORM_PS && layout == LAYOUT_INTERLEAVED && ne >= (int64_t)Handle::SOL_CHUNKS * 8192) {
     int32_t runMax = -1;
     int64_t e = 0;
     for (int c = 0; c < Handle::SOL_CHUNKS; ++c) {
@@ -1326,7 +1348,7 @@ int ikb_upload_mesh(ikb_handle hh, const double* corner, const int64_t* elemDofs
   h->fusedTried = h->fusedOk = false;
   h->stateVersion++;
   h->Lap.release();
-  if (h->order == 1 && h->easM == 0 && h->form != FORM_SVK) {
+  if (h->order == 1 && h->easM == 0 && h->form != FORM_SVK && h->form != FORM_PS) {
     IKB_CUDA(h, h->Lap.alloc((size_t)h->npair * ne));
     if (D == 3)
       lap_q1_kernel<3><<<gridFor(ne, 128), 128, 0, h->stream>>>(h->X.p, ne, h->Lap.p);

@@ -24,12 +24,19 @@
 // formulation of the variant (parity first); it moves about 2 MB through shared memory per Hex8 element.
 #pragma once
 #include "ikb_elem_eas.cuh"
+#include "ikb_material_ps.cuh"
 
 namespace ikb {
 
-template <int D, bool TR>
+// what the internal variables enhance: the displacement gradient, its transposed form, or (ENH_STRAIN) the
+// Green-Lagrange strain with the ansatz tables of ikb_elem_eas.cuh (MM = 0: the plain displacement element)
+enum { ENH_DG = 0, ENH_DGT = 1, ENH_STRAIN = 2 };
+
+template <int D, int ENH, int MM = D * D>
 struct DgCfg {
-  static constexpr int N = 1 << D, ND = N * D, M = D * D, G = ND + M;
+  static constexpr bool TR = ENH == ENH_DGT, ST = ENH == ENH_STRAIN;
+  static constexpr int N = 1 << D, ND = N * D, M = ST ? MM : D * D, G = ND + M;
+  static constexpr int MX = M > 0 ? M : 1;       // array extent that stays legal for M = 0
   static constexpr int SYM = D * (D + 1) / 2;
   static constexpr int NP = G * (G + 1) / 2;     // generalised dof pairs I <= J
   static constexpr int NS = (NP + 31) / 32;      // pairs per lane
@@ -40,8 +47,8 @@ struct DgCfg {
   static constexpr int REC = REC0 | 1;           // odd stride: lanes on different dofs hit different banks
   static constexpr int GS = G | 1;               // row stride of the generalised tangent
   static constexpr int O_REC = 0, O_KG = O_REC + G * REC, O_RG = O_KG + G * GS, O_X = O_RG + G, O_U = O_X + ND,
-                       O_AL = O_U + ND, O_DU = O_AL + M, O_RHS = O_DU + ND;
-  static constexpr int WARP_DOUBLES = (O_RHS + M + 1) / 2 * 2;
+                       O_AL = O_U + ND, O_DU = O_AL + M, O_RHS = O_DU + ND, O_T0 = O_RHS + M;
+  static constexpr int WARP_DOUBLES = (O_T0 + (ST ? SYM * SYM : 0) + 1) / 2 * 2;
   static constexpr int WARPS = 4;
   static constexpr size_t SMEM = (size_t)WARPS * WARP_DOUBLES * 8;
 };
@@ -52,10 +59,12 @@ __device__ __forceinline__ constexpr int symI(int i, int j) {
   return symIdx<D>(i, j);
 }
 
-template <int D, int FORM, bool TR>
-__global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(EasArgs EA) {
-  static_assert(FORM == FORM_SVK || FORM == FORM_NH, "the displacement gradient enhances the nonlinear element");
-  using C = DgCfg<D, TR>;
+template <int D, int FORM, int ENH, int MM>
+__global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kernel(EasArgs EA) {
+  static_assert(FORM == FORM_SVK || FORM == FORM_NH || FORM == FORM_PS,
+                "the displacement gradient enhances the nonlinear element");
+  using C = DgCfg<D, ENH, MM>;
+  constexpr bool TR = C::TR, ST = C::ST;
   constexpr int N = C::N, ND = C::ND, M = C::M, G = C::G, SYM = C::SYM, REC = C::REC, GS = C::GS;
   constexpr unsigned FULL = 0xffffffffu;
   const ElemArgs& A = EA.E;
@@ -83,20 +92,26 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
     dus[t] = EA.updateMode ? __ldg(EA.dU + dof) : 0.0;
   }
   for (int t = lane; t < M; t += 32) al[t] = EA.alpha[(size_t)e * M + t];
+  // strain enhancement: (T(centre) detJ0)^-1 of the element (enhancedassumedstrains.hh:378-390), row-major S x S
+  [[maybe_unused]] double* T0 = ws + C::O_T0;
+  if constexpr (ST && M > 0)
+    for (int t = lane; t < SYM * SYM; t += 32) T0[t] = __ldg(EA.T0inv + (size_t)t * A.nElem + e);
   __syncwarp();
 
   // the pairs of this lane: t = lane + 32 s  ->  (I, J), I <= J, rows of G - I pairs each
   uint16_t pairIJ[C::NS];
   {
-    int I = 0, off = 0;  // off = index of pair (I, I)
+    // row I starts at pair index off(I) = I G - I (I - 1) / 2; closed form + one correction step each way
 #pragma unroll
     for (int s = 0; s < C::NS; ++s) {
       const int t = lane + 32 * s;
-      while (I < G - 1 && t >= off + (G - I)) {
-        off += G - I;
-        ++I;
-      }
-      const int J = I + (t - off);
+      const int tc = t < C::NP ? t : C::NP - 1;
+      int I = (int)(((float)(2 * G + 1) - sqrtf((float)((2 * G + 1) * (2 * G + 1) - 8 * tc))) * 0.5f);
+      I = I < 0 ? 0 : (I > G - 1 ? G - 1 : I);
+      if (I * G - I * (I - 1) / 2 > tc) --I;
+      if (I + 1 < G && (I + 1) * G - (I + 1) * I / 2 <= tc) ++I;
+      const int off = I * G - I * (I - 1) / 2;
+      const int J = I + (tc - off);
       pairIJ[s] = (t < C::NP) ? (uint16_t)(I | (J << 8)) : (uint16_t)0xffff;
     }
   }
@@ -104,6 +119,7 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
 #pragma unroll
   for (int s = 0; s < C::NS; ++s) acc[s] = 0.0;
   double rI[2] = {0.0, 0.0};  // R_gen of dofs lane and lane + 32
+  [[maybe_unused]] double energy = 0.0;
 
   // ---- element centre: J0^-T, detJ0, (transposed form) grad N^0 and F_c0
   double JI0[D][D], detJ0;
@@ -185,7 +201,18 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
     const double sc = detJ0 / detJ;
     // compatible gradient H_c[c][j] = sum_i Hx[c][i] Ji[j][i]; enhanced part Ht = sc J0^-T (alpha_(i,j) t_j) J0^-1
     double H[D][D], Hs[D][D];
-    {
+    if constexpr (ST) {
+#pragma unroll
+      for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) s = fma(Hx[c][i], Ji[j][i], s);
+          H[c][j] = s;
+          Hs[c][j] = 0.0;
+        }
+    } else {
       double T1[D][D];  // (alpha_(i,j) t_j) J0^-1 :  T1[i][l] = sum_j alpha_(Di+j) t_j JI0[l][j]
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -236,10 +263,49 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
         for (int k = 0; k < D; ++k) s = fma(F[k][i], F[k][j], s);
         Cm[i][j] = s;
       }
+    // strain enhancement: E = E_c + T0inv (sum_j s_j alpha_j e_(r_j)), s_j = p_j(xi) / detJ  (easfunctions/
+    // greenlagrangestrain.hh:40-141 with the ansatz of easvariants/linearandglstrains.hh), i.e. C += 2 (E - E_c)
+    [[maybe_unused]] double sm[D == 3 ? 6 : 3];
+    if constexpr (ST && M > 0) {
+      using T = EasTable<D, M>;
+      monomials<D>(g, 1.0 / detJ, sm);
+      double v[SYM];
+#pragma unroll
+      for (int q = 0; q < SYM; ++q) v[q] = 0.0;
+#pragma unroll
+      for (int j = 0; j < M; ++j) v[T::row(j)] = fma(sm[T::mono(j)], al[j], v[T::row(j)]);
+#pragma unroll
+      for (int p = 0; p < SYM; ++p) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < SYM; ++q) s = fma(T0[p * SYM + q], v[q], s);
+        int i, j;
+        voigtPair<D>(p, i, j);
+        if (i == j) {
+          Cm[i][i] = fma(2.0, s, Cm[i][i]);  // Voigt strain: shear entries are doubled
+        } else {
+          Cm[i][j] += s;
+          Cm[j][i] += s;
+        }
+      }
+    }
     // material: S, X, l', m'  (svk.hh; neohooke.hh:79-142 with C = 2E + I; plane strain: the 3D law at zero
     // out-of-plane strain, vanishingstrain.hh)
     double Sm[D][D], Xm[D][D], lp, mp;
-    if constexpr (FORM == FORM_SVK) {
+    [[maybe_unused]] double Np[3][3], L1[3][3], L2[3][3];  // principal frame and moduli of the principal-stretch laws
+    if constexpr (FORM == FORM_PS) {
+      double Sp[3], psi;
+      if (!principalLaw<D>(A.mu, Cm, Np, Sp, L1, L2, psi) && lane == 0)
+        atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
+      principalStress<D>(Np, Sp, Sm);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) Xm[i][j] = (i == j) ? 1.0 : 0.0;
+      lp = 0.0;   // the pair loop below then adds wd B_I : (CC : B_J), with CC : B_J in the X B X slot of the record
+      mp = 0.5;
+      energy = fma(wd, psi, energy);
+    } else if constexpr (FORM == FORM_SVK) {
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < D; ++i) tr += 0.5 * (Cm[i][i] - 1.0);
@@ -319,7 +385,7 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
           for (int r = 0; r < D; ++r)
 #pragma unroll
             for (int j = 0; j < D; ++j) dF[r][j] = (r == c) ? gph[j] : 0.0;
-        } else {
+        } else if constexpr (!ST) {
           const int p = I - ND, i0 = p / D, j0 = p - i0 * D;
           double Ht[D][D];
           const double f = sc * (j0 == 0 ? tt[0] : (j0 == 1 ? tt[1] : tt[D - 1]));
@@ -368,7 +434,8 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
           }
         }
         // B = sym(F^T dF), X B X, X:B, dF S
-        double FtdF[D][D], Bm[D][D], XB[D][D];
+        double FtdF[D][D], Bm[D][D];
+        [[maybe_unused]] double XB[D][D];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -382,30 +449,59 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
         for (int i = 0; i < D; ++i)
 #pragma unroll
           for (int j = 0; j < D; ++j) Bm[i][j] = 0.5 * (FtdF[i][j] + FtdF[j][i]);
+        if constexpr (ST && M > 0) {
+          if (I >= ND) {
+            // enhanced strain dof: dE/dalpha_j = column j of M(xi) = T0inv[:, r_j] s_j, no variation of F
+            using T = EasTable<D, M>;
+            const int jj = I - ND;
+            const int rj = T::row(jj);
+            const double sj = sm[T::mono(jj)];
 #pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) s = fma(Xm[i][k], Bm[k][j], s);
-            XB[i][j] = s;
+            for (int p = 0; p < SYM; ++p) {
+              int i, j;
+              voigtPair<D>(p, i, j);
+              const double v = T0[p * SYM + rj] * sj;
+              Bm[i][j] = Bm[j][i] = (i == j) ? v : 0.5 * v;
+            }
           }
+        }
         double* r = rec + I * REC;
         double tI = 0.0, rS = 0.0;
+        if constexpr (FORM == FORM_PS) {
+          double CB[D][D];
+          principalTangentTimes<D>(Np, L1, L2, Bm, CB);
 #pragma unroll
-        for (int i = 0; i < D; ++i)
+          for (int i = 0; i < D; ++i)
 #pragma unroll
-          for (int j = i; j < D; ++j) {
-            double s = 0.0;
+            for (int j = i; j < D; ++j) {
+              r[C::O_B + symI<D>(i, j)] = Bm[i][j];
+              r[C::O_XBX + symI<D>(i, j)] = CB[i][j];
+            }
+        } else {
 #pragma unroll
-            for (int k = 0; k < D; ++k) s = fma(XB[i][k], Xm[k][j], s);
-            r[C::O_B + symI<D>(i, j)] = Bm[i][j];
-            r[C::O_XBX + symI<D>(i, j)] = s;
-          }
+          for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              double s = 0.0;
+#pragma unroll
+              for (int k = 0; k < D; ++k) s = fma(Xm[i][k], Bm[k][j], s);
+              XB[i][j] = s;
+            }
+#pragma unroll
+          for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+              double s = 0.0;
+#pragma unroll
+              for (int k = 0; k < D; ++k) s = fma(XB[i][k], Xm[k][j], s);
+              r[C::O_B + symI<D>(i, j)] = Bm[i][j];
+              r[C::O_XBX + symI<D>(i, j)] = s;
+            }
+#pragma unroll
+          for (int i = 0; i < D; ++i) tI += XB[i][i];
+        }
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          tI += XB[i][i];
 #pragma unroll
           for (int j = 0; j < D; ++j) rS = fma(Bm[i][j], Sm[i][j], rS);
         }
@@ -459,6 +555,9 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
 
   // ---- generalised tangent and residual to shared memory
   __syncwarp();
+  if constexpr (FORM == FORM_PS && M == 0) {
+    if ((A.what & IKB_SCALAR) && lane == 0) A.Est[e] = energy;  // int psi dV (nonlinearelastic.hh:276-290)
+  }
 #pragma unroll
   for (int s = 0; s < C::NS; ++s) {
     const unsigned pj = pairIJ[s];
@@ -505,7 +604,7 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
       __syncwarp();
     }
     const double ip = 1.0 / Kg[(ND + k) * GS + ND + k];
-    double f[M];
+    double f[C::MX];
 #pragma unroll
     for (int r = 0; r < M; ++r) f[r] = Kg[(ND + r) * GS + ND + k];
     __syncwarp();
@@ -562,15 +661,15 @@ __global__ void __launch_bounds__(32 * DgCfg<D, TR>::WARPS) elem_easdg_kernel(Ea
   }
 }
 
-template <int D, int FORM, bool TR>
+template <int D, int FORM, int ENH, int MM = D * D>
 cudaError_t launchElemEasDg(const EasArgs& A, cudaStream_t st) {
-  using C = DgCfg<D, TR>;
-  cudaError_t e =
-      cudaFuncSetAttribute(elem_easdg_kernel<D, FORM, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  using C = DgCfg<D, ENH, MM>;
+  cudaError_t e = cudaFuncSetAttribute(elem_easdg_kernel<D, FORM, ENH, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((A.E.nElem + C::WARPS - 1) / C::WARPS);
   if (grid == 0) return cudaSuccess;
-  elem_easdg_kernel<D, FORM, TR><<<grid, 32 * C::WARPS, C::SMEM, st>>>(A);
+  elem_easdg_kernel<D, FORM, ENH, MM><<<grid, 32 * C::WARPS, C::SMEM, st>>>(A);
   return cudaGetLastError();
 }
 

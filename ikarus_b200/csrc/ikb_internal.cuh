@@ -11,7 +11,8 @@
 
 namespace ikb {
 
-enum Form { FORM_LE = 0, FORM_SVK = 1, FORM_NH = 2 };
+// FORM_PS: the principal-stretch hyperelastic laws (ikb_material_ps.cuh), served by the generalised-tangent kernel
+enum Form { FORM_LE = 0, FORM_SVK = 1, FORM_NH = 2, FORM_PS = 3 };
 enum Layout { LAYOUT_INTERLEAVED = 0, LAYOUT_LEXICOGRAPHIC = 1 };
 
 constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;

@@ -8,6 +8,7 @@
 // (VTK output, stress checks), bandwidth-light and far off the assembly hot path.
 #pragma once
 #include "ikb_elem_eas.cuh"
+#include "ikb_material_ps.cuh"
 #include "ikb_internal.cuh"
 
 namespace ikb {
@@ -48,6 +49,15 @@ __device__ __forceinline__ void easColumn(int m, int j, int& row, int& mono) {
 
 // 3D law on the full Voigt strain E6 (shear entries doubled): S6.  Returns false for det C <= 0 (NeoHooke).
 __device__ __forceinline__ bool stress3d(int form, double lambda, double mu, const double (&E6)[6], double (&S6)[6]) {
+  if (form == FORM_PS) {  // principal-stretch laws (hyperelastic/interface.hh:124-141), ikb_material_ps.cuh
+    double Cm[3][3], Np[3][3], Sp[3], L1[3][3], L2[3][3], psi, Sm[3][3];
+    Cm[0][0] = 2.0 * E6[0] + 1.0, Cm[1][1] = 2.0 * E6[1] + 1.0, Cm[2][2] = 2.0 * E6[2] + 1.0;
+    Cm[1][2] = Cm[2][1] = E6[3], Cm[0][2] = Cm[2][0] = E6[4], Cm[0][1] = Cm[1][0] = E6[5];
+    if (!principalLaw<3>(mu, Cm, Np, Sp, L1, L2, psi)) return false;
+    principalStress<3>(Np, Sp, Sm);
+    S6[0] = Sm[0][0], S6[1] = Sm[1][1], S6[2] = Sm[2][2], S6[3] = Sm[1][2], S6[4] = Sm[0][2], S6[5] = Sm[0][1];
+    return true;
+  }
   if (form != FORM_NH) {  // svk.hh:77-164, linearelasticity.hh:33-136
     const double tr = E6[0] + E6[1] + E6[2];
     for (int i = 0; i < 3; ++i) S6[i] = lambda * tr + 2.0 * mu * E6[i];

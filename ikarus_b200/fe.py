@@ -56,6 +56,13 @@ class Materials:
     def NeoHooke(p):
         return _Material("NeoHooke", capi.MAT_NEOHOOKE, capi.STRAIN_GL, p)
 
+    @staticmethod
+    def makeBlatzKo(mu):
+        """Materials::makeBlatzKo(mu) = Hyperelastic<Deviatoric<BlatzKoT>, Volumetric<VF0T>>, the principal-stretch
+        framework (materials/hyperelastic/factory.hh:34-39, interface.hh:99-232, deviatoric/blatzko.hh:60-92)."""
+        return _Material("Hyperelastic (Deviatoric function: BlatzKo, Volumetric function: None)", capi.MAT_BLATZKO,
+                         capi.STRAIN_GL, LamesFirstParameterAndShearModulus(0.0, float(mu)))
+
 
 def planeStrain(mat: _Material) -> _Material:
     """Materials::planeStrain (mechanics/materials/vanishingstrain.hh:147-198)."""

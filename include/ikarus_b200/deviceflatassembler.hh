@@ -131,6 +131,14 @@ struct MaterialCode<Ikarus::Materials::NeoHookeT<ST>>
 {
   static constexpr int material = IKB_MAT_NEOHOOKE, reduction = IKB_REDUCE_NONE;
 };
+/** makeBlatzKo(mu) = Hyperelastic<Deviatoric<BlatzKoT<ST>>> without a volumetric part (materials/hyperelastic/
+ *  factory.hh:34-39, interface.hh:33-41); its material parameter is the scalar mu (deviatoric/blatzko.hh:49-63) */
+template <typename ST, typename VOL>
+requires(!Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::Materials::BlatzKoT<ST>>, VOL>::hasVolumetricPart)
+struct MaterialCode<Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::Materials::BlatzKoT<ST>>, VOL>>
+{
+  static constexpr int material = IKB_MAT_BLATZKO, reduction = IKB_REDUCE_NONE;
+};
 /** planeStrain(mat) (materials/vanishingstrain.hh:186-198) */
 template <auto pairs, typename MI>
 struct MaterialCode<Ikarus::Materials::VanishingStrain<pairs, MI>>
@@ -165,8 +173,19 @@ struct ElementAccess<FE>
   /** VanishingStress keeps its tolerance private (vanishingstress.hh:231); planeStress() defaults to 1e-8
    *  (vanishingstress.hh:254-257).  Specialise ElementAccess to pass another one. */
   static double reductionTolerance(const FE&) { return 1e-8; }
-  static double lambda(const FE& fe) { return fe.material().materialParameters().lambda; }
-  static double mu(const FE& fe) { return fe.material().materialParameters().mu; }
+  /** Lame parameters of the two-parameter laws; a principal-stretch law with one scalar parameter passes it as mu */
+  static double lambda(const FE& fe) {
+    if constexpr (requires { fe.material().materialParameters().lambda; })
+      return fe.material().materialParameters().lambda;
+    else
+      return 0.0;
+  }
+  static double mu(const FE& fe) {
+    if constexpr (requires { fe.material().materialParameters().mu; })
+      return fe.material().materialParameters().mu;
+    else
+      return static_cast<double>(fe.material().materialParameters());
+  }
   static int numberOfInternalVariables(const FE& fe) {
     if constexpr (requires { fe.numberOfInternalVariables(); })
       return fe.numberOfInternalVariables();

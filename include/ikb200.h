@@ -43,8 +43,12 @@ enum { IKB_OK = 0, IKB_EINVAL = -1, IKB_ECUDA = -2, IKB_ESTATE = -3, IKB_ENOTIMP
  * nonLinearElastic (mechanics/nonlinearelastic.hh) */
 enum { IKB_STRAIN_LINEAR = 0, IKB_STRAIN_GREEN_LAGRANGE = 1 };
 /* Materials::LinearElasticity / StVenantKirchhoff / NeoHooke
- * (mechanics/materials/linearelasticity.hh, svk.hh, hyperelastic/neohooke.hh) */
-enum { IKB_MAT_LINEAR_ELASTICITY = 0, IKB_MAT_SVK = 1, IKB_MAT_NEOHOOKE = 2 };
+ * (mechanics/materials/linearelasticity.hh, svk.hh, hyperelastic/neohooke.hh);
+ * IKB_MAT_BLATZKO: Materials::makeBlatzKo(mu) = Hyperelastic<Deviatoric<BlatzKoT>, Volumetric<VF0T>>, the
+ * principal-stretch framework (hyperelastic/interface.hh:99-232, deviatoric/interface.hh:77-115,
+ * deviatoric/blatzko.hh:60-92, factory.hh:34-39): ikb_desc.mu is its parameter, lambda is ignored; Q1 elements
+ * (plain and every EAS form), 3D or planeStrain */
+enum { IKB_MAT_LINEAR_ELASTICITY = 0, IKB_MAT_SVK = 1, IKB_MAT_NEOHOOKE = 2, IKB_MAT_BLATZKO = 3 };
 /* DBCOption (assembler/dirichletbcenforcement.hh) */
 enum { IKB_DBC_RAW = 0, IKB_DBC_REDUCED = 1, IKB_DBC_FULL = 2 };
 /* affordance bits: ScalarAffordance::mechanicalPotentialEnergy, VectorAffordance::forces,

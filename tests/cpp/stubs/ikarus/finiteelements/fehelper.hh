@@ -3,6 +3,7 @@
 #include <array>
 #include <cstddef>
 #include <string>
+#include <type_traits>
 #include <vector>
 namespace Ikarus {
 enum class StrainTags { linear, deformationGradient, displacementGradient, greenLagrangian, rightCauchyGreenTensor };
@@ -37,6 +38,51 @@ namespace Materials {
     LamesFirstParameterAndShearModulus p;
     static std::string name() { return "NeoHooke"; }
     const auto& materialParameters() const { return p; }
+  };
+  // the principal-stretch framework as far as the adapter reads it (materials/hyperelastic/interface.hh:33-97,
+  // deviatoric/interface.hh:35-66, deviatoric/blatzko.hh:34-63, volumetric/interface.hh:31, volumetricfunctions.hh:30-45)
+  template <typename ST>
+  struct BlatzKoT
+  {
+    using ScalarType         = ST;
+    using MaterialParameters = double;
+    double mu_;
+    MaterialParameters materialParametersImpl() const { return mu_; }
+    static std::string name() { return "BlatzKo"; }
+  };
+  template <typename DF>
+  struct Deviatoric
+  {
+    using ScalarType         = typename DF::ScalarType;
+    using DeviatoricFunction = DF;
+    using MaterialParameters = typename DF::MaterialParameters;
+    DF deviatoricFunction_;
+    const MaterialParameters materialParameters() const { return deviatoricFunction_.materialParametersImpl(); }
+    static std::string name() { return "Deviatoric function: " + DF::name(); }
+  };
+  template <typename ST>
+  struct VF0T
+  {
+    static std::string name() { return "None"; }
+  };
+  template <typename VF>
+  struct Volumetric
+  {
+    using VolumetricFunction = VF;
+    using MaterialParameter  = double;
+    static std::string name() { return "Volumetric function: " + VF::name(); }
+  };
+  using NoVolumetricPart = Volumetric<VF0T<double>>;
+  template <typename DEV, typename VOL = NoVolumetricPart>
+  struct Hyperelastic
+  {
+    static constexpr bool hasVolumetricPart = !std::is_same_v<VOL, NoVolumetricPart>;
+    static constexpr auto strainTag         = StrainTags::rightCauchyGreenTensor;
+    static constexpr bool isReduced         = false;
+    using MaterialParameters = typename DEV::MaterialParameters;
+    DEV dev_;
+    static std::string name() { return "Hyperelastic (" + DEV::name() + ")"; }
+    const MaterialParameters materialParameters() const { return dev_.materialParameters(); }
   };
   struct MatrixIndexPair
   {

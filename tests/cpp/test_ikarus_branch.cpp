@@ -103,6 +103,10 @@ static_assert(MaterialCode<NH>::material == IKB_MAT_NEOHOOKE && MaterialCode<NH>
 static_assert(MaterialCode<PStrain>::material == IKB_MAT_SVK && MaterialCode<PStrain>::reduction == IKB_REDUCE_PLANE_STRAIN);
 static_assert(MaterialCode<PStress>::material == IKB_MAT_LINEAR_ELASTICITY &&
               MaterialCode<PStress>::reduction == IKB_REDUCE_PLANE_STRESS);
+using BK        = Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::Materials::BlatzKoT<double>>>;
+using BKPStrain = Ikarus::Materials::VanishingStrain<onePair, BK>;
+static_assert(MaterialCode<BK>::material == IKB_MAT_BLATZKO && MaterialCode<BKPStrain>::material == IKB_MAT_BLATZKO &&
+              MaterialCode<BKPStrain>::reduction == IKB_REDUCE_PLANE_STRAIN);  // makeBlatzKo(mu), factory.hh:34-39
 static_assert(MaterialCode<int>::material < 0);
 
 // a nonlinear solver's broadcaster, as far as subscribeTo() needs it (utils/broadcaster)

@@ -9,7 +9,7 @@ _MAT = {"linear": ik.Materials.LinearElasticity, "svk": ik.Materials.StVenantKir
 
 def device_assembler(mesh, kind, mat, flags, layout="interleaved", fext=None, dense=False, mode="mirror", volume=None):
     p = ik.fe.LamesFirstParameterAndShearModulus(mat.lam, mat.mu)
-    m = _MAT[mat.kind](p)
+    m = ik.Materials.makeBlatzKo(mat.mu) if mat.kind == "blatzko" else _MAT[mat.kind](p)
     if mat.plane_strain:
         m = ik.planeStrain(m)
     if getattr(mat, "plane_stress", False):
