@@ -68,3 +68,29 @@ def test_linear_patch_test_with_inhomogeneous_dirichlet_values():
         u = d[mesh.elem_dofs()].reshape(5, 4, 2)
         sig = o.stress_at(kind, mat, mesh.corner_coords, u, np.array([0.5, 0.5]))
         assert np.abs(sig[:, 0] - GOLDEN["plane_stress_patch_test"]["sigma_xx"]).max() < 1e-10  # constant stress state
+
+
+import pytest
+
+
+@pytest.mark.xfail(strict=True, reason="anchor B1 is not reproduced by the restatement (3e-5 relative); see DESIGN.md section 8")
+def test_B1_plane_stress_block_under_volume_load_is_not_reproduced():
+    """tests/src/testnonlinearelasticity.hh:47-150 with createGrid<Grids::Yasp> (tests/src/testcommon.hh:70-79):
+    unit square, 10 x 10 Quad4, planeStress(SVK(E = 1000, nu = 0.3), 1e-8), volume load (lambda, 2 lambda), y = 0
+    clamped, lambda 0 -> 50.  Kept as a strict xfail so that the day the cause is found this test says so: none of
+    load scale, E, nu alone maps the restatement's (energy, max d) onto the reference's pair, NR and TR reach the same
+    minimum, and for SVK the stress reduction is exact after one Newton step, so the tolerance plays no role."""
+    g = GOLDEN["not_reproduced"]["plane_stress_volume_load_B1"]
+    mesh = o.structured_mesh((10, 10), (1.0, 1.0))
+    lam, mu = o.lame_from_E_nu(1000.0, 0.3)
+    mat = o.Material("svk", lam, mu, plane_stress=True, ps_tol=1e-8)
+    kind = o.ElementKind(2, 1, "gl")
+    flags = o.fix_nodes(mesh, o.boundary_nodes(mesh, 1, 0.0))
+    fext = o.volume_load_vector(mesh, kind, lambda x: (1.0, 2.0))
+    asm = o.FlatAssembler(mesh, kind, mat, flags, fext=fext)
+    d, lamb, info = o.load_control(asm, np.zeros(asm.n), 5, 0.0, 50.0, tol=1e-11, dbc="full", max_iter=50)
+    assert info["success"]
+    # what the restatement gives is pinned too, so a change of the oracle shows up here
+    assert abs(asm.scalar(d, lamb) - g["oracle_energy"]) < 1e-9 and abs(d.max() - g["oracle_max_d"]) < 1e-10
+    assert abs(asm.scalar(d, lamb) - g["energy"]) < 1e-8 * abs(g["energy"])
+    assert abs(d.max() - g["max_d"]) < 1e-12
