@@ -130,17 +130,22 @@ def tensor4_to_voigt(T):
 # --------------------------------------------------------------------------------------
 
 
-# deviatoric functions of the principal-stretch framework: (W, dW/dlambda_i, "second derivative" dS[i][k] as the
-# reference's secondDerivativeImpl returns it), all of (mu, lambda[..., 3], J)
-def _blatzko():
+# deviatoric functions of the principal-stretch framework: each returns (W, dW/dlambda_i, dS[i][k]) of lambda[..., 3],
+# dS as the reference's secondDerivativeImpl returns it (= Hess W - diag(W,i / lambda_i), the array the Deviatoric
+# interface divides by lambda_i lambda_k, deviatoric/interface.hh:95-99).  The formulas follow the reference's
+# statements term by term.
+def _blatzko(mu):
     # deviatoric/blatzko.hh:60-92:  W = mu/2 (sum lambda_i^-2 + 2 J - 5)
-    def W(mu, lam, J):
+    def W(lam):
+        J = lam.prod(-1)
         return 0.5 * mu * ((1.0 / lam**2).sum(-1) + 2.0 * J - 5.0)
 
-    def dW(mu, lam, J):
+    def dW(lam):
+        J = lam.prod(-1)
         return mu * (-1.0 / lam**3 + J[..., None] / lam)
 
-    def d2S(mu, lam, J):
+    def d2S(lam):
+        J = lam.prod(-1)
         dS = J[..., None, None] / (lam[..., :, None] * lam[..., None, :])
         diag = (1.0 / lam**2) * (1.0 / lam**2 - J[..., None]) + 3.0 / lam**4
         idx = np.arange(3)
@@ -150,7 +155,260 @@ def _blatzko():
     return W, dW, d2S
 
 
-_DEVIATORIC = {"blatzko": _blatzko()}
+def _ogden(mus, alphas, deviatoric):
+    """deviatoric/ogden.hh:98-190, total or deviatoric stretches (lambdaBar = J^(-1/3) lambda, materialhelpers.hh:150-156)."""
+    mus, alphas = [float(m) for m in mus], [float(a) for a in alphas]
+
+    def bar(lam):
+        return lam * (lam.prod(-1) ** (-1.0 / 3.0))[..., None]
+
+    def W(lam):
+        e = 0.0
+        if deviatoric:
+            lb = bar(lam)
+            for m, a in zip(mus, alphas):
+                e = e + m / a * ((lb**a).sum(-1) - 3.0)
+        else:
+            logJ = np.log(lam.prod(-1))
+            for m, a in zip(mus, alphas):
+                e = e + m / a * ((lam**a).sum(-1) - 3.0) - m * logJ
+        return e
+
+    def dW(lam):
+        if deviatoric:
+            lb = bar(lam)
+            dWb = sum(m * lb ** (a - 1.0) for m, a in zip(mus, alphas))
+            sumLb = (lb * dWb).sum(-1)
+            return (lb * dWb - (1.0 / 3.0) * sumLb[..., None]) / lam
+        return sum(m * (lam**a - 1.0) for m, a in zip(mus, alphas)) / lam
+
+    def d2S(lam):
+        dS = np.zeros(lam.shape + (3,))
+        idx = np.arange(3)
+        if deviatoric:
+            lb = bar(lam)
+            dWl = dW(lam)
+            for a_ in range(3):
+                for b_ in range(3):
+                    v = 0.0
+                    for m, al in zip(mus, alphas):
+                        psum = (lb**al).sum(-1)
+                        if a_ == b_:
+                            v = v + m * al * (1.0 / 3.0 * lb[..., a_] ** al + 1.0 / 9.0 * psum)
+                        else:
+                            v = v + m * al * (-(1.0 / 3.0) * (lb[..., a_] ** al + lb[..., b_] ** al) + 1.0 / 9.0 * psum)
+                    v = v * (1.0 / (lam[..., a_] * lam[..., b_]))
+                    if a_ == b_:
+                        v = v - (2.0 / lam[..., a_]) * dWl[..., a_]
+                    dS[..., a_, b_] = v
+        else:
+            for m, al in zip(mus, alphas):
+                dS[..., idx, idx] += (-2.0 * m * (lam**al - 1.0) + m * lam**al * al) / lam**2
+        return dS
+
+    return W, dW, d2S
+
+
+def _dev_invariants(lam):
+    """deviatoric/deviatoricinvariants.hh:52-107 over materialhelpers.hh:158-170: W1 = I1 I3^(-1/3), W2 = I2 I3^(-2/3) and
+    their first / second derivatives with respect to the principal stretches."""
+    l2 = lam * lam
+    I1 = l2.sum(-1)
+    I2 = l2[..., 0] * l2[..., 1] + l2[..., 1] * l2[..., 2] + l2[..., 0] * l2[..., 2]
+    I3 = l2.prod(-1)
+    p13, p23 = I3 ** (1.0 / 3.0), I3 ** (2.0 / 3.0)
+    W1 = I1 * I3 ** (-1.0 / 3.0)
+    W2 = I2 * I3 ** (-2.0 / 3.0)
+    d1 = 2.0 * (3.0 * l2 - I1[..., None]) / (3.0 * lam * p13[..., None])
+    d2 = -2.0 * (3.0 * I3[..., None] / l2 - I2[..., None]) / (3.0 * lam * p23[..., None])
+    dd1 = np.zeros(lam.shape + (3,))
+    dd2 = np.zeros(lam.shape + (3,))
+    for i in range(3):
+        for j in range(3):
+            if i == j:
+                dd1[..., i, i] = (2.0 / 9.0) * (5.0 * I1 - 3.0 * l2[..., i]) / (l2[..., i] * p13)
+                dd2[..., i, i] = (2.0 / 9.0) * ((15.0 * I3 / l2[..., i]) - I2) / (l2[..., i] * p23)
+            else:
+                dd1[..., i, j] = (4.0 / 9.0) * (I1 - 3.0 * (l2[..., i] + l2[..., j])) / (lam[..., i] * lam[..., j] * p13)
+                dd2[..., i, j] = (-4.0 / 9.0) * (2.0 * I2 - 3.0 * l2[..., i] * l2[..., j]) / (lam[..., i] * lam[..., j] * p23)
+    return W1, W2, d1, d2, dd1, dd2
+
+
+def _pam(x, p, m):
+    # InvariantBasedT::powerAndMultiply (invariantbased.hh:205-214)
+    if m == 0:
+        return 0.0 * x
+    if p == 0:
+        return m + 0.0 * x
+    return x ** int(p) * m
+
+
+def _invariant_based(pex, qex, c):
+    """deviatoric/invariantbased.hh:84-188: W = sum_i c_i (W1 - 3)^p_i (W2 - 3)^q_i (Mooney-Rivlin: p = (1, 0), q = (0, 1);
+    Yeoh: p = (1, 2, 3), q = 0; factory.hh:68-108)."""
+    pex, qex, c = [int(v) for v in pex], [int(v) for v in qex], [float(v) for v in c]
+    assert all(p or q for p, q in zip(pex, qex)), "the exponents p_i and q_i must not both be zero (invariantbased.hh:216-221)"
+
+    def W(lam):
+        W1, W2 = _dev_invariants(lam)[:2]
+        W1, W2 = W1 - 3.0, W2 - 3.0
+        return sum(m * W1**p * W2**q for m, p, q in zip(c, pex, qex))
+
+    def dW(lam):
+        W1, W2, d1, d2, _, _ = _dev_invariants(lam)
+        W1, W2 = W1 - 3.0, W2 - 3.0
+        out = np.zeros_like(lam)
+        for m, p, q in zip(c, pex, qex):
+            out += m * ((_pam(W1, p - 1, p) * W2**q)[..., None] * d1 + (W1**p * _pam(W2, q - 1, q))[..., None] * d2)
+        return out
+
+    def d2S(lam):
+        W1, W2, d1, d2, dd1, dd2 = _dev_invariants(lam)
+        W1, W2 = W1 - 3.0, W2 - 3.0
+        dS = np.zeros(lam.shape + (3,))
+        for m, p, q in zip(c, pex, qex):
+            a1, a2 = _pam(W1, p - 1, p), _pam(W2, q - 1, q)
+            b1, b2 = _pam(W1, p - 2, p * (p - 1)), _pam(W2, q - 2, q * (q - 1))
+            for i in range(3):
+                for j in range(3):
+                    mix = d1[..., i] * d2[..., j] + d1[..., j] * d2[..., i]
+                    f1 = (a2 * mix + W2**q * dd1[..., i, j]) * a1 * m
+                    f2 = a2 * dd2[..., i, j] * W1**p * m
+                    f3 = b1 * W2**q * d1[..., i] * d1[..., j] * m
+                    f4 = b2 * W1**p * d2[..., i] * d2[..., j] * m
+                    dS[..., i, j] += f1 + f2 + f3 + f4
+                    if i == j:
+                        dS[..., i, j] -= (1.0 / lam[..., i]) * m * (a1 * W2**q * d1[..., i] + W1**p * a2 * d2[..., i])
+        return dS
+
+    return W, dW, d2S
+
+
+_AB_ALPHAS = (0.5, 1.0 / 20.0, 11.0 / 1050.0, 19.0 / 7000.0, 519.0 / 673750.0)
+
+
+def _arruda_boyce(mu, lambdaM):
+    """deviatoric/arrudaboyce.hh:88-160: five-term series in W1 with beta = 1 / lambdaM^2."""
+    beta = 1.0 / lambdaM**2.0
+
+    def W(lam):
+        W1 = _dev_invariants(lam)[0]
+        return mu * sum(a * beta**i * (W1 ** (i + 1) - 3.0 ** (i + 1)) for i, a in enumerate(_AB_ALPHAS))
+
+    def dW(lam):
+        W1, _, d1, _, _, _ = _dev_invariants(lam)
+        return sum((mu * a * beta**j * W1**j * (j + 1))[..., None] * d1 for j, a in enumerate(_AB_ALPHAS))
+
+    def d2S(lam):
+        W1, _, d1, _, dd1, _ = _dev_invariants(lam)
+        dyad = d1[..., :, None] * d1[..., None, :]
+        dS = np.zeros(lam.shape + (3,))
+        idx = np.arange(3)
+        for p, a in enumerate(_AB_ALPHAS):
+            f1 = mu * a * beta**p
+            f2 = (W1**p)[..., None, None] * dd1 * (p + 1)
+            f3 = (W1 ** (p - 1) * p * (p + 1))[..., None, None] * dyad if p else 0.0
+            dS += f1 * (f2 + f3)
+            dS[..., idx, idx] -= d1 / lam * f1 * (W1**p * (p + 1))[..., None]
+        return dS
+
+    return W, dW, d2S
+
+
+def _gent(mu, Jm):
+    """deviatoric/gent.hh:88-150: W = -mu/2 Jm ln(1 - (W1 - 3) / Jm)."""
+
+    def check(W1):
+        if np.any(Jm <= W1 - 3.0):
+            raise FloatingPointError("The material parameter Jm should be greater than (W1 - 3)")
+
+    def W(lam):
+        W1 = _dev_invariants(lam)[0]
+        check(W1)
+        return -(mu / 2.0) * Jm * np.log(1.0 - ((W1 - 3.0) / Jm))
+
+    def dW(lam):
+        W1, _, d1, _, _, _ = _dev_invariants(lam)
+        check(W1)
+        return (mu * d1 * Jm) / (2.0 * (Jm - W1) + 6.0)[..., None]
+
+    def d2S(lam):
+        W1, _, d1, _, dd1, _ = _dev_invariants(lam)
+        check(W1)
+        f = 1.0 - ((W1 - 3.0) / Jm)
+        dS = (mu / (2.0 * f))[..., None, None] * (dd1 + d1[..., :, None] * d1[..., None, :] / (f * Jm)[..., None, None])
+        idx = np.arange(3)
+        dS[..., idx, idx] -= (mu / (2.0 * lam * f[..., None])) * d1
+        return dS
+
+    return W, dW, d2S
+
+
+def _no_deviatoric():
+    # deviatoric/nodeviatoricfunction.hh (makePureVolumetric, factory.hh:161-165)
+    return (lambda lam: 0.0 * lam[..., 0]), (lambda lam: 0.0 * lam), (lambda lam: np.zeros(lam.shape + (3,)))
+
+
+def _volumetric(vf, beta):
+    """volumetric/volumetricfunctions.hh:25-380: (U, U', U'') of J for VF0..VF12; VF4, VF7, VF10 take beta."""
+    b = beta
+    ln = np.log
+    table = {
+        0: (lambda J: 0.0 * J, lambda J: 0.0 * J, lambda J: 0.0 * J),
+        1: (lambda J: 0.5 * (J - 1.0) ** 2, lambda J: J - 1.0, lambda J: 1.0 + 0.0 * J),
+        2: (lambda J: 0.25 * ((J - 1.0) ** 2 + ln(J) ** 2), lambda J: 0.5 * (J - 1.0 + 1.0 / J * ln(J)),
+            lambda J: 1.0 / (2.0 * J * J) * (1.0 + J * J - ln(J))),
+        3: (lambda J: 0.5 * ln(J) ** 2, lambda J: 1.0 / J * ln(J), lambda J: 1.0 / J**2 * (1.0 - ln(J))),
+        4: (lambda J: (1.0 / b**2) * ((1.0 / J**b) - 1.0 + b * ln(J)), lambda J: (1.0 / b) * ((1.0 / J) - (1.0 / (J ** (1.0 + b)))),
+            lambda J: (1.0 / b) * ((1.0 / J ** (2.0 + b)) * (1.0 + b - J**b))),
+        5: (lambda J: 0.25 * (J**2 - 1.0 - 2.0 * ln(J)), lambda J: 0.5 * (J - (1.0 / J)), lambda J: 0.5 * (1.0 + (1.0 / J**2))),
+        6: (lambda J: J - ln(J) - 1.0, lambda J: 1.0 - (1.0 / J), lambda J: 1.0 / J**2),
+        7: (lambda J: J**b * (b * ln(J) - 1.0) + 1.0, lambda J: b**2 * (1.0 / J ** (1.0 - b)) * ln(J),
+            lambda J: b**2 * J ** (b - 2.0) * (1.0 + (b - 1.0) * ln(J))),
+        8: (lambda J: J * ln(J) - J + 1.0, lambda J: ln(J), lambda J: 1.0 / J),
+        9: (lambda J: (1.0 / 32.0) * (J**2 - J**-2.0) ** 2, lambda J: (1.0 / 8.0) * (J**3 - (1.0 / J**5)),
+            lambda J: (1.0 / 8.0) * (5.0 * J**-6.0 + (3.0 * J**2))),
+        10: (lambda J: (J / b) * (1.0 - (J**-b / (1.0 - b))) + (1.0 / (b - 1.0)), lambda J: (1.0 / b) * (1.0 - J**-b),
+             lambda J: J ** (-1.0 - b)),
+        11: (lambda J: (1.0 / 50.0) * (J**5.0 + J**-5.0 - 2.0), lambda J: (1.0 / 10.0) * (J**4.0 - J**-6.0),
+             lambda J: (1.0 / 10.0) * (4.0 * J**3.0 + 6.0 * J**-7.0)),
+        12: (lambda J: J - 1.0, lambda J: 1.0 + 0.0 * J, lambda J: 0.0 * J),
+    }
+    return table[int(vf)]
+
+
+@dataclass
+class Hyper:
+    """A material of the principal-stretch framework, Hyperelastic<Deviatoric<DF>, Volumetric<VF>> as the factories build
+    it (materials/hyperelastic/factory.hh:12-165).  dev / params:
+      'blatzko' (mu,) | 'ogden_total' | 'ogden_dev' (mus, alphas) | 'invariant' (pex, qex, c) | 'arrudaboyce' (mu, lambdaM)
+      | 'gent' (mu, Jm) | 'none' ();  vf = 0..12 with the penalty parameter K (Lame's first parameter for total, the bulk
+    modulus for deviatoric stretches) and beta for VF4 / VF7 / VF10."""
+
+    dev: str
+    params: tuple
+    vf: int = 0
+    K: float = 0.0
+    beta: float = 0.0
+
+    def functions(self):
+        d, p = self.dev, self.params
+        if d == "blatzko":
+            return _blatzko(float(p[0]))
+        if d in ("ogden_total", "ogden_dev"):
+            return _ogden(p[0], p[1], d == "ogden_dev")
+        if d == "invariant":
+            return _invariant_based(*p)
+        if d == "arrudaboyce":
+            return _arruda_boyce(float(p[0]), float(p[1]))
+        if d == "gent":
+            return _gent(float(p[0]), float(p[1]))
+        if d == "none":
+            return _no_deviatoric()
+        raise NotImplementedError(d)
+
+
+_DEVIATORIC = ("blatzko", "hyperelastic")
 
 
 def lame_from_E_nu(E, nu):
@@ -172,6 +430,7 @@ class Material:
     # planeStress(mat, tol) = VanishingStress<{2,2},{1,2},{0,2}> (materials/vanishingstress.hh:35-230, 252-260)
     plane_stress: bool = False
     ps_tol: float = 1e-12
+    hyper: "Hyper | None" = None  # kind 'hyperelastic': the principal-stretch law; kind 'blatzko' = Hyper('blatzko', (mu,))
 
     # --- 3D law on Voigt GL strain (batched: E6[..., 6]) --------------------------------
     def _law3d(self, E6):
@@ -218,17 +477,18 @@ class Material:
             CC  = sum_ik L_iikk N_iN_i (x) N_kN_k + sum_{i != k} L_ikik N_iN_k (x) (N_iN_k + N_kN_i)
                   + J ((U' + J U'') C^-1 (x) C^-1 - 2 U' sym(C^-1 (.) C^-1))
         Here mu is the deviatoric parameter (makeBlatzKo(mu), factory.hh:34-39); the volumetric function is VF0 (none)."""
-        W, dW, d2S = _DEVIATORIC[self.kind]
+        law = self.hyper if self.kind == "hyperelastic" else Hyper("blatzko", (self.mu,))
+        W, dW, d2S = law.functions()
+        U, dU, ddU = _volumetric(law.vf, law.beta)
         Cm = 2.0 * from_voigt(E6, strain=True) + np.eye(3)
         ev, N = np.linalg.eigh(Cm)  # ascending, like Eigen::SelfAdjointEigenSolver
         lam = np.sqrt(ev)
         J = lam.prod(-1)
         if np.any(J <= 0.0) or np.any(ev <= 0.0):
             raise FloatingPointError("Determinant of right Cauchy Green tensor C must be greater than zero")
-        mu = self.mu
-        psi = W(mu, lam, J)
-        Sp = dW(mu, lam, J) / lam  # principal PK2 stresses
-        dS = d2S(mu, lam, J)       # [.., i, k]
+        psi = W(lam)
+        Sp = dW(lam) / lam  # principal PK2 stresses
+        dS = d2S(lam)       # [.., i, k]
         L1 = dS / (lam[..., :, None] * lam[..., None, :])  # L_iikk
         lam2 = lam * lam
         num = Sp[..., :, None] - Sp[..., None, :]
@@ -243,6 +503,17 @@ class Material:
         off = 1.0 - np.eye(3)
         T = T + np.einsum("...ik,ik,...ai,...bk,...ci,...dk->...abcd", L2, off, N, N, N, N)
         T = T + np.einsum("...ik,ik,...ai,...bk,...ck,...di->...abcd", L2, off, N, N, N, N)
+        if law.vf:
+            # interface.hh:103-157, 196-216: + K U(J);  S += J K U' C^-1;  CC += J ((U' + J U'') C^-1 (x) C^-1 - 2 U' sym(...))
+            Up, Upp = law.K * dU(J), law.K * ddU(J)
+            invC = np.linalg.inv(Cm)
+            psi = psi + law.K * U(J)
+            Sm = Sm + (J * Up)[..., None, None] * invC
+            dy = np.einsum("...ij,...kl->...ijkl", invC, invC)
+            ikjl = np.einsum("...ik,...jl->...ijkl", invC, invC)
+            iljk = np.einsum("...il,...jk->...ijkl", invC, invC)
+            T = T + J[..., None, None, None, None] * ((Up + J * Upp)[..., None, None, None, None] * dy
+                                                        - (2.0 * Up)[..., None, None, None, None] * 0.5 * (ikjl + iljk))
         return psi, to_voigt(Sm, strain=False), tensor4_to_voigt(T)
 
     def _reduce_stress(self, Ev):
