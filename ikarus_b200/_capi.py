@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libikb200.so")
 IKB_ABI_VERSION = 3
 OK, EINVAL, ECUDA, ESTATE, ENOTIMPL, EMATERIAL, ENCCL = 0, -1, -2, -3, -4, -5, -6
 STRAIN_LINEAR, STRAIN_GL = 0, 1
-MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE, MAT_BLATZKO = 0, 1, 2, 3
+MAT_LINEAR, MAT_SVK, MAT_NEOHOOKE, MAT_BLATZKO, MAT_HYPERELASTIC = 0, 1, 2, 3, 4
+DEV_NONE, DEV_BLATZKO, DEV_OGDEN_TOTAL, DEV_OGDEN_DEVIATORIC, DEV_INVARIANT_BASED, DEV_ARRUDA_BOYCE, DEV_GENT = range(7)
 DBC_RAW, DBC_REDUCED, DBC_FULL = 0, 1, 2
 SCALAR, VECTOR, MATRIX = 1, 2, 4
 
@@ -20,6 +21,13 @@ class Desc(C.Structure):
                 ("material", C.c_int32), ("plane_strain", C.c_int32), ("eas_m", C.c_int32), ("device", C.c_int32),
                 ("lam", C.c_double), ("mu", C.c_double), ("n_elem", C.c_int64), ("n_dof", C.c_int64),
                 ("reduce_tol", C.c_double), ("eas_function", C.c_int32), ("reserved_", C.c_int32)]
+
+
+class Hyperelastic(C.Structure):
+    """ikb_hyperelastic: a law of the principal-stretch framework (hyperelastic/factory.hh)."""
+    _fields_ = [("deviatoric", C.c_int32), ("n", C.c_int32), ("volumetric", C.c_int32), ("reserved_", C.c_int32),
+                ("pex", C.c_int32 * 3), ("qex", C.c_int32 * 3), ("par", C.c_double * 3), ("ex", C.c_double * 3),
+                ("K", C.c_double), ("beta", C.c_double)]
 
 
 class TcgInfo(C.Structure):
@@ -56,6 +64,7 @@ SYMBOLS = {
     "ikb_get_matrix_values": [C.c_void_p, C.c_int, C.c_void_p],
     "ikb_get_dense_matrix": [C.c_void_p, C.c_int, C.c_void_p],
     "ikb_vector_norm": [C.c_void_p, C.c_int, C.POINTER(C.c_double)],
+    "ikb_set_hyperelastic": [C.c_void_p, C.POINTER(Hyperelastic)],
     "ikb_eas_update": [C.c_void_p, C.c_void_p],
     "ikb_eas_get_alpha": [C.c_void_p, C.c_void_p],
     "ikb_eas_set_alpha": [C.c_void_p, C.c_void_p],

@@ -154,6 +154,11 @@ class _FlatAssemblerBase:
                                             "(displacement-gradient forms: nonlinear element, m = 4 / 9)")
         if rc != 0:
             raise ValueError(f"ikb_create failed with code {rc}")
+        if mat.hyper is not None:
+            dev, n, vfi, pex, qex, par, ex, K, beta = mat.hyper
+            law = capi.Hyperelastic(dev, n, vfi, 0, (C.c_int32 * 3)(*pex), (C.c_int32 * 3)(*qex), (C.c_double * 3)(*par),
+                                    (C.c_double * 3)(*ex), K, beta)
+            self._check(self._lib.ikb_set_hyperelastic(self._h, C.byref(law)))
         self._check(self._lib.ikb_upload_mesh(self._h, capi.ptr(fes.corner_coords), capi.ptr(fes.elem_dofs)))
         self._flags_u8 = np.ascontiguousarray(flags, dtype=np.uint8)
         self._check(self._lib.ikb_upload_dirichlet(self._h, capi.ptr(self._flags_u8)))

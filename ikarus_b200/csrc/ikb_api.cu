@@ -163,6 +163,7 @@ int launchElements(Handle* h, unsigned what, const double* dU = nullptr, const d
     if (Uoverride) EA.E.U = Uoverride;
     EA.dU = dU;
     EA.updateMode = dU ? 1 : 0;
+    EA.ps = h->ps;
     e = launchEas(h, EA);
   } else if (h->order == 2 && h->easM == 0) {
     if (h->dim == 3) {
@@ -1083,7 +1084,8 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
     form = FORM_SVK;
   else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_NEOHOOKE)
     form = FORM_NH;
-  else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE && desc->material == IKB_MAT_BLATZKO)
+  else if (desc->strain == IKB_STRAIN_GREEN_LAGRANGE &&
+           (desc->material == IKB_MAT_BLATZKO || desc->material == IKB_MAT_HYPERELASTIC))
     form = FORM_PS;
   else
     return IKB_EINVAL;  // the reference statically rejects these strain/material pairings too
@@ -1118,6 +1120,11 @@ int ikb_create(ikb_handle* out, const ikb_desc* desc) {
   h->nc = 1 << h->dim;
   h->npair = h->nn * (h->nn + 1) / 2;
   h->form = form;
+  if (desc->material == IKB_MAT_BLATZKO) {
+    h->ps.dev = IKB_DEV_BLATZKO;
+    h->ps.par[0] = desc->mu;
+    h->psSet = true;
+  }
   h->easM = m;
   h->easFunction = m ? desc->eas_function : IKB_EAS_STRAIN;
   h->nElem = desc->n_elem;
@@ -1790,6 +1797,7 @@ int ikb_assemble(ikb_handle hh, unsigned what, int dbc) {
   if (!dbcValid(dbc) || (what & ~7u) || what == 0) return fail(h, IKB_EINVAL, "bad affordance/dbc");
   if (!h->meshUploaded || !h->patternBuilt) return fail(h, IKB_ESTATE, "mesh/pattern missing");
   if (dbc != IKB_DBC_RAW && !h->hasFlags) return fail(h, IKB_ESTATE, "Dirichlet flags missing");
+  if (h->form == FORM_PS && !h->psSet) return fail(h, IKB_ESTATE, "ikb_set_hyperelastic has not been called");
   if ((what & IKB_SCALAR) && h->easM)
     return fail(h, IKB_ENOTIMPL,
                 "EAS element do not support any scalar calculations, i.e. they are not derivable from a potential");
@@ -2053,6 +2061,7 @@ int ikb_calculate_at(ikb_handle hh, int resultType, const double* local, int nPo
   A.layout = h->layout;
   A.npts = nPoints;
   A.form = h->form;
+  A.ps = h->ps;
   A.planeStrain = h->desc.plane_strain;
   A.easM = h->easM;
   A.easFunction = h->easFunction;
@@ -2084,6 +2093,44 @@ int ikb_eas_get_alpha(ikb_handle hh, double* alpha) {
   IKB_CUDA(h, cudaStreamSynchronize(h->stream));
   return IKB_OK;
 }
+int ikb_set_hyperelastic(ikb_handle hh, const ikb_hyperelastic* law) {
+  Handle* h = H(hh);
+  if (checkHandle(h) || !law) return IKB_EINVAL;
+  if (h->form != FORM_PS || h->desc.material != IKB_MAT_HYPERELASTIC)
+    return fail(h, IKB_EINVAL, "the handle was not created with IKB_MAT_HYPERELASTIC");
+  if (law->deviatoric < IKB_DEV_NONE || law->deviatoric > IKB_DEV_GENT || law->volumetric < 0 || law->volumetric > 12)
+    return fail(h, IKB_EINVAL, "unknown deviatoric or volumetric function");
+  const bool terms = law->deviatoric == IKB_DEV_OGDEN_TOTAL || law->deviatoric == IKB_DEV_OGDEN_DEVIATORIC ||
+                     law->deviatoric == IKB_DEV_INVARIANT_BASED;
+  if (terms && (law->n < 1 || law->n > 3)) return fail(h, IKB_ENOTIMPL, "1 to 3 terms are served");
+  if (law->deviatoric == IKB_DEV_NONE && law->volumetric == 0) return fail(h, IKB_EINVAL, "a law without any part");
+  PsLaw ps;
+  ps.dev = law->deviatoric;
+  ps.n = terms ? law->n : 0;
+  ps.vf = law->volumetric;
+  for (int i = 0; i < 3; ++i) {
+    ps.par[i] = law->par[i];
+    ps.ex[i] = law->ex[i];
+    ps.pex[i] = law->pex[i];
+    ps.qex[i] = law->qex[i];
+    if (law->deviatoric == IKB_DEV_INVARIANT_BASED && i < law->n) {
+      // InvariantBasedT::checkExponents (invariantbased.hh:216-221); exponents are std::size_t there
+      if (law->pex[i] < 0 || law->qex[i] < 0 || (law->pex[i] == 0 && law->qex[i] == 0))
+        return fail(h, IKB_EINVAL, "the exponents p_i and q_i should not be zero at the same time");
+    }
+    if ((law->deviatoric == IKB_DEV_OGDEN_TOTAL || law->deviatoric == IKB_DEV_OGDEN_DEVIATORIC) && i < law->n &&
+        law->ex[i] == 0.0)
+      return fail(h, IKB_EINVAL, "an Ogden exponent is zero");
+  }
+  ps.K = law->K;
+  ps.beta = law->beta;
+  if ((ps.vf == 4 || ps.vf == 7 || ps.vf == 10) && ps.beta == 0.0) return fail(h, IKB_EINVAL, "this volumetric function needs beta");
+  h->ps = ps;
+  h->psSet = true;
+  h->stateVersion++;
+  return IKB_OK;
+}
+
 int ikb_eas_set_alpha(ikb_handle hh, const double* alpha) {
   Handle* h = H(hh);
   if (checkHandle(h)) return IKB_EINVAL;

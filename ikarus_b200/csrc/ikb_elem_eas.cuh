@@ -28,6 +28,7 @@ struct EasArgs {
   double* alpha;        // [nElem][M]
   const double* dU;     // correction (update mode), indexed like U
   int updateMode;       // 0: K/R   1: alpha -= D^-1 (Rt + L du)
+  PsLaw ps;             // FORM_PS (generalised-tangent kernel): the principal-stretch law
 };
 
 // ansatz tables: row r_j and monomial id per column.  3D monomials: 0 tx, 1 ty, 2 tz, 3 txty, 4 txtz, 5 tytz;

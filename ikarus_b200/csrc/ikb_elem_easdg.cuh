@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
     [[maybe_unused]] double Np[3][3], L1[3][3], L2[3][3];  // principal frame and moduli of the principal-stretch laws
     if constexpr (FORM == FORM_PS) {
       double Sp[3], psi;
-      if (!principalLaw<D>(A.mu, Cm, Np, Sp, L1, L2, psi) && lane == 0)
+      if (!principalLaw<D>(EA.ps, Cm, Np, Sp, L1, L2, psi) && lane == 0)
         atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
       principalStress<D>(Np, Sp, Sm);
 #pragma unroll

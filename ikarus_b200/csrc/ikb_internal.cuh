@@ -15,6 +15,18 @@ namespace ikb {
 enum Form { FORM_LE = 0, FORM_SVK = 1, FORM_NH = 2, FORM_PS = 3 };
 enum Layout { LAYOUT_INTERLEAVED = 0, LAYOUT_LEXICOGRAPHIC = 1 };
 
+// The law, as ikb_set_hyperelastic receives it (include/ikb200.h: ikb_hyperelastic)
+struct PsLaw {
+  int dev = 1;  // IKB_DEV_*: 0 none, 1 BlatzKo, 2 Ogden (total stretches), 3 Ogden (deviatoric), 4 InvariantBased, 5 ArrudaBoyce, 6 Gent
+  int n = 0;    // terms of Ogden / InvariantBased (<= 3)
+  int vf = 0;   // VF0 .. VF12
+  int pex[3] = {0, 0, 0}, qex[3] = {0, 0, 0};
+  double par[3] = {0, 0, 0};  // Ogden: mu_i; InvariantBased: c_i; BlatzKo: mu; ArrudaBoyce: mu, lambdaM; Gent: mu, Jm
+  double ex[3] = {0, 0, 0};   // Ogden: alpha_i
+  double K = 0.0, beta = 0.0; // penalty parameter and beta (VF4, VF7, VF10) of the volumetric function
+};
+
+
 constexpr uint32_t SRC_TRANSPOSE = 0x80000000u;
 constexpr uint32_t SRC_MASK = 0x7fffffffu;
 // doubles per staged K_e block
@@ -70,6 +82,8 @@ struct Handle {
   ikb_desc desc{};
   int dim = 0, order = 0, nn = 0, nd = 0, nc = 0, npair = 0, form = 0, easM = 0;
   int easFunction = 0;  // IKB_EAS_*
+  PsLaw ps;             // FORM_PS: the principal-stretch law
+  bool psSet = false;
   int layout = 0;
   int64_t nElem = 0, nDof = 0, nNodes = 0;
   int device = 0;

@@ -26,6 +26,7 @@ struct ResultArgs {
   int layout, npts, form, planeStrain, easM, resultType, ncomp;
   int easFunction = 0;  // IKB_EAS_*
   double lambda, mu, psTol;
+  PsLaw ps;  // FORM_PS
 };
 
 template <int D>
@@ -48,12 +49,13 @@ __device__ __forceinline__ void easColumn(int m, int j, int& row, int& mono) {
 }
 
 // 3D law on the full Voigt strain E6 (shear entries doubled): S6.  Returns false for det C <= 0 (NeoHooke).
-__device__ __forceinline__ bool stress3d(int form, double lambda, double mu, const double (&E6)[6], double (&S6)[6]) {
+__device__ __forceinline__ bool stress3d(int form, double lambda, double mu, const PsLaw& ps, const double (&E6)[6],
+                                         double (&S6)[6]) {
   if (form == FORM_PS) {  // principal-stretch laws (hyperelastic/interface.hh:124-141), ikb_material_ps.cuh
     double Cm[3][3], Np[3][3], Sp[3], L1[3][3], L2[3][3], psi, Sm[3][3];
     Cm[0][0] = 2.0 * E6[0] + 1.0, Cm[1][1] = 2.0 * E6[1] + 1.0, Cm[2][2] = 2.0 * E6[2] + 1.0;
     Cm[1][2] = Cm[2][1] = E6[3], Cm[0][2] = Cm[2][0] = E6[4], Cm[0][1] = Cm[1][0] = E6[5];
-    if (!principalLaw<3>(mu, Cm, Np, Sp, L1, L2, psi)) return false;
+    if (!principalLaw<3>(ps, Cm, Np, Sp, L1, L2, psi)) return false;
     principalStress<3>(Np, Sp, Sm);
     S6[0] = Sm[0][0], S6[1] = Sm[1][1], S6[2] = Sm[2][2], S6[3] = Sm[1][2], S6[4] = Sm[0][2], S6[5] = Sm[0][1];
     return true;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(128) result_at_kernel(ResultArgs A) {
       }
     }
   }
-  if (!(ok && stress3d(A.form, A.lambda, A.mu, E6, S6))) {
+  if (!(ok && stress3d(A.form, A.lambda, A.mu, A.ps, E6, S6))) {
     atomicMin(A.errFlag, (int32_t)(e < 0x7fffffff ? e : 0x7ffffffe));
     for (int p = 0; p < 6; ++p) S6[p] = 0.0;
   }

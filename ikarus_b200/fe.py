@@ -35,6 +35,7 @@ class _Material:
     params: LamesFirstParameterAndShearModulus
     reduced: int = 0  # 0: 3D law, 1: planeStrain wrapper, 2: planeStress wrapper (capi IKB_REDUCE_*)
     reduce_tol: float = 1e-12
+    hyper: tuple = None  # MAT_HYPERELASTIC: (deviatoric, n, volumetric, pex, qex, par, ex, K, beta) of ikb_hyperelastic
 
     def materialParameters(self):
         return self.params
@@ -64,15 +65,83 @@ class Materials:
                          capi.STRAIN_GL, LamesFirstParameterAndShearModulus(0.0, float(mu)))
 
 
+class VF:
+    """A volumetric function VF0 .. VF12 (materials/hyperelastic/volumetric/volumetricfunctions.hh); beta for VF4/7/10."""
+
+    def __init__(self, index: int, beta: float = 0.0):
+        self.index, self.beta = int(index), float(beta)
+
+
+def _pad3(v, cast=float):
+    v = [cast(x) for x in v]
+    if not 1 <= len(v) <= 3:
+        raise NotImplementedError("1 to 3 terms are served on the device")
+    return tuple(v + [cast(0)] * (3 - len(v)))
+
+
+def _hyper(name, dev, n=0, par=(), ex=(), pex=(), qex=(), K=0.0, vf=None):
+    vf = vf or VF(0)
+    law = (dev, int(n), vf.index, _pad3(pex or [0], int), _pad3(qex or [0], int), _pad3(par or [0.0]), _pad3(ex or [0.0]),
+           float(K), vf.beta)
+    return _Material(name, capi.MAT_HYPERELASTIC, capi.STRAIN_GL, LamesFirstParameterAndShearModulus(0.0, 0.0), hyper=law)
+
+
+def makeOgden(mu, alpha, K=0.0, vf=None, tag="total"):
+    """Materials::makeOgden<n, tag>(mu, alpha, K, vf) (hyperelastic/factory.hh:17-41, deviatoric/ogden.hh);
+    tag = 'total' | 'deviatoric' (PrincipalStretchTags)."""
+    if len(mu) != len(alpha):
+        raise ValueError("as many exponents as parameters")
+    dev = capi.DEV_OGDEN_TOTAL if tag == "total" else capi.DEV_OGDEN_DEVIATORIC
+    return _hyper(f"Hyperelastic (Ogden n = {len(mu)}, {tag})", dev, len(mu), par=mu, ex=alpha, K=K, vf=vf)
+
+
+def makeInvariantBased(mu, pex, qex, K=0.0, vf=None):
+    """Materials::makeInvariantBased<n>(mu, pex, qex, K, vf) (factory.hh:43-67, deviatoric/invariantbased.hh)."""
+    if any(int(p) == 0 and int(q) == 0 for p, q in zip(pex, qex)):
+        raise ValueError("the exponents p_i and q_i should not be zero at the same time")  # invariantbased.hh:216-221
+    return _hyper(f"Hyperelastic (InvariantBased n = {len(mu)})", capi.DEV_INVARIANT_BASED, len(mu), par=mu, pex=pex,
+                  qex=qex, K=K, vf=vf)
+
+
+def makeMooneyRivlin(mu, K=0.0, vf=None):
+    """Materials::makeMooneyRivlin (factory.hh:69-88): InvariantBased<2> with p = (1, 0), q = (0, 1)."""
+    return makeInvariantBased(mu, (1, 0), (0, 1), K, vf)
+
+
+def makeYeoh(mu, K=0.0, vf=None):
+    """Materials::makeYeoh (factory.hh:90-109): InvariantBased<3> with p = (1, 2, 3), q = 0."""
+    return makeInvariantBased(mu, (1, 2, 3), (0, 0, 0), K, vf)
+
+
+def makeArrudaBoyce(mu, lambdaM, K=0.0, vf=None):
+    """Materials::makeArrudaBoyce({mu, lambdaM}, K, vf) (factory.hh:111-131, deviatoric/arrudaboyce.hh)."""
+    return _hyper("Hyperelastic (ArrudaBoyce)", capi.DEV_ARRUDA_BOYCE, par=(mu, lambdaM), K=K, vf=vf)
+
+
+def makeGent(mu, Jm, K=0.0, vf=None):
+    """Materials::makeGent({mu, Jm}, K, vf) (factory.hh:133-153, deviatoric/gent.hh)."""
+    return _hyper("Hyperelastic (Gent)", capi.DEV_GENT, par=(mu, Jm), K=K, vf=vf)
+
+
+def makePureVolumetric(vf, K):
+    """Materials::makePureVolumetric(vf, K) (factory.hh:155-165)."""
+    return _hyper("Hyperelastic (pure volumetric)", capi.DEV_NONE, K=K, vf=vf)
+
+
+for _f in (makeOgden, makeInvariantBased, makeMooneyRivlin, makeYeoh, makeArrudaBoyce, makeGent, makePureVolumetric):
+    setattr(Materials, _f.__name__, staticmethod(_f))
+Materials.VF = VF
+
+
 def planeStrain(mat: _Material) -> _Material:
     """Materials::planeStrain (mechanics/materials/vanishingstrain.hh:147-198)."""
-    return _Material(mat.name, mat.code, mat.strain, mat.params, 1)
+    return _Material(mat.name, mat.code, mat.strain, mat.params, 1, hyper=mat.hyper)
 
 
 def planeStress(mat: _Material, tol: float = 1e-12) -> _Material:
     """Materials::planeStress(mat, tol) = VanishingStress with S33 = S23 = S13 = 0
     (mechanics/materials/vanishingstress.hh:35-230, 252-260)."""
-    return _Material(mat.name, mat.code, mat.strain, mat.params, 2, float(tol))
+    return _Material(mat.name, mat.code, mat.strain, mat.params, 2, float(tol), hyper=mat.hyper)
 
 
 # ------------------------------------------------------------------------------------- skills

@@ -48,7 +48,13 @@ enum { IKB_STRAIN_LINEAR = 0, IKB_STRAIN_GREEN_LAGRANGE = 1 };
  * principal-stretch framework (hyperelastic/interface.hh:99-232, deviatoric/interface.hh:77-115,
  * deviatoric/blatzko.hh:60-92, factory.hh:34-39): ikb_desc.mu is its parameter, lambda is ignored; Q1 elements
  * (plain and every EAS form), 3D or planeStrain */
-enum { IKB_MAT_LINEAR_ELASTICITY = 0, IKB_MAT_SVK = 1, IKB_MAT_NEOHOOKE = 2, IKB_MAT_BLATZKO = 3 };
+enum { IKB_MAT_LINEAR_ELASTICITY = 0, IKB_MAT_SVK = 1, IKB_MAT_NEOHOOKE = 2, IKB_MAT_BLATZKO = 3, IKB_MAT_HYPERELASTIC = 4 };
+/* IKB_MAT_HYPERELASTIC: any Materials::Hyperelastic<Deviatoric<DF>, Volumetric<VF>> of the factories in
+ * hyperelastic/factory.hh:12-165, described by ikb_set_hyperelastic below (required before the first assembly) */
+/* deviatoric functions: nodeviatoricfunction.hh, blatzko.hh, ogden.hh (PrincipalStretchTags::total | deviatoric),
+ * invariantbased.hh (makeMooneyRivlin, makeYeoh, makeInvariantBased), arrudaboyce.hh, gent.hh */
+enum { IKB_DEV_NONE = 0, IKB_DEV_BLATZKO = 1, IKB_DEV_OGDEN_TOTAL = 2, IKB_DEV_OGDEN_DEVIATORIC = 3,
+       IKB_DEV_INVARIANT_BASED = 4, IKB_DEV_ARRUDA_BOYCE = 5, IKB_DEV_GENT = 6 };
 /* DBCOption (assembler/dirichletbcenforcement.hh) */
 enum { IKB_DBC_RAW = 0, IKB_DBC_REDUCED = 1, IKB_DBC_FULL = 2 };
 /* affordance bits: ScalarAffordance::mechanicalPotentialEnergy, VectorAffordance::forces,
@@ -142,6 +148,23 @@ int ikb_get_dense_matrix(ikb_handle h, int dbc, double* out);
 /* 2-norm of the assembled vector (NewtonRaphson needs ||rx|| on the host,
  * solver/nonlinearsolver/newtonraphson.hh:206) */
 int ikb_vector_norm(ikb_handle h, int dbc, double* norm);
+
+/* ---- principal-stretch hyperelastic laws ---------------------------------------- */
+typedef struct ikb_hyperelastic {
+  int32_t deviatoric;  /* IKB_DEV_* */
+  int32_t n;           /* terms of Ogden<n, tag> / InvariantBased<n>, 1..3 (the reference's own tests use up to 3) */
+  int32_t volumetric;  /* 0..12: VF0 (none) .. VF12 (volumetric/volumetricfunctions.hh:25-380) */
+  int32_t reserved_;
+  int32_t pex[3], qex[3]; /* InvariantBased exponents of (W1 - 3), (W2 - 3); not both zero (invariantbased.hh:216-221) */
+  double par[3];       /* Ogden: mu_i; InvariantBased: material parameters; BlatzKo: {mu}; ArrudaBoyce: {mu, lambdaM};
+                          Gent: {mu, Jm} */
+  double ex[3];        /* Ogden: alpha_i */
+  double K;            /* Volumetric(matPar, vf): Lame's first parameter for total, the bulk modulus for deviatoric
+                          stretches (volumetric/interface.hh:40-52) */
+  double beta;         /* VF4, VF7, VF10 */
+} ikb_hyperelastic;
+/* replaces the Hyperelastic ctor (hyperelastic/interface.hh:74-82) for a handle created with IKB_MAT_HYPERELASTIC */
+int ikb_set_hyperelastic(ikb_handle h, const ikb_hyperelastic* law);
 
 /* ---- EAS internal variables ----------------------------------------------------- */
 /* EnhancedAssumedStrains::updateStateImpl on CORRECTION_UPDATED

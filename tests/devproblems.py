@@ -7,9 +7,30 @@ import ikarus_oracle as o
 _MAT = {"linear": ik.Materials.LinearElasticity, "svk": ik.Materials.StVenantKirchhoff, "neohooke": ik.Materials.NeoHooke}
 
 
+def _device_hyper(h):
+    """oracle Hyper -> the factory call of the Python mirror (hyperelastic/factory.hh)."""
+    M = ik.Materials
+    vf = M.VF(h.vf, h.beta)
+    d, p = h.dev, h.params
+    if d == "blatzko":
+        return M.makeBlatzKo(p[0])
+    if d in ("ogden_total", "ogden_dev"):
+        return M.makeOgden(p[0], p[1], h.K, vf, "total" if d == "ogden_total" else "deviatoric")
+    if d == "invariant":
+        return M.makeInvariantBased(p[2], p[0], p[1], h.K, vf)
+    if d == "arrudaboyce":
+        return M.makeArrudaBoyce(p[0], p[1], h.K, vf)
+    if d == "gent":
+        return M.makeGent(p[0], p[1], h.K, vf)
+    return M.makePureVolumetric(vf, h.K)
+
+
 def device_assembler(mesh, kind, mat, flags, layout="interleaved", fext=None, dense=False, mode="mirror", volume=None):
     p = ik.fe.LamesFirstParameterAndShearModulus(mat.lam, mat.mu)
-    m = ik.Materials.makeBlatzKo(mat.mu) if mat.kind == "blatzko" else _MAT[mat.kind](p)
+    if mat.kind == "hyperelastic":
+        m = _device_hyper(mat.hyper)
+    else:
+        m = ik.Materials.makeBlatzKo(mat.mu) if mat.kind == "blatzko" else _MAT[mat.kind](p)
     if mat.plane_strain:
         m = ik.planeStrain(m)
     if getattr(mat, "plane_stress", False):

@@ -150,3 +150,102 @@ def test_blatzko_descriptor_rules():
     with pytest.raises(NotImplementedError):
         device_assembler(mesh, o.ElementKind(2, 1, "gl"), o.Material("blatzko", lam, mu, plane_stress=True),
                          np.zeros(mesh.n_nodes * 2, dtype=bool))
+
+
+# ------------------------------------------------------------------ every law of the framework (IKB_MAT_HYPERELASTIC)
+_MU = 1000.0 / (2.0 * 1.25)  # the parameters of tests/src/testhyperelasticity.hh:231-249 (E = 1000, nu = 0.25)
+_LAME = 1000.0 * 0.25 / (1.25 * 0.5)
+_BULK = 1000.0 / (3.0 * 0.5)
+_OG = ((2.0 * _MU / 3.0, _MU / 6.0, _MU / 6.0), (1.23, 0.59, 0.18))
+LAWS = {
+    "ogden_total+VF3": o.Hyper("ogden_total", _OG, vf=3, K=_LAME),
+    "ogden_dev+VF2": o.Hyper("ogden_dev", _OG, vf=2, K=_BULK),
+    "mooney_rivlin+VF1": o.Hyper("invariant", ((1, 0), (0, 1), (_MU / 2.0, _MU / 2.0)), vf=1, K=_BULK),
+    "yeoh+VF5": o.Hyper("invariant", ((1, 2, 3), (0, 0, 0), (_MU / 2.0, _MU / 6.0, _MU / 3.0)), vf=5, K=_BULK),
+    "arruda_boyce+VF6": o.Hyper("arrudaboyce", (_MU, 0.85), vf=6, K=_BULK),
+    "gent+VF8": o.Hyper("gent", (_MU, 2.5), vf=8, K=_BULK),
+    "ogden1_dev+VF4": o.Hyper("ogden_dev", ((_MU,), (2.0,)), vf=4, K=_BULK, beta=0.5),
+    "mooney_rivlin+VF7": o.Hyper("invariant", ((1, 0), (0, 1), (_MU / 2.0, _MU / 2.0)), vf=7, K=_BULK, beta=0.5),
+    "yeoh+VF9": o.Hyper("invariant", ((1, 2, 3), (0, 0, 0), (_MU / 2.0, _MU / 6.0, _MU / 3.0)), vf=9, K=_BULK),
+    "gent+VF10": o.Hyper("gent", (_MU, 2.5), vf=10, K=_BULK, beta=0.4),
+    "arruda_boyce+VF11": o.Hyper("arrudaboyce", (_MU, 0.85), vf=11, K=_BULK),
+    "ogden_total_no_volumetric": o.Hyper("ogden_total", _OG),
+    # the law of the reference's incompressible block (tests/src/testincompressibleblock.cpp:60); VF12 alone has a tangent
+    # whose rows cancel to rounding noise, so it is paired with a deviatoric part here
+    "ogden1_dev+VF12": o.Hyper("ogden_dev", ((_MU,), (2.0,)), vf=12, K=_BULK),
+    "pure_volumetric_VF3": o.Hyper("none", (), vf=3, K=_BULK),
+}
+
+
+@pytest.mark.parametrize("dim,m,fn", [(3, 0, "strain"), (2, 0, "strain"), (3, 9, "strain"), (2, 4, "dgt")], ids=lambda v: str(v))
+@pytest.mark.parametrize("law", sorted(LAWS))
+def test_every_hyperelastic_law_matches_the_oracle(law, dim, m, fn):
+    """Hyperelastic<Deviatoric<DF>, Volumetric<VF>> for every deviatoric function and VF1..VF12 through
+    ikb_set_hyperelastic: K, R (and the energy of the plain element) and the PK2 stress against the oracle, whose laws
+    reproduce the reference's material result tables (tests/test_hyperelastic_oracle.py)."""
+    if law.startswith("pure_volumetric") and m:
+        pytest.skip("a purely volumetric law leaves the enhanced block singular")
+    mesh, kind, _, flags, d, alpha, rng = _setup(dim, m, fn)
+    mat = o.Material("hyperelastic", 0.0, 0.0, plane_strain=(dim == 2), hyper=LAWS[law])
+    ref = o.FlatAssembler(mesh, kind, mat, flags)
+    dev = device_assembler(mesh, kind, mat, flags)
+    if m:
+        ref.alpha = alpha.copy()
+        dev.setInternalVariables(alpha)
+    req = ik.FERequirements(d, 0.0)
+    for mode, dbc in (("raw", ik.DBCOption.Raw), ("reduced", ik.DBCOption.Reduced)):
+        K = dev.matrix(req, ik.MatrixAffordance.stiffness, dbc)
+        outer, _ = ref.pattern(mode)
+        rows = np.repeat(np.arange(outer.shape[0] - 1), np.diff(outer))
+        Kref = ref.matrix_values(d, 0.0, mode)
+        assert entry_error(K.data, Kref, rows) <= TOL_8D, mode
+        assert _row_scaled_error(K.data, Kref, rows) <= TOL, mode
+        R = dev.vector(req, ik.VectorAffordance.forces, dbc)
+        Rr = ref.vector(d, 0.0, mode)
+        assert np.abs(R - Rr).max() <= TOL_8D * np.abs(Rr).max(), mode
+    if m == 0:
+        E = dev.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+        Er = ref.scalar(d, 0.0)
+        assert abs(E - Er) <= 1e-11 * abs(Er)
+    u = d[mesh.elem_dofs("interleaved")].reshape(mesh.n_elem, -1, dim)
+    xi = np.full(dim, 0.3)
+    S = dev.calculateAt(RT.PK2Stress, req, xi[None])
+    r = o.stress_at(kind, mat, mesh.corner_coords, u, xi, alpha=alpha if m else None, result="native")
+    assert np.abs(S[:, 0] - r).max() <= 1e-11 * np.abs(r).max()
+
+
+def test_neohooke_recovery_on_the_device():
+    """tests/src/testhyperelasticity.hh:139-196 through the assembler: Ogden<1, total>({mu}, {2}) with VF3 and Lame's
+    first parameter IS the NeoHooke material -- the generalised-tangent kernel with the principal-stretch law against
+    the factored NeoHooke kernels (tensor-core Hex8 kernel included), two independent device formulations."""
+    for dim in (3, 2):
+        mesh, kind, _, flags, d, _, _ = _setup(dim, 0, "strain")
+        nh = device_assembler(mesh, kind, o.Material("neohooke", _LAME, _MU, plane_strain=(dim == 2)), flags)
+        og = device_assembler(mesh, kind, o.Material("hyperelastic", 0.0, 0.0, plane_strain=(dim == 2),
+                                                     hyper=o.Hyper("ogden_total", ((_MU,), (2.0,)), vf=3, K=_LAME)), flags)
+        req = ik.FERequirements(d, 0.0)
+        Ka = nh.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Full)
+        Kb = og.matrix(req, ik.MatrixAffordance.stiffness, ik.DBCOption.Full)
+        rows = np.repeat(np.arange(Ka.indptr.shape[0] - 1), np.diff(Ka.indptr))
+        assert entry_error(Kb.data, Ka.data, rows) <= TOL_8D
+        Ra = nh.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Full)
+        Rb = og.vector(req, ik.VectorAffordance.forces, ik.DBCOption.Full)
+        assert np.abs(Ra - Rb).max() <= TOL_8D * np.abs(Ra).max()
+        Ea = nh.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+        Eb = og.scalar(req, ik.ScalarAffordance.mechanicalPotentialEnergy)
+        assert abs(Ea - Eb) <= 1e-11 * abs(Ea)
+
+
+def test_hyperelastic_descriptor_rules():
+    mesh = o.structured_mesh((2, 2, 2), (1.0, 1.0, 1.0))
+    flags = np.zeros(mesh.n_nodes * 3, dtype=bool)
+    with pytest.raises(ValueError):  # InvariantBasedT::checkExponents (invariantbased.hh:216-221)
+        ik.Materials.makeInvariantBased((500.0, 500.0), (0, 0), (0, 1))
+    with pytest.raises(NotImplementedError):  # more than three terms
+        ik.Materials.makeOgden((1.0,) * 4, (2.0,) * 4)
+    # Gent beyond its limiting stretch: Jm <= W1 - 3 throws in the reference (gent.hh:176-180)
+    mat = o.Material("hyperelastic", 0.0, 0.0, hyper=o.Hyper("gent", (_MU, 1e-3)))
+    dev = device_assembler(mesh, o.ElementKind(3, 1, "gl"), mat, flags)
+    d = 0.2 * np.random.default_rng(0).uniform(-1, 1, flags.shape[0])
+    with pytest.raises(Exception):
+        dev.matrix(ik.FERequirements(d, 0.0), ik.MatrixAffordance.stiffness, ik.DBCOption.Raw)
