@@ -97,6 +97,13 @@ struct ElementAccess
   static double reductionTolerance(const FE& fe) { return fe.reduceTol; }
   static double lambda(const FE& fe) { return fe.lambda; }
   static double mu(const FE& fe) { return fe.mu; }
+  /** IKB_MAT_HYPERELASTIC: the law of the principal-stretch framework; false for the other materials */
+  static bool hyperelastic(const FE& fe, ikb_hyperelastic& law) {
+    if (fe.material != IKB_MAT_HYPERELASTIC)
+      return false;
+    law = fe.hyperelastic;
+    return true;
+  }
   static int numberOfInternalVariables(const FE& fe) { return fe.easM; }
   /** IKB_EAS_*: the ES of eas<ES>(m) (mechanics/enhancedassumedstrains.hh:69) */
   static int easFunction(const FE& fe) { return fe.easFunction; }
@@ -138,6 +145,73 @@ requires(!Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::
 struct MaterialCode<Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::Materials::BlatzKoT<ST>>, VOL>>
 {
   static constexpr int material = IKB_MAT_BLATZKO, reduction = IKB_REDUCE_NONE;
+};
+/** Any other Hyperelastic<Deviatoric<DF>, Volumetric<VF>> (hyperelastic/interface.hh:33-97) goes through
+ *  ikb_set_hyperelastic; HyperelasticLaw below reads what the reference's public accessors expose. */
+template <typename DEV, typename VOL>
+struct MaterialCode<Ikarus::Materials::Hyperelastic<DEV, VOL>>
+{
+  static constexpr int material = IKB_MAT_HYPERELASTIC, reduction = IKB_REDUCE_NONE;
+};
+/** VF0 .. VF12 -> index (volumetric/volumetricfunctions.hh:25-380); beta() of VF4 / VF7 / VF10 */
+template <typename VF>
+struct VolumetricIndex
+{
+  static constexpr int value = -1;
+};
+  #define IKB_VF(N)                                   \
+    template <>                                       \
+    struct VolumetricIndex<Ikarus::Materials::VF##N>  \
+    {                                                 \
+      static constexpr int value = N;                 \
+    };
+IKB_VF(0) IKB_VF(1) IKB_VF(2) IKB_VF(3) IKB_VF(4) IKB_VF(5) IKB_VF(6) IKB_VF(7) IKB_VF(8) IKB_VF(9) IKB_VF(10) IKB_VF(11) IKB_VF(12)
+  #undef IKB_VF
+/** Fills ikb_hyperelastic from a material object.  Deviatoric<DF> exposes only DF::materialParametersImpl()
+ *  (deviatoric/interface.hh:66): enough for BlatzKo {mu}, ArrudaBoyce {mu, lambdaM} and Gent {mu, Jm}.  The exponents of
+ *  Ogden and InvariantBased are not reachable through the reference's public interface -- specialise
+ *  ElementAccess<FE>::hyperelastic for those (the factories' arguments are at hand where the material is built). */
+template <typename M>
+struct HyperelasticLaw
+{
+  static bool fill(const M&, ikb_hyperelastic&) { return false; }
+};
+template <typename DEV, typename VOL>
+struct HyperelasticLaw<Ikarus::Materials::Hyperelastic<DEV, VOL>>
+{
+  using Mat = Ikarus::Materials::Hyperelastic<DEV, VOL>;
+  using DF  = typename DEV::DeviatoricFunction;
+  static bool fill(const Mat& mat, ikb_hyperelastic& law) {
+    law = ikb_hyperelastic{};
+    const auto p = mat.deviatoricFunction().materialParameters();
+    if constexpr (requires { p.lambdaM; }) {
+      law.deviatoric = IKB_DEV_ARRUDA_BOYCE, law.par[0] = p.mu, law.par[1] = p.lambdaM;
+    } else if constexpr (requires { p.Jm; }) {
+      law.deviatoric = IKB_DEV_GENT, law.par[0] = p.mu, law.par[1] = p.Jm;
+    } else if constexpr (std::is_arithmetic_v<std::remove_cvref_t<decltype(p)>>) {
+      law.deviatoric = IKB_DEV_BLATZKO, law.par[0] = static_cast<double>(p);
+    } else {
+      IKB_THROW(NotImplemented, "material " + Mat::name() +
+                                    ": exponents are not exposed by Deviatoric<DF>; specialise "
+                                    "Ikarus::B200::ElementAccess<FE>::hyperelastic to pass the law");
+    }
+    if constexpr (Mat::hasVolumetricPart) {
+      using VF = typename VOL::VolumetricFunction;
+      static_assert(VolumetricIndex<VF>::value >= 0, "unknown volumetric function");
+      law.volumetric = VolumetricIndex<VF>::value;
+      law.K          = mat.volumetricFunction().materialParameter();
+      if constexpr (requires { mat.volumetricFunction().volumetricFunction().beta(); })
+        law.beta = mat.volumetricFunction().volumetricFunction().beta();
+    }
+    return true;
+  }
+};
+template <auto pairs, typename MI>
+struct HyperelasticLaw<Ikarus::Materials::VanishingStrain<pairs, MI>>
+{
+  static bool fill(const Ikarus::Materials::VanishingStrain<pairs, MI>& mat, ikb_hyperelastic& law) {
+    return HyperelasticLaw<MI>::fill(mat.underlying(), law);
+  }
 };
 /** planeStrain(mat) (materials/vanishingstrain.hh:186-198) */
 template <auto pairs, typename MI>
@@ -185,6 +259,12 @@ struct ElementAccess<FE>
       return fe.material().materialParameters().mu;
     else
       return static_cast<double>(fe.material().materialParameters());
+  }
+  static bool hyperelastic(const FE& fe, ikb_hyperelastic& law) {
+    if constexpr (MaterialCode<Mat>::material == IKB_MAT_HYPERELASTIC)
+      return HyperelasticLaw<Mat>::fill(fe.material(), law);
+    else
+      return false;
   }
   static int numberOfInternalVariables(const FE& fe) {
     if constexpr (requires { fe.numberOfInternalVariables(); })
@@ -278,6 +358,8 @@ public:
     std::int64_t nElem = 0;
     ikb_desc desc{};
     desc.abi_version = IKB_ABI_VERSION;
+    ikb_hyperelastic law{};
+    bool hasLaw = false;
     for (const auto& fe : fes_) {
       using A = ElementAccess<FE>;
       if (nElem == 0) {
@@ -291,6 +373,7 @@ public:
         desc.eas_function = A::easFunction(fe);
         desc.lambda       = A::lambda(fe);
         desc.mu           = A::mu(fe);
+        hasLaw            = A::hyperelastic(fe, law);
       }
       A::globalIndices(fe, dofs);
       A::corners(fe, corners);
@@ -330,6 +413,8 @@ public:
       IKB_THROW(NotImplemented, "EAS is only supported for Q1, Q2 and H1 elements");
     if (rc != IKB_OK)
       IKB_THROW(InvalidState, "ikb_create failed (" + std::to_string(rc) + "): unsupported element description");
+    if (hasLaw)
+      check(ikb_set_hyperelastic(h_, &law));
     check(ikb_upload_mesh(h_, corners.data(), dofs.data()));
     check(ikb_upload_dirichlet(h_, flags.data()));
     check(ikb_build_pattern(h_));

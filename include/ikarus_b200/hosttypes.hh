@@ -134,6 +134,7 @@ struct HostFE
   bool planeStrain{false}, planeStress{false};
   double reduceTol{1e-12};
   double lambda{0.0}, mu{0.0};
+  ikb_hyperelastic hyperelastic{};  // material == IKB_MAT_HYPERELASTIC: the law (hyperelastic/factory.hh)
   std::vector<std::int64_t> dofs;
   std::vector<double> corners;
 };

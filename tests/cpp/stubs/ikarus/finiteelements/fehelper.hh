@@ -60,19 +60,58 @@ namespace Materials {
     const MaterialParameters materialParameters() const { return deviatoricFunction_.materialParametersImpl(); }
     static std::string name() { return "Deviatoric function: " + DF::name(); }
   };
-  template <typename ST>
-  struct VF0T
+  struct ArrudaBoyceMatParameters
   {
-    static std::string name() { return "None"; }
+    double mu, lambdaM;
   };
+  struct GentMatParameters
+  {
+    double mu, Jm;
+  };
+  template <typename ST>
+  struct ArrudaBoyceT
+  {
+    using ScalarType         = ST;
+    using MaterialParameters = ArrudaBoyceMatParameters;
+    MaterialParameters p;
+    MaterialParameters materialParametersImpl() const { return p; }
+    static std::string name() { return "ArrudaBoyce"; }
+  };
+  template <typename ST>
+  struct GentT
+  {
+    using ScalarType         = ST;
+    using MaterialParameters = GentMatParameters;
+    MaterialParameters p;
+    MaterialParameters materialParametersImpl() const { return p; }
+    static std::string name() { return "Gent"; }
+  };
+  // volumetricfunctions.hh:25-380: plain structs VF0 .. VF12, beta() on VF4 / VF7 / VF10
+  struct VF0 { static std::string name() { return "None"; } };
+  struct VF1 { static std::string name() { return "Function 1"; } };
+  struct VF2 { static std::string name() { return "Function 2"; } };
+  struct VF3 { static std::string name() { return "Function 3"; } };
+  struct VF4 { double beta_; double beta() const { return beta_; } static std::string name() { return "Function 4"; } };
+  struct VF5 { static std::string name() { return "Function 5"; } };
+  struct VF6 { static std::string name() { return "Function 6"; } };
+  struct VF7 { double beta_; double beta() const { return beta_; } static std::string name() { return "Function 7"; } };
+  struct VF8 { static std::string name() { return "Function 8"; } };
+  struct VF9 { static std::string name() { return "Function 9"; } };
+  struct VF10 { double beta_; double beta() const { return beta_; } static std::string name() { return "Function 10"; } };
+  struct VF11 { static std::string name() { return "Function 11"; } };
+  struct VF12 { static std::string name() { return "Function 12"; } };
   template <typename VF>
   struct Volumetric
   {
     using VolumetricFunction = VF;
     using MaterialParameter  = double;
+    MaterialParameter matPar_{};
+    VF volumetricFunction_{};
+    const VolumetricFunction& volumetricFunction() const { return volumetricFunction_; }
+    const MaterialParameter materialParameter() const { return matPar_; }
     static std::string name() { return "Volumetric function: " + VF::name(); }
   };
-  using NoVolumetricPart = Volumetric<VF0T<double>>;
+  using NoVolumetricPart = Volumetric<VF0>;
   template <typename DEV, typename VOL = NoVolumetricPart>
   struct Hyperelastic
   {
@@ -81,8 +120,11 @@ namespace Materials {
     static constexpr bool isReduced         = false;
     using MaterialParameters = typename DEV::MaterialParameters;
     DEV dev_;
+    VOL vol_{};
     static std::string name() { return "Hyperelastic (" + DEV::name() + ")"; }
     const MaterialParameters materialParameters() const { return dev_.materialParameters(); }
+    const DEV& deviatoricFunction() const { return dev_; }
+    const VOL& volumetricFunction() const { return vol_; }
   };
   struct MatrixIndexPair
   {
@@ -95,7 +137,8 @@ namespace Materials {
     static constexpr bool isReduced = true;
     MI mat;
     static std::string name() { return "VanishingStrain_" + MI::name(); }
-    const auto& materialParameters() const { return mat.materialParameters(); }
+    decltype(auto) materialParameters() const { return mat.materialParameters(); }
+    auto& underlying() const { return mat; }
   };
   template <auto pairs, typename MI>
   struct VanishingStress

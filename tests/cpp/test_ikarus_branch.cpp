@@ -107,6 +107,9 @@ using BK        = Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<
 using BKPStrain = Ikarus::Materials::VanishingStrain<onePair, BK>;
 static_assert(MaterialCode<BK>::material == IKB_MAT_BLATZKO && MaterialCode<BKPStrain>::material == IKB_MAT_BLATZKO &&
               MaterialCode<BKPStrain>::reduction == IKB_REDUCE_PLANE_STRAIN);  // makeBlatzKo(mu), factory.hh:34-39
+using GentVF4 = Ikarus::Materials::Hyperelastic<Ikarus::Materials::Deviatoric<Ikarus::Materials::GentT<double>>,
+                                             Ikarus::Materials::Volumetric<Ikarus::Materials::VF4>>;
+static_assert(MaterialCode<GentVF4>::material == IKB_MAT_HYPERELASTIC && VolumetricIndex<Ikarus::Materials::VF10>::value == 10);
 static_assert(MaterialCode<int>::material < 0);
 
 // a nonlinear solver's broadcaster, as far as subscribeTo() needs it (utils/broadcaster)
@@ -227,6 +230,49 @@ int main(int argc, char** argv) {
     for (std::size_t i = 0; i < n; ++i) req.d[(Eigen::Index)i] -= corr[(Eigen::Index)i];
   }
   CHECK(rnorm <= 1e-10 && iter > 1 && iter < 10);
+
+  // A material of the principal-stretch framework read off the TYPE and the public accessors (makeGent({mu, Jm}, K,
+  // VF4{beta}), hyperelastic/factory.hh:133-153).  At d = 0 every such law is linear elasticity with shear modulus mu and
+  // bulk modulus K U''(1) = K, and so is NeoHooke with lambda = K - 2 mu / 3: the two device kernels must agree there.
+  {
+    using FEG = FES<GentVF4>;
+    const double Kb = 3.0 * lam;
+    std::vector<FEG> fg;
+    std::vector<FE> fn;
+    for (const auto& f : fes) {
+      FEG g;
+      g.mat.dev_.deviatoricFunction_.p = {mu, 2.5};
+      g.mat.vol_.matPar_               = Kb;
+      g.mat.vol_.volumetricFunction_   = {0.5};
+      g.dofs_                          = f.dofs_;
+      g.el                             = f.el;
+      fg.push_back(g);
+      FE nh = f;
+      nh.mat.p = {Kb - 2.0 * mu / 3.0, mu};
+      fn.push_back(nh);
+    }
+    auto ag = makeDeviceSparseFlatAssembler(fg, dv);
+    auto an = makeDeviceSparseFlatAssembler(fn, dv);
+    Ikarus::FERequirements rq;
+    rq.d.resize(static_cast<Eigen::Index>(n));
+    rq.d.setZero();
+    rq.lambda = 0.0;
+    const Eigen::SparseMatrix<double> Kg = ag->matrix(rq, Ikarus::MatrixAffordance::stiffness, DBC::Full);
+    const Eigen::SparseMatrix<double> Kn = an->matrix(rq, Ikarus::MatrixAffordance::stiffness, DBC::Full);
+    CHECK(Kg.nonZeros() == Kn.nonZeros() && Kg.nonZeros() > 0);
+    double big = 0, err = 0;
+    for (Eigen::Index p = 0; p < Kg.nonZeros(); ++p) {
+      big = std::max(big, std::abs(Kn.valuePtr()[p]));
+      err = std::max(err, std::abs(Kg.valuePtr()[p] - Kn.valuePtr()[p]));
+    }
+    CHECK(big > 1.0 && err <= 1e-11 * big);
+    // and away from d = 0 the Gent law differs from NeoHooke
+    const Eigen::SparseMatrix<double> Kg2 = ag->matrix(req, Ikarus::MatrixAffordance::stiffness, DBC::Full);
+    const Eigen::SparseMatrix<double> Kn2 = an->matrix(req, Ikarus::MatrixAffordance::stiffness, DBC::Full);
+    double diff = 0;
+    for (Eigen::Index p = 0; p < Kg2.nonZeros(); ++p) diff = std::max(diff, std::abs(Kg2.valuePtr()[p] - Kn2.valuePtr()[p]));
+    CHECK(diff > 1e-6 * big);
+  }
   std::printf("run-mode ok: Ikarus branch, Newton converged in %d iterations, |R| = %.3e\n", iter, rnorm);
   return 0;
 }
