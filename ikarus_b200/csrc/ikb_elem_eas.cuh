@@ -583,10 +583,56 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     __syncwarp();
   }
 
+  // ------------------------------------------------------------------ LDL^T (D = Lf diag(d) Lf^T)
+  double* invd = Pm + N * M;  // [M] reciprocal pivots
+#ifndef IKB_EAS_SMEM_LDL
+  // In registers: thread a keeps rows {a, a+N, ..} of D (the rows it accumulated in pass C), full rows so that by
+  // symmetry row k carries what the elimination of column k needs; per pivot the owner's row is broadcast inside the
+  // element's N-lane group with shuffles and every thread updates its own rows.  No shared-memory traffic, no barrier
+  // and no cross-thread dependency other than the shuffles: the 21 dependent steps of E21 cost ~150 cycles each instead
+  // of a shared-memory round trip per entry (the shared-memory factorisation below held 45 % of the kernel's stall
+  // samples at 4 warps per SM).  Same operations per entry as the right-looking elimination below.
+  {
+    double Dr[C::ROWS][M];
+#pragma unroll
+    for (int jj = 0; jj < C::ROWS; ++jj)
+#pragma unroll
+      for (int k = 0; k < M; ++k) Dr[jj][k] = (a + jj * N < M) ? Dm[(a + jj * N) * M + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const int o = k % N, jo = k / N;  // owner lane (inside the element's group) and its local row
+      double v[M];
+#pragma unroll
+      for (int j = k; j < M; ++j) v[j] = __shfl_sync(0xffffffffu, Dr[jo][j], o, N);
+      const double idk = 1.0 / v[k];
+      if (a == 0) invd[k] = idk;
+#pragma unroll
+      for (int jj = 0; jj < C::ROWS; ++jj) {
+        if (jj * N + N - 1 <= k) continue;  // every row of this slot is at or above the pivot
+        const int i = a + jj * N;
+        if (i > k && i < M) {
+          const double lik = Dr[jj][k] * idk;
+#pragma unroll
+          for (int j = k + 1; j < M; ++j) Dr[jj][j] = fma(-lik, v[j], Dr[jj][j]);
+          Dr[jj][k] = lik;
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < C::ROWS; ++jj) {
+      const int i = a + jj * N;
+      if (i < M) {
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+          if (k < i) Dm[i * M + k] = Dr[jj][k];
+      }
+    }
+    __syncwarp();
+  }
+#else
   // ------------------------------------------------------------------ cooperative LDL^T (lower triangle, in place)
   // The reciprocal of pivot k+1 is computed by the owner of row k+1 while the others scale column k, so no
   // thread waits on a division inside the elimination, and the solves below need no divisions at all.
-  double* invd = Pm + N * M;  // [M]
   if (a == 0) invd[0] = 1.0 / Dm[0];
   __syncwarp();
 #pragma unroll 1
@@ -616,6 +662,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     if (k + 1 < M && ((k + 1) % N) == a) invd[k + 1] = 1.0 / Dm[(k + 1) * M + k + 1];
     __syncwarp();
   }
+#endif
   // ------------------------------------------------------------------ solves
   // With D = Lf diag(d) Lf^T:  L^T D^-1 L = Y^T diag(1/d) Y  and  L^T D^-1 Rt = Y^T diag(1/d) y_R  with
   // Y = Lf^-1 L, y_R = Lf^-1 Rt, so the assembly only needs FORWARD substitutions.  Thread a does the D columns
@@ -625,7 +672,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-      for (int c = 0; c < D; ++c) z[i][c] = Lr[i][c];
+      for (int c = 0; c < D; ++c) z[i][c] = Lm[i * ND + a * D + c];  // = Lr, not kept live through the factorisation
 #pragma unroll
     for (int i = 1; i < M; ++i)
 #pragma unroll
