@@ -44,6 +44,22 @@ struct EasArgs {
       constexpr int r[MM][2] = {__VA_ARGS__};                                                        \
       return r[j][1];                                                                                \
     }                                                                                                \
+    /* the table packed 3 bits per column: a run-time column index costs a shift and a mask instead */ \
+    /* of a copy of the table on the thread's stack */                                                 \
+    __host__ __device__ static constexpr unsigned long long bits(int which) {                        \
+      constexpr int r[MM][2] = {__VA_ARGS__};                                                        \
+      unsigned long long b = 0;                                                                      \
+      for (int j = 0; j < MM; ++j) b |= (unsigned long long)r[j][which] << (3 * j);                  \
+      return b;                                                                                      \
+    }                                                                                                \
+    __host__ __device__ static int rowRt(int j) {                                                    \
+      constexpr unsigned long long b = bits(0);                                                      \
+      return (int)((b >> (3 * j)) & 7ull);                                                           \
+    }                                                                                                \
+    __host__ __device__ static int monoRt(int j) {                                                   \
+      constexpr unsigned long long b = bits(1);                                                      \
+      return (int)((b >> (3 * j)) & 7ull);                                                           \
+    }                                                                                                \
   };
 template <int D, int M>
 struct EasTable;
@@ -124,6 +140,15 @@ __device__ __forceinline__ void monomials(int g, double invDet, double (&s)[D ==
     s[1] = t[1] * invDet;
     s[2] = t[0] * t[1] * invDet;
   }
+}
+
+// s[m] for a run-time m without indexing the register array
+template <int NM>
+__device__ __forceinline__ double pickMono(const double (&s)[NM], int m) {
+  double v = s[0];
+#pragma unroll
+  for (int q = 1; q < NM; ++q) v = (m == q) ? s[q] : v;
+  return v;
 }
 
 template <int D, int FORM, int M>
@@ -483,13 +508,13 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       double drow[M];
 #pragma unroll
       for (int k = 0; k < M; ++k) drow[k] = 0.0;
-      const int rj = T::row(j), mj = T::mono(j);
+      const int rj = T::rowRt(j), mj = T::monoRt(j);
 #pragma unroll 1
       for (int g = 0; g < N; ++g) {
         const double* gp = rec + g * C::GPS;
         double sm[C::NMONO];
         monomials<D>(g, gp[C::O_IDET], sm);
-        const double sj = sm[mj];
+        const double sj = pickMono(sm, mj);
         const double* Grow = gp + C::O_GG + rj * S;
 #pragma unroll
         for (int k = 0; k < M; ++k) drow[k] = fma(sj * sm[T::mono(k)], Grow[T::row(k)], drow[k]);
@@ -727,6 +752,11 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   }
   if (A.what & IKB_MATRIX) {
     double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
+    // the parked block of pair k + 1 is fetched before the 9 M FMAs of pair k (it was written by this thread and comes
+    // back from L2: the load latency would otherwise be exposed once per pair at 4 warps per SM)
+    double nxt[DD];
+#pragma unroll
+    for (int q = 0; q < DD; ++q) nxt[q] = Ke[(size_t)a * blockStride(D) + q];
 #pragma unroll 1
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
@@ -734,7 +764,12 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       double blk[DD];
       double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
 #pragma unroll
-      for (int q = 0; q < DD; ++q) blk[q] = dst[q];
+      for (int q = 0; q < DD; ++q) blk[q] = nxt[q];
+      if (k + 1 < NK && !(k + 1 == C::KMAX && a >= N / 2)) {
+        const double* src = Ke + (size_t)((k + 1) * N + a) * blockStride(D);
+#pragma unroll
+        for (int q = 0; q < DD; ++q) nxt[q] = src[q];
+      }
 #pragma unroll
       for (int j = 0; j < M; ++j) {
         double zb[D];

@@ -454,8 +454,8 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
             // enhanced strain dof: dE/dalpha_j = column j of M(xi) = T0inv[:, r_j] s_j, no variation of F
             using T = EasTable<D, M>;
             const int jj = I - ND;
-            const int rj = T::row(jj);
-            const double sj = sm[T::mono(jj)];
+            const int rj = T::rowRt(jj);
+            const double sj = pickMono(sm, T::monoRt(jj));
 #pragma unroll
             for (int p = 0; p < SYM; ++p) {
               int i, j;
