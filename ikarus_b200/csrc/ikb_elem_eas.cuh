@@ -425,79 +425,6 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   const int a = t;
   constexpr int NK = C::KMAX + 1;
   double* Dm = rec + (C::REC0 > C::SCR ? C::REC0 : C::SCR);  // [M][M], outside the record area
-  // ------------------------------------------------------------------ pass A: K_uu pairs and R_a
-  double Ra[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) Ra[i] = 0.0;
-  if (!EA.updateMode) {
-    double acc[NK][DD];
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-#pragma unroll
-      for (int q = 0; q < DD; ++q) acc[k][q] = 0.0;
-#pragma unroll 1
-    for (int g = 0; g < N; ++g) {
-      const double* gp = rec + g * C::GPS;
-      const double c1 = gp[C::O_C1], c2 = gp[C::O_C2];
-      double ma[D], ga[D], p1[D], p2[D], ha[D], sg[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        ga[i] = gp[C::O_G + i * N + a];
-        ma[i] = gp[C::O_M + i * N + a];
-        p1[i] = c1 * ma[i];
-        p2[i] = c2 * ma[i];
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          Ra[i] = fma(gp[C::O_WP + i * D + j], ga[j], Ra[i]);
-          s1 = fma(gp[C::O_X + symIdx<D>(i, j)], ga[j], s1);
-          s2 = fma(gp[C::O_WS + symIdx<D>(i, j)], ga[j], s2);
-        }
-        ha[i] = s1;
-        sg[i] = s2;
-      }
-#pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const int b = (a + k) & (N - 1);
-        double mb[D], gb[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          gb[i] = gp[C::O_G + i * N + b];
-          mb[i] = gp[C::O_M + i * N + b];
-        }
-        double cab = 0.0, sab = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          cab = fma(ha[i], gb[i], cab);
-          sab = fma(sg[i], gb[i], sab);
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int j = 0; j < D; ++j)
-            acc[k][i * D + j] = fma(p1[i], mb[j],
-                                    fma(mb[i], p2[j], fma(cab, gp[C::O_A2 + symIdx<D>(i, j)], acc[k][i * D + j])));
-#pragma unroll
-        for (int i = 0; i < D; ++i) acc[k][i * D + i] += sab;
-      }
-    }
-    // park the uncondensed blocks in the staging array (this thread re-reads them after the solve) -- only when the
-    // matrix was asked for: a VECTOR-only sweep must leave a staged, already condensed K_e of the same state untouched
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
-#pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      if (k == C::KMAX && a >= N / 2) break;
-      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
-      if (active && (A.what & IKB_MATRIX)) {
-#pragma unroll
-        for (int q = 0; q < DD; ++q) dst[q] = acc[k][q];
-      }
-    }
-  }
-
   // ------------------------------------------------------------------ pass C: rows {a, a+N, ..} of D and Rt
   double Rt[C::ROWS];
 #pragma unroll
@@ -565,11 +492,16 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
       for (int c = 0; c < D; ++c) Lr[j][c] = fma(sm[T::mono(j)], QB[T::row(j)][c], Lr[j][c]);
   }
-  __syncwarp();  // all passes done: the record area becomes condensation scratch
+  __syncwarp();  // passes B and C done: the slots [O_F, GPS) of every Gauss-point record become condensation scratch
 
-  double* Lm = rec;                 // [M][ND]  L, overwritten by Y = Lf^-1 L (D = Lf diag(d) Lf^T)
-  double* Rm = Lm + M * ND;         // [M]      Rt -> Lf^-1 Rt (assembly) / D^-1 (Rt + L du) (update)
-  double* Pm = Rm + M;              // [N][M]   partial sums of L du (update mode)
+  // Row j of L (overwritten by Y = Lf^-1 L, D = Lf diag(d) Lf^T) lives in the free tail of Gauss-point record j / RPG;
+  // Rt and the reciprocal pivots in the tail of the last record; the partial sums of L du (update mode, no pass A)
+  // in the head of record b.  Pass A still finds its slots [0, O_F) intact.
+  constexpr int RPG = (C::GPS - C::O_F) / ND;  // rows of L per record tail
+  static_assert(RPG >= 1 && (M + RPG - 1) / RPG <= N - 1 && 2 * M <= C::GPS - C::O_F && M <= C::O_F, "scratch layout");
+#define IKB_LM(j) (rec + ((j) / RPG) * C::GPS + C::O_F + ((j) % RPG) * ND)
+#define IKB_PM(b) (rec + (b) * C::GPS)
+  double* Rm = rec + (N - 1) * C::GPS + C::O_F;  // [M]  Rt -> Lf^-1 Rt (assembly) / D^-1 (Rt + L du) (update)
 #pragma unroll
   for (int jj = 0; jj < C::ROWS; ++jj) {
     const int j = a + jj * N;
@@ -578,7 +510,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
   for (int j = 0; j < M; ++j)
 #pragma unroll
-    for (int c = 0; c < D; ++c) Lm[j * ND + a * D + c] = Lr[j][c];
+    for (int c = 0; c < D; ++c) IKB_LM(j)[a * D + c] = Lr[j][c];
   if (EA.updateMode) {
     // partial_j = sum_c L[j][a,c] du[a,c]
     const int64_t node = __ldg(A.elemNode + (size_t)a * A.nElem + e);
@@ -590,7 +522,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       double s = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) s = fma(Lr[j][c], du[c], s);
-      Pm[a * M + j] = s;
+      IKB_PM(a)[j] = s;
     }
   }
   __syncwarp();
@@ -601,7 +533,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       const int j = a + jj * N;
       if (j < M) {
         double s = Rm[j];
-        for (int b = 0; b < N; ++b) s += Pm[b * M + j];
+        for (int b = 0; b < N; ++b) s += IKB_PM(b)[j];
         Rm[j] = s;
       }
     }
@@ -609,7 +541,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   }
 
   // ------------------------------------------------------------------ LDL^T (D = Lf diag(d) Lf^T)
-  double* invd = Pm + N * M;  // [M] reciprocal pivots
+  double* invd = Rm + M;  // [M] reciprocal pivots
 #ifndef IKB_EAS_SMEM_LDL
   // In registers: thread a keeps rows {a, a+N, ..} of D (the rows it accumulated in pass C), full rows so that by
   // symmetry row k carries what the elimination of column k needs; per pivot the owner's row is broadcast inside the
@@ -692,12 +624,12 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   // With D = Lf diag(d) Lf^T:  L^T D^-1 L = Y^T diag(1/d) Y  and  L^T D^-1 Rt = Y^T diag(1/d) y_R  with
   // Y = Lf^-1 L, y_R = Lf^-1 Rt, so the assembly only needs FORWARD substitutions.  Thread a does the D columns
   // of node a together, fully unrolled in registers (each factor entry is loaded once for D columns).
-  double z[M][D];
   if (!EA.updateMode) {
+    double z[M][D];
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-      for (int c = 0; c < D; ++c) z[i][c] = Lm[i * ND + a * D + c];  // = Lr, not kept live through the factorisation
+      for (int c = 0; c < D; ++c) z[i][c] = IKB_LM(i)[a * D + c];  // = Lr, not kept live through the factorisation
 #pragma unroll
     for (int i = 1; i < M; ++i)
 #pragma unroll
@@ -709,7 +641,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-      for (int c = 0; c < D; ++c) Lm[i * ND + a * D + c] = z[i][c];
+      for (int c = 0; c < D; ++c) IKB_LM(i)[a * D + c] = z[i][c];
   }
   if (a == N - 1) {
     double zr[M];
@@ -742,62 +674,113 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     return;
   }
 
-  // ------------------------------------------------------------------ condensation
-  // K_ab -= Y_a^T diag(1/d) Y_b ; R_a -= Y_a^T diag(1/d) y_R   (enhancedassumedstrains.hh:292-296, 341-345)
+  // ------------------------------------------------------------------ pass A, then the condensation in registers
+  // K_ab = sum_g (...) - Y_a^T diag(1/d) Y_b ; R_a -= Y_a^T diag(1/d) y_R   (enhancedassumedstrains.hh:292-296, 341-345)
+  // ------------------------------------------------------------------ pass A: K_uu pairs and R_a
+  // (after the solves: the records it reads, [0, O_F) of every Gauss point, are not touched by the scratch below, and
+  // the blocks stay in registers until the condensed values are written -- no round trip through the staging array)
+  double Ra[D];
 #pragma unroll
+  for (int i = 0; i < D; ++i) Ra[i] = 0.0;
+  double acc[NK][DD];
+  {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int q = 0; q < DD; ++q) acc[k][q] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < N; ++g) {
+      const double* gp = rec + g * C::GPS;
+      const double c1 = gp[C::O_C1], c2 = gp[C::O_C2];
+      double ma[D], ga[D], p1[D], p2[D], ha[D], sg[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        ga[i] = gp[C::O_G + i * N + a];
+        ma[i] = gp[C::O_M + i * N + a];
+        p1[i] = c1 * ma[i];
+        p2[i] = c2 * ma[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          Ra[i] = fma(gp[C::O_WP + i * D + j], ga[j], Ra[i]);
+          s1 = fma(gp[C::O_X + symIdx<D>(i, j)], ga[j], s1);
+          s2 = fma(gp[C::O_WS + symIdx<D>(i, j)], ga[j], s2);
+        }
+        ha[i] = s1;
+        sg[i] = s2;
+      }
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int b = (a + k) & (N - 1);
+        double mb[D], gb[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          gb[i] = gp[C::O_G + i * N + b];
+          mb[i] = gp[C::O_M + i * N + b];
+        }
+        double cab = 0.0, sab = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          cab = fma(ha[i], gb[i], cab);
+          sab = fma(sg[i], gb[i], sab);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            acc[k][i * D + j] = fma(p1[i], mb[j],
+                                    fma(mb[i], p2[j], fma(cab, gp[C::O_A2 + symIdx<D>(i, j)], acc[k][i * D + j])));
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[k][i * D + i] += sab;
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll 3
   for (int j = 0; j < M; ++j) {
     const double id = invd[j];
+    const double* Yj = IKB_LM(j);
+    double za[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) z[j][c] *= id;
-  }
-  if (A.what & IKB_MATRIX) {
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
-    // the parked block of pair k + 1 is fetched before the 9 M FMAs of pair k (it was written by this thread and comes
-    // back from L2: the load latency would otherwise be exposed once per pair at 4 warps per SM)
-    double nxt[DD];
+    for (int c = 0; c < D; ++c) za[c] = Yj[a * D + c] * id;
+    if (A.what & IKB_MATRIX) {
 #pragma unroll
-    for (int q = 0; q < DD; ++q) nxt[q] = Ke[(size_t)a * blockStride(D) + q];
-#pragma unroll 1
-    for (int k = 0; k < NK; ++k) {
-      if (k == C::KMAX && a >= N / 2) break;
-      const int b = (a + k) & (N - 1);
-      double blk[DD];
-      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
-#pragma unroll
-      for (int q = 0; q < DD; ++q) blk[q] = nxt[q];
-      if (k + 1 < NK && !(k + 1 == C::KMAX && a >= N / 2)) {
-        const double* src = Ke + (size_t)((k + 1) * N + a) * blockStride(D);
-#pragma unroll
-        for (int q = 0; q < DD; ++q) nxt[q] = src[q];
-      }
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
+      for (int k = 0; k < NK; ++k) {
+        const int b = (a + k) & (N - 1);
         double zb[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) zb[c] = Lm[j * ND + b * D + c];
+        for (int c = 0; c < D; ++c) zb[c] = Yj[b * D + c];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-          for (int c = 0; c < D; ++c) blk[i * D + c] = fma(-z[j][i], zb[c], blk[i * D + c]);
+          for (int c = 0; c < D; ++c) acc[k][i * D + c] = fma(-za[i], zb[c], acc[k][i * D + c]);
       }
-      if (active) {
+    }
+    const double zR = Rm[j];
 #pragma unroll
-        for (int i = 0; i < D; ++i)
+    for (int i = 0; i < D; ++i) Ra[i] = fma(-za[i], zR, Ra[i]);
+  }
+  if ((A.what & IKB_MATRIX) && active) {
+    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
 #pragma unroll
-          for (int j = 0; j < D; ++j) dst[i * D + j] = (k == 0 && i > j) ? blk[j * D + i] : blk[i * D + j];
-      }
+    for (int k = 0; k < NK; ++k) {
+      if (k == C::KMAX && a >= N / 2) break;
+      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) dst[i * D + j] = (k == 0 && i > j) ? acc[k][j * D + i] : acc[k][i * D + j];
     }
   }
   if ((A.what & IKB_VECTOR) && active) {
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      const double zR = Rm[j];
-#pragma unroll
-      for (int i = 0; i < D; ++i) Ra[i] = fma(-z[j][i], zR, Ra[i]);
-    }
-#pragma unroll
     for (int i = 0; i < D; ++i) A.Rst[(size_t)e * ND + a * D + i] = Ra[i];
   }
+#undef IKB_LM
+#undef IKB_PM
 }
 
 template <int D, int FORM, int M>
