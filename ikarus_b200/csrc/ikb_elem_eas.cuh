@@ -171,6 +171,12 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 
   // ------------------------------------------------------------------ phase 1: Gauss point t
   {
+    // (T(centre) detJ0)^-1 is fetched first: its latency hides behind the geometry and the kinematics
+    double T0[S][S];
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+#pragma unroll
+      for (int q = 0; q < S; ++q) T0[p][q] = __ldg(EA.T0inv + (size_t)(p * S + q) * A.nElem + e);
     const double lo = 0.5 - 0.28867513459481287, hi = 0.5 + 0.28867513459481287;
     double xi[D], om[D];
 #pragma unroll
@@ -253,11 +259,6 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       Ev[q] = (i == j) ? v : 2.0 * v;
     }
     // enhanced strain: E += T0inv * (sum_j s_j alpha_j e_{r_j})
-    double T0[S][S];
-#pragma unroll
-    for (int p = 0; p < S; ++p)
-#pragma unroll
-      for (int q = 0; q < S; ++q) T0[p][q] = __ldg(EA.T0inv + (size_t)(p * S + q) * A.nElem + e);
     double sm[C::NMONO];
     monomials<D>(t, invDet, sm);
     {
@@ -567,12 +568,12 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
       for (int jj = 0; jj < C::ROWS; ++jj) {
         if (jj * N + N - 1 <= k) continue;  // every row of this slot is at or above the pivot
         const int i = a + jj * N;
-        if (i > k && i < M) {
-          const double lik = Dr[jj][k] * idk;
+        // rows at or above the pivot (and the padding rows past M) take lik = 0: no divergent branch in the chain
+        const bool below = i > k && i < M;
+        const double lik = below ? Dr[jj][k] * idk : 0.0;
 #pragma unroll
-          for (int j = k + 1; j < M; ++j) Dr[jj][j] = fma(-lik, v[j], Dr[jj][j]);
-          Dr[jj][k] = lik;
-        }
+        for (int j = k + 1; j < M; ++j) Dr[jj][j] = fma(-lik, v[j], Dr[jj][j]);
+        Dr[jj][k] = below ? lik : Dr[jj][k];
       }
     }
 #pragma unroll
@@ -763,16 +764,31 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
     for (int i = 0; i < D; ++i) Ra[i] = fma(-za[i], zR, Ra[i]);
   }
-  if ((A.what & IKB_MATRIX) && active) {
-    double* Ke = A.Kst + (size_t)e * C::NPAIR * blockStride(D);
+  if (A.what & IKB_MATRIX) {
+    // write-out through the (now free) record area: the element's N lanes then store 16-byte vectors to consecutive
+    // addresses, full sectors instead of 8-byte pieces 72 bytes apart (the staged K_e of an element is contiguous)
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
       if (k == C::KMAX && a >= N / 2) break;
-      double* dst = Ke + (size_t)(k * N + a) * blockStride(D);
+      double* dst = rec + (k * N + a) * DD;
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < D; ++j) dst[i * D + j] = (k == 0 && i > j) ? acc[k][j * D + i] : acc[k][i * D + j];
+    }
+    __syncwarp();
+    if (active) {
+      constexpr int TOT = C::NPAIR * DD;
+      double* Ke = A.Kst + (size_t)e * TOT;
+      if constexpr (TOT % 2 == 0) {
+        // rec is 16-byte aligned (ES is a multiple of 16 doubles) and so is Ke (TOT even)
+        const double2* src2 = reinterpret_cast<const double2*>(rec);
+        double2* dst2 = reinterpret_cast<double2*>(Ke);
+        for (int q = a; q < TOT / 2; q += N) dst2[q] = src2[q];
+      } else {
+        for (int q = a; q < TOT; q += N) Ke[q] = rec[q];
+      }
     }
   }
   if ((A.what & IKB_VECTOR) && active) {
