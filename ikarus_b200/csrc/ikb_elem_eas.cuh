@@ -556,12 +556,17 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     for (int jj = 0; jj < C::ROWS; ++jj)
 #pragma unroll
       for (int k = 0; k < M; ++k) Dr[jj][k] = (a + jj * N < M) ? Dm[(a + jj * N) * M + k] : 0.0;
+    // the right-hand side rides along as one more column: y_R = Lf^-1 Rt comes out of the same elimination
+    double rr[C::ROWS];
+#pragma unroll
+    for (int jj = 0; jj < C::ROWS; ++jj) rr[jj] = (a + jj * N < M) ? Rm[a + jj * N] : 0.0;
 #pragma unroll
     for (int k = 0; k < M; ++k) {
       const int o = k % N, jo = k / N;  // owner lane (inside the element's group) and its local row
       double v[M];
 #pragma unroll
       for (int j = k; j < M; ++j) v[j] = __shfl_sync(0xffffffffu, Dr[jo][j], o, N);
+      const double yk = __shfl_sync(0xffffffffu, rr[jo], o, N);
       const double idk = 1.0 / v[k];
       if (a == 0) invd[k] = idk;
 #pragma unroll
@@ -574,6 +579,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
         for (int j = k + 1; j < M; ++j) Dr[jj][j] = fma(-lik, v[j], Dr[jj][j]);
         Dr[jj][k] = below ? lik : Dr[jj][k];
+        rr[jj] = fma(-lik, yk, rr[jj]);
       }
     }
 #pragma unroll
@@ -583,6 +589,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
         for (int k = 0; k < M; ++k)
           if (k < i) Dm[i * M + k] = Dr[jj][k];
+        Rm[i] = rr[jj];
       }
     }
     __syncwarp();
@@ -644,14 +651,20 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
       for (int c = 0; c < D; ++c) IKB_LM(i)[a * D + c] = z[i][c];
   }
+#ifndef IKB_EAS_SMEM_LDL
+  if (a == N - 1 && EA.updateMode) {  // the forward substitution of Rt happened inside the factorisation
+#else
   if (a == N - 1) {
+#endif
     double zr[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) zr[i] = Rm[i];
+#ifdef IKB_EAS_SMEM_LDL
 #pragma unroll
     for (int i = 1; i < M; ++i)
 #pragma unroll
       for (int j = 0; j < i; ++j) zr[i] = fma(-Dm[i * M + j], zr[j], zr[i]);
+#endif
     if (EA.updateMode) {
 #pragma unroll
       for (int i = 0; i < M; ++i) zr[i] *= invd[i];
