@@ -104,7 +104,9 @@ struct EasCfg {
   static constexpr int EPC0 = (100 * 1024) / (ES * 8);
   static constexpr int EPC1 = (EPC0 / EPW) * EPW;
   static constexpr int EPC2 = EPC1 > 128 / N ? 128 / N : EPC1;
-  static constexpr int EPC = EPC2 < EPW ? EPW : EPC2;
+  // one warp per CTA: the shared memory of an SM then divides into as many resident warps as fit (E9: 5 x 45 KB instead
+  // of 2 CTAs of 2 warps; E21: 4 x 56 KB either way) -- the kernel is latency bound, every resident warp counts
+  static constexpr int EPC = EPW + 0 * EPC2;
   static constexpr int TPB = EPC * N;
   static constexpr size_t SMEM = (size_t)EPC * ES * 8;
 };
