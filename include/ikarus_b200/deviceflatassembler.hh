@@ -191,9 +191,9 @@ struct HyperelasticLaw<Ikarus::Materials::Hyperelastic<DEV, VOL>>
     } else if constexpr (std::is_arithmetic_v<std::remove_cvref_t<decltype(p)>>) {
       law.deviatoric = IKB_DEV_BLATZKO, law.par[0] = static_cast<double>(p);
     } else {
-      IKB_THROW(NotImplemented, "material " + Mat::name() +
-                                    ": exponents are not exposed by Deviatoric<DF>; specialise "
-                                    "Ikarus::B200::ElementAccess<FE>::hyperelastic to pass the law");
+      // Ogden / InvariantBased: the exponents are private in the reference; the caller hands the law over with
+      // DeviceSparseFlatAssembler::setHyperelasticLaw() before the first assembly (IKB_ESTATE otherwise)
+      return false;
     }
     if constexpr (Mat::hasVolumetricPart) {
       using VF = typename VOL::VolumetricFunction;
@@ -424,6 +424,10 @@ public:
     corners_ = std::move(corners);  // kept for the host-side load sampling
     dofs_    = std::move(dofs);
   }
+  /** The law of a principal-stretch material (IKB_MAT_HYPERELASTIC) where it cannot be read off the material object:
+   *  Deviatoric<DF> exposes only materialParameters() (deviatoric/interface.hh:61-66), so the exponents of makeOgden /
+   *  makeMooneyRivlin / makeYeoh / makeInvariantBased are handed over here, before the first assembly. */
+  void setHyperelasticLaw(const ikb_hyperelastic& law) { check(ikb_set_hyperelastic(h_, &law)); }
   ~DeviceSparseFlatAssembler() {
     if (h_)
       ikb_destroy(h_);
