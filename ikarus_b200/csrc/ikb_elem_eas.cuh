@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
       for (int j = k; j < M; ++j) v[j] = __shfl_sync(0xffffffffu, Dr[jo][j], o, N);
       const double yk = __shfl_sync(0xffffffffu, rr[jo], o, N);
-      const double idk = 1.0 / v[k];
+      const double idk = __drcp_rn(v[k]);  // correctly rounded like 1.0 / x, without the division's slow path
       if (a == 0) invd[k] = idk;
 #pragma unroll
       for (int jj = 0; jj < C::ROWS; ++jj) {

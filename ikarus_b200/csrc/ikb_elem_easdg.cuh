@@ -40,6 +40,16 @@ struct DgCfg {
   static constexpr int SYM = D * (D + 1) / 2;
   static constexpr int NP = G * (G + 1) / 2;     // generalised dof pairs I <= J
   static constexpr int NS = (NP + 31) / 32;      // pairs per lane
+  // register tiles of the pair loop: the dofs form NG groups of TS, lane t owns the TS x TS block of the group pair
+  // (gi <= gj) number t; TS is the smallest size whose NG (NG + 1) / 2 blocks fit the 32 lanes
+  static constexpr int tileSize() {
+    for (int ts = 1; ts <= 16; ++ts) {
+      const int ng = (G + ts - 1) / ts;
+      if (ng * (ng + 1) / 2 <= 32) return ts;
+    }
+    return 16;
+  }
+  static constexpr int TS = tileSize(), NG = (G + TS - 1) / TS, NT = NG * (NG + 1) / 2;
   // record of a generalised dof at a Gauss point
   static constexpr int O_B = 0, O_XBX = SYM, O_T = 2 * SYM, O_DF = 2 * SYM + 1, O_DFS = O_DF + D * D;
   static constexpr int O_MA = O_DFS + D * D, O_MB = O_MA + D * D;  // transposed form: the mixed second variation
@@ -98,26 +108,26 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
     for (int t = lane; t < SYM * SYM; t += 32) T0[t] = __ldg(EA.T0inv + (size_t)t * A.nElem + e);
   __syncwarp();
 
-  // the pairs of this lane: t = lane + 32 s  ->  (I, J), I <= J, rows of G - I pairs each
-  uint16_t pairIJ[C::NS];
+  // the tile of this lane: group pair (gi, gj), gi <= gj, number lane (row gi holds NG - gi tiles); lanes past NT idle
+  constexpr int TS = C::TS, NG = C::NG;
+  int gi = 0, gj = 0;
   {
-    // row I starts at pair index off(I) = I G - I (I - 1) / 2; closed form + one correction step each way
-#pragma unroll
-    for (int s = 0; s < C::NS; ++s) {
-      const int t = lane + 32 * s;
-      const int tc = t < C::NP ? t : C::NP - 1;
-      int I = (int)(((float)(2 * G + 1) - sqrtf((float)((2 * G + 1) * (2 * G + 1) - 8 * tc))) * 0.5f);
-      I = I < 0 ? 0 : (I > G - 1 ? G - 1 : I);
-      if (I * G - I * (I - 1) / 2 > tc) --I;
-      if (I + 1 < G && (I + 1) * G - (I + 1) * I / 2 <= tc) ++I;
-      const int off = I * G - I * (I - 1) / 2;
-      const int J = I + (tc - off);
-      pairIJ[s] = (t < C::NP) ? (uint16_t)(I | (J << 8)) : (uint16_t)0xffff;
+    int t = lane < C::NT ? lane : 0, row = NG;
+    while (t >= row) {
+      t -= row;
+      --row;
+      ++gi;
     }
+    gj = gi + t;
   }
-  double acc[C::NS];
+  const bool tileActive = lane < C::NT;
+  // first dof of the two groups; slots past G read the last dof (their products are never stored)
+  const int I0 = gi * TS, J0 = gj * TS;
+  double acc[TS][TS];
 #pragma unroll
-  for (int s = 0; s < C::NS; ++s) acc[s] = 0.0;
+  for (int i = 0; i < TS; ++i)
+#pragma unroll
+    for (int j = 0; j < TS; ++j) acc[i][j] = 0.0;
   double rI[2] = {0.0, 0.0};  // R_gen of dofs lane and lane + 32
   [[maybe_unused]] double energy = 0.0;
 
@@ -525,30 +535,44 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
     }
     __syncwarp();
 
-    // ---- pairs
+    // ---- pairs, channel by channel: for every scalar channel q of the records (X:B, the 6 (3) strain components, the D^2
+    // entries of dF against dF S, and the mixed terms of the transposed form) the tile takes the outer product of the TS
+    // row values with the TS column values -- 2 TS shared-memory loads for TS^2 FMAs instead of two whole records per pair
     const double c1 = wd * lp, c2 = 2.0 * wd * mp;
+    if (tileActive) {
+      const double* ra[TS];
+      const double* rb[TS];
 #pragma unroll
-    for (int s = 0; s < C::NS; ++s) {
-      const unsigned pj = pairIJ[s];
-      if (pj != 0xffffu) {
-        const double* a = rec + (pj & 0xffu) * REC;
-        const double* b = rec + (pj >> 8) * REC;
-        double mat = 0.0, geo = 0.0;
+      for (int i = 0; i < TS; ++i) {
+        const int I = I0 + i < G ? I0 + i : G - 1, J = J0 + i < G ? J0 + i : G - 1;
+        ra[i] = rec + I * REC;
+        rb[i] = rec + J * REC;
+      }
+      auto channel = [&](int oa, int ob, double coef) {
+        double x[TS], y[TS];
 #pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int j = i; j < D; ++j) {
-            const double v = a[C::O_B + symI<D>(i, j)] * b[C::O_XBX + symI<D>(i, j)];
-            mat += (i == j) ? v : 2.0 * v;
-          }
-#pragma unroll
-        for (int q = 0; q < D * D; ++q) geo = fma(a[C::O_DF + q], b[C::O_DFS + q], geo);
-        if constexpr (TR) {
-#pragma unroll
-          for (int q = 0; q < D * D; ++q)
-            geo = fma(a[C::O_MA + q], b[C::O_MB + q], fma(a[C::O_MB + q], b[C::O_MA + q], geo));
+        for (int i = 0; i < TS; ++i) {
+          x[i] = coef * ra[i][oa];
+          y[i] = rb[i][ob];
         }
-        acc[s] += c1 * a[C::O_T] * b[C::O_T] + c2 * mat + wd * geo;
+#pragma unroll
+        for (int i = 0; i < TS; ++i)
+#pragma unroll
+          for (int j = 0; j < TS; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
+      };
+      if constexpr (FORM != FORM_PS) channel(C::O_T, C::O_T, c1);  // lp = 0 for the principal-stretch laws
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = i; j < D; ++j) channel(C::O_B + symI<D>(i, j), C::O_XBX + symI<D>(i, j), (i == j) ? c2 : 2.0 * c2);
+#pragma unroll
+      for (int q = 0; q < D * D; ++q) channel(C::O_DF + q, C::O_DFS + q, wd);
+      if constexpr (TR) {
+#pragma unroll
+        for (int q = 0; q < D * D; ++q) {
+          channel(C::O_MA + q, C::O_MB + q, wd);
+          channel(C::O_MB + q, C::O_MA + q, wd);
+        }
       }
     }
   }
@@ -558,14 +582,17 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
   if constexpr (FORM == FORM_PS && M == 0) {
     if ((A.what & IKB_SCALAR) && lane == 0) A.Est[e] = energy;  // int psi dV (nonlinearelastic.hh:276-290)
   }
+  if (tileActive) {
 #pragma unroll
-  for (int s = 0; s < C::NS; ++s) {
-    const unsigned pj = pairIJ[s];
-    if (pj != 0xffffu) {
-      const int I = pj & 0xffu, J = pj >> 8;
-      Kg[I * GS + J] = acc[s];
-      Kg[J * GS + I] = acc[s];
-    }
+    for (int i = 0; i < TS; ++i)
+#pragma unroll
+      for (int j = 0; j < TS; ++j) {
+        const int I = I0 + i, J = J0 + j;
+        if (I < G && J < G && I <= J) {  // diagonal tiles keep their upper triangle
+          Kg[I * GS + J] = acc[i][j];
+          Kg[J * GS + I] = acc[i][j];
+        }
+      }
   }
 #pragma unroll
   for (int rnd = 0; rnd < (G + 31) / 32; ++rnd)
