@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
   for (int i = 0; i < TS; ++i)
 #pragma unroll
     for (int j = 0; j < TS; ++j) acc[i][j] = 0.0;
-  double rI[2] = {0.0, 0.0};  // R_gen of dofs lane and lane + 32
+  double rI[2] = {0.0, 0.0};  // R_gen of the nodal dof lane and of the enhanced dof ND + lane
   [[maybe_unused]] double energy = 0.0;
 
   // ---- element centre: J0^-T, detJ0, (transposed form) grad N^0 and F_c0
@@ -344,9 +344,11 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
     // ---- record(s) of this lane's generalised dof(s)
     __syncwarp();  // the pair loop of the previous Gauss point has read the records
 #pragma unroll
-    for (int rnd = 0; rnd < (G + 31) / 32; ++rnd) {
-      const int I = lane + 32 * rnd;
-      if (I < G) {
+    // round 0: the nodal dofs (lane < ND), round 1: the enhanced ones (lane < M) -- every round runs one of the two
+    // record formulas on all its lanes instead of both on a mixed set
+    for (int rnd = 0; rnd < (M > 0 ? 2 : 1); ++rnd) {
+      const int I = rnd == 0 ? lane : ND + lane;
+      if (rnd == 0 ? lane < ND : lane < M) {
         double dF[D][D], mA[D][D], mB[D][D];
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -595,8 +597,8 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
       }
   }
 #pragma unroll
-  for (int rnd = 0; rnd < (G + 31) / 32; ++rnd)
-    if (lane + 32 * rnd < G) Rg[lane + 32 * rnd] = rI[rnd];
+  if (lane < ND) Rg[lane] = rI[0];
+  if (lane < M) Rg[ND + lane] = rI[1];
   __syncwarp();
   // right-hand side of the enhanced block: Rtilde, in update mode Rtilde + L du (enhancedassumedstrains.hh:243)
   if (lane < M) {
