@@ -609,8 +609,79 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
   }
   __syncwarp();
 
-  // ---- [D | L | rhs] -> [I | D^-1 L | D^-1 rhs]: Gauss-Jordan with partial pivoting on the rows ND.. of Kg.  The
+  // ---- [D | L | rhs] -> [I | D^-1 L | D^-1 rhs]: Gauss-Jordan with partial pivoting (the reference inverts D).  The
   // columns ND.. of the rows below ND keep L^T for the condensation.
+#ifndef IKB_DG_SMEM_GJ
+  // In registers, one lane per COLUMN of the augmented matrix (G + 1 columns on 32 lanes: NCOL per lane), so a row
+  // operation is lane-local.  Per pivot the owner of column ND + k picks the pivot row and hands it, with the column's
+  // entries (the multipliers), to all lanes by shuffles; the row exchange is a select chain (no dynamic register index).
+  // No shared-memory access and no barrier inside the M dependent steps.
+  if constexpr (M > 0) {
+    constexpr int NCOL = (G + 1 + 31) / 32;
+    double col[NCOL][C::MX];
+#pragma unroll
+    for (int sl = 0; sl < NCOL; ++sl) {
+      const int c = lane + 32 * sl;
+#pragma unroll
+      for (int r = 0; r < M; ++r) col[sl][r] = c < G ? Kg[(ND + r) * GS + c] : (c == G ? rhs[r] : 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      constexpr unsigned FULLM = 0xffffffffu;
+      const int ol = (ND + k) % 32, os = (ND + k) / 32;  // owner lane and slot of column ND + k
+      // pivot row: first maximum of |column| over r >= k, decided by the owner
+      int piv = k;
+      double best = fabs(col[os][k]);
+#pragma unroll
+      for (int r = k + 1; r < M; ++r) {
+        const double v = fabs(col[os][r]);
+        const bool gt = v > best;
+        best = gt ? v : best;
+        piv = gt ? r : piv;
+      }
+      piv = __shfl_sync(FULLM, piv, ol);
+      double f[C::MX];
+#pragma unroll
+      for (int r = 0; r < M; ++r) f[r] = __shfl_sync(FULLM, col[os][r], ol);
+      // exchange rows k and piv in the multipliers and in this lane's columns
+      {
+        double fp = f[k];
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) fp = (r == piv) ? f[r] : fp;
+        const double fk = f[k];
+        f[k] = fp;
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) f[r] = (r == piv) ? fk : f[r];
+      }
+      const double ip = 1.0 / f[k];
+#pragma unroll
+      for (int sl = 0; sl < NCOL; ++sl) {
+        double cp = col[sl][k];
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) cp = (r == piv) ? col[sl][r] : cp;
+        const double ck = col[sl][k];
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) col[sl][r] = (r == piv) ? ck : col[sl][r];
+        const double pk = cp * ip;
+        col[sl][k] = pk;
+#pragma unroll
+        for (int r = 0; r < M; ++r)
+          if (r != k) col[sl][r] = fma(-f[r], pk, col[sl][r]);
+      }
+    }
+    // D^-1 L and D^-1 rhs back to shared memory (the columns ND.. have become the identity and are not needed)
+#pragma unroll
+    for (int sl = 0; sl < NCOL; ++sl) {
+      const int c = lane + 32 * sl;
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        if (c < ND) Kg[(ND + r) * GS + c] = col[sl][r];
+        if (c == G) rhs[r] = col[sl][r];
+      }
+    }
+    __syncwarp();
+  }
+#else
   for (int k = 0; k < M; ++k) {
     int piv = k;
     double best = fabs(Kg[(ND + k) * GS + ND + k]);
@@ -650,6 +721,8 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
     }
     __syncwarp();
   }
+
+#endif
 
   if (EA.updateMode) {
     if (lane < M) EA.alpha[(size_t)e * M + lane] -= rhs[lane];
