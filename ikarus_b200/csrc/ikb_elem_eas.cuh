@@ -173,7 +173,18 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 
   // ------------------------------------------------------------------ phase 1: Gauss point t
   {
-    // (T(centre) detJ0)^-1 is fetched first: its latency hides behind the geometry and the kinematics
+    // The element's nodes and, behind them, its displacements are fetched first (two dependent global loads), then
+    // (T(centre) detJ0)^-1: their latency hides behind the geometry
+    double ue[N][D];
+    {
+      int64_t nodes[N];
+#pragma unroll
+      for (int a = 0; a < N; ++a) nodes[a] = __ldg(A.elemNode + (size_t)a * A.nElem + e);
+#pragma unroll
+      for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) ue[a][c] = __ldg(A.U + dofOf(A.layout, D, A.nNodes, nodes[a], c));
+    }
     double T0[S][S];
 #pragma unroll
     for (int p = 0; p < S; ++p)
@@ -234,10 +245,9 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
         g[j] = s;
         gp[C::O_G + j * N + a] = s;
       }
-      const int64_t node = __ldg(A.elemNode + (size_t)a * A.nElem + e);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        const double u = __ldg(A.U + dofOf(A.layout, D, A.nNodes, node, c));
+        const double u = ue[a][c];
 #pragma unroll
         for (int j = 0; j < D; ++j) H[c][j] = fma(u, g[j], H[c][j]);
       }
