@@ -244,6 +244,57 @@ int main(int argc, char** argv) {
     CHECK(std::isfinite(m.scalar(req, ScalarAffordance::mechanicalPotentialEnergy)));
   }
 
+  // Principal-stretch framework through the wrapper (HostFE::hyperelastic -> ikb_set_hyperelastic): the NeoHooke recovery
+  // of tests/src/testhyperelasticity.hh:139-196 -- Ogden<1, total>({mu}, {2}) with VF3 and Lame's first parameter IS the
+  // NeoHooke material, so the generalised-tangent kernel must reproduce the factored NeoHooke kernel: K, R and the energy.
+  {
+    const double E = 1000, nu = 0.3, lam = E * nu / ((1 + nu) * (1 - 2 * nu)), mu = E / (2 * (1 + nu));
+    auto fo = makeMesh(nx, ny, nz, 0.5, IKB_MAT_HYPERELASTIC, IKB_STRAIN_GREEN_LAGRANGE, 0);
+    for (auto& fe : fo) {
+      fe.hyperelastic            = ikb_hyperelastic{};
+      fe.hyperelastic.deviatoric = IKB_DEV_OGDEN_TOTAL;
+      fe.hyperelastic.n          = 1;
+      fe.hyperelastic.par[0]     = mu;
+      fe.hyperelastic.ex[0]      = 2.0;
+      fe.hyperelastic.volumetric = 3;
+      fe.hyperelastic.K          = lam;
+    }
+    auto ao = makeDeviceSparseFlatAssembler(fo, dv);
+    ao->setExternalLoad(fext);  // the same load as on the NeoHooke assembler
+    const HostSparseMatrix Ko = ao->matrix(req, MatrixAffordance::stiffness, DBCOption::Full);
+    const HostSparseMatrix Kn = asmb->matrix(req, MatrixAffordance::stiffness, DBCOption::Full);
+    CHECK(Ko.values.size() == Kn.values.size());
+    double big = 0, err = 0;
+    for (std::size_t p = 0; p < Kn.values.size(); ++p) {
+      big = std::max(big, std::abs(Kn.values[p]));
+      err = std::max(err, std::abs(Ko.values[p] - Kn.values[p]));
+    }
+    CHECK(big > 1.0 && err <= 1e-11 * big);
+    const std::vector<double> Ro = ao->vector(req, VectorAffordance::forces, DBCOption::Full);
+    const std::vector<double> Rn = asmb->vector(req, VectorAffordance::forces, DBCOption::Full);
+    double rb = 0, re = 0;
+    for (std::size_t i = 0; i < n; ++i) {
+      rb = std::max(rb, std::abs(Rn[i]));
+      re = std::max(re, std::abs(Ro[i] - Rn[i]));
+    }
+    CHECK(rb > 0 && re <= 1e-11 * rb);
+    const double Eo = ao->scalar(req, ScalarAffordance::mechanicalPotentialEnergy);
+    const double En = asmb->scalar(req, ScalarAffordance::mechanicalPotentialEnergy);
+    CHECK(std::abs(Eo - En) <= 1e-10 * std::max(1.0, std::abs(En)));
+    // a law that was never handed over is a state error, not a silent default
+    auto fm = makeMesh(1, 1, 1, 1.0, IKB_MAT_HYPERELASTIC, IKB_STRAIN_GREEN_LAGRANGE, 0);
+    HostDirichletValues dv1(24);
+    bool thrown = false;
+    try {
+      auto am = makeDeviceSparseFlatAssembler(fm, dv1);  // deviatoric = none, volumetric = VF0: refused by ikb_set_hyperelastic
+    } catch (const InvalidState&) {
+      thrown = true;
+    } catch (const std::exception&) {
+      thrown = true;
+    }
+    CHECK(thrown);
+  }
+
   // Load skills through the wrapper (loads/volume.hh:67-106, loads/traction.hh:70-138): a volume load and a traction on
   // the face x = nx*h with a non-proportional dependence on the load factor.  At d = 0 the internal forces vanish, so
   // R = -fext(lambda): totals against the exact integrals, nodal values against the wrapper's own sampling.
