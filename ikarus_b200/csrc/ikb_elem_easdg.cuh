@@ -16,12 +16,18 @@
 // so K_uu, L, D and R, Rtilde are blocks of ONE generalised tangent over the G = N D + D^2 generalised dofs, with the
 // isotropic moduli in the factored form of ikb_elem_q1.cuh:  B_I : CC : B_J = l' (X:B_I)(X:B_J) + 2 m' tr(X B_I X B_J).
 //
+// The same kernel serves a third mode, ENH_STRAIN: the enhanced dofs contribute dE/dalpha_j = column j of M(xi) (the
+// strain enhancements E4..E21, easfunctions/greenlagrangestrain.hh:40-141) and no variation of F; with m = 0 it is the plain
+// displacement element.  It is the element kernel of the principal-stretch laws (FORM_PS, ikb_material_ps.cuh), whose
+// CC : B_J takes the X B X slot of the record.
+//
 // One warp per element.  Per Gauss point every lane evaluates the kinematics and the material (redundantly: a few
-// hundred flops), writes the record of its own generalised dof(s) -- B, X B X, X:B, dF, dF S -- to shared memory, and
-// the G(G+1)/2 dof pairs are accumulated in registers, 18 pairs per lane for Hex8.  The enhanced block is then
-// eliminated in shared memory (Gauss-Jordan with partial pivoting on [D | L | Rtilde]; the reference inverts D), the
-// condensed K_e leaves in the symmetric-packed staging form of the other element kernels.  This is the first, plain
-// formulation of the variant (parity first); it moves about 2 MB through shared memory per Hex8 element.
+// hundred flops) and writes the record of its generalised dof -- B, X B X, X:B, dF, dF S -- to shared memory, the nodal
+// dofs in one round, the enhanced ones in a second.  The pair loop runs on register tiles: the dofs form NG groups of TS,
+// a lane owns the TS x TS block of one group pair and contracts the records channel by channel (2 TS shared-memory loads
+// per TS^2 FMAs).  The enhanced block is then eliminated in registers, one lane per column of [D | L | Rtilde]
+// (Gauss-Jordan with partial pivoting; the reference inverts D), and the condensed K_e leaves in the symmetric-packed
+// staging form of the other element kernels.
 #pragma once
 #include "ikb_elem_eas.cuh"
 #include "ikb_material_ps.cuh"
@@ -38,8 +44,6 @@ struct DgCfg {
   static constexpr int N = 1 << D, ND = N * D, M = ST ? MM : D * D, G = ND + M;
   static constexpr int MX = M > 0 ? M : 1;       // array extent that stays legal for M = 0
   static constexpr int SYM = D * (D + 1) / 2;
-  static constexpr int NP = G * (G + 1) / 2;     // generalised dof pairs I <= J
-  static constexpr int NS = (NP + 31) / 32;      // pairs per lane
   // register tiles of the pair loop: the dofs form NG groups of TS, lane t owns the TS x TS block of the group pair
   // (gi <= gj) number t; TS is the smallest size whose NG (NG + 1) / 2 blocks fit the 32 lanes
   static constexpr int tileSize() {
@@ -76,7 +80,6 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
   using C = DgCfg<D, ENH, MM>;
   constexpr bool TR = C::TR, ST = C::ST;
   constexpr int N = C::N, ND = C::ND, M = C::M, G = C::G, SYM = C::SYM, REC = C::REC, GS = C::GS;
-  constexpr unsigned FULL = 0xffffffffu;
   const ElemArgs& A = EA.E;
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -596,7 +599,6 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
         }
       }
   }
-#pragma unroll
   if (lane < ND) Rg[lane] = rI[0];
   if (lane < M) Rg[ND + lane] = rI[1];
   __syncwarp();
