@@ -12,10 +12,12 @@
 //   D[j][k]  += s_j s_k G[r_j][r_k]      L[j][a,c] += s_j (Q^T B_a)[r_j][c]      Rt[j] += s_j TS[r_j]
 // (s_j = p_j/detJ), so the m x m and m x ndof products of the reference collapse to table lookups.
 //
-// N = 2^D threads per element: phase 1 thread = Gauss point; pass A thread a = node pairs (a, a+k) of
-// K_uu and R_a; pass B thread a = columns of L belonging to node a and rows {a, a+N, ..} of Rt;
-// pass C the same rows of D.  D is factorised cooperatively (LDL^T, right-looking) in shared memory,
-// each thread solves its own right-hand sides, then K_ab -= L_a^T D^-1 L_b and R_a -= L_a^T D^-1 Rt.
+// N = 2^D threads per element, one warp per CTA.  Phase 1: thread = Gauss point (records in shared memory).  Pass C:
+// thread a = rows {a, a+N, ..} of D and Rt; pass B: the columns of L belonging to node a.  D is then factorised in
+// REGISTERS (LDL^T, right-looking: the rows stay with the thread that accumulated them, the pivot row is broadcast with
+// shuffles, Rt rides along as one more column), each thread solves its own right-hand sides, L / Y = Lf^-1 L live in the
+// record tails that passes B and C have released, and only then pass A accumulates the K_uu node pairs (a, a+k) and
+// R_a, which are condensed in registers:  K_ab -= Y_a^T d^-1 Y_b,  R_a -= Y_a^T d^-1 y_R.
 #pragma once
 #include "ikb_elem_q1.cuh"
 #include "ikb_internal.cuh"
