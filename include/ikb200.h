@@ -33,6 +33,8 @@
 extern "C" {
 #endif
 
+/* 3: ikb_desc.eas_function.  Additions since (no layout change, same version): IKB_MAT_BLATZKO, IKB_MAT_HYPERELASTIC with
+ * ikb_set_hyperelastic / ikb_hyperelastic. */
 #define IKB_ABI_VERSION 3
 
 typedef struct ikb_handle_s* ikb_handle;
