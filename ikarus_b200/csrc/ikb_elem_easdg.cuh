@@ -63,7 +63,7 @@ struct DgCfg {
   static constexpr int O_REC = 0, O_KG = O_REC + G * REC, O_RG = O_KG + G * GS, O_X = O_RG + G, O_U = O_X + ND,
                        O_AL = O_U + ND, O_DU = O_AL + M, O_RHS = O_DU + ND, O_T0 = O_RHS + M;
   static constexpr int WARP_DOUBLES = (O_T0 + (ST ? SYM * SYM : 0) + 1) / 2 * 2;
-  static constexpr int WARPS = 4;
+  static constexpr int WARPS = 1;  // one warp per CTA: the register file then holds 9 warps of the 216-register variants instead of 2 CTAs of 4
   static constexpr size_t SMEM = (size_t)WARPS * WARP_DOUBLES * 8;
 };
 
