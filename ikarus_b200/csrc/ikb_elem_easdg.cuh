@@ -574,10 +574,9 @@ __global__ void __launch_bounds__(32 * DgCfg<D, ENH, MM>::WARPS) elem_easdg_kern
       for (int q = 0; q < D * D; ++q) channel(C::O_DF + q, C::O_DFS + q, wd);
       if constexpr (TR) {
 #pragma unroll
-        for (int q = 0; q < D * D; ++q) {
-          channel(C::O_MA + q, C::O_MB + q, wd);
-          channel(C::O_MB + q, C::O_MA + q, wd);
-        }
+        // mixed second variation: mA is carried by the nodal dofs only, mB by the enhanced ones only, and the tiles hold
+        // I <= J (nodal before enhanced), so the term mB_I mA_J of the symmetrised product never contributes
+        for (int q = 0; q < D * D; ++q) channel(C::O_MA + q, C::O_MB + q, wd);
       }
     }
   }
