@@ -6,7 +6,8 @@ mesh, through the C-ABI of libikb200.so.
 
   --gpus 1   BASELINE.json configs[1] (C2): 3D cantilever Hex8 Q1 NeoHooke, YaspGrid 128x32x32, ~420k DOF.
              The same run also times configs[4] (C5, Hex8 NeoHooke 256^3) on the ONE GPU (`c5_single_gpu`), which
-             is the same-workload reference for the strong-scaling lines below.
+             is the same-workload reference for the strong-scaling lines below, and configs[3] (C4, Hex8 + EAS(21)
+             NeoHooke nu = 0.499, 96^3; plus its E9 variant) as `c4_single_gpu` with the SURVEY 8d targets beside them.
   --gpus N   BASELINE.json configs[4] (C5): Hex8 Q1 NeoHooke 256x256x256 (~51M DOF, 4.09e9 nnz), the FIXED mesh cut
              into N z-slabs ("scaling": "strong"): every rank owns a contiguous row block, evaluates the elements
              touching it (one ghost element layer, no collective in assembly) and the Newton step runs the
@@ -484,6 +485,8 @@ def run_ours(args):
         if world == 1 and wl == "C2" and not args.no_c5:
             del asm
             extra["c5_single_gpu"] = c5_on_one_gpu(local, torch)
+        if world == 1 and wl == "C2" and not args.no_c4:
+            extra["c4_single_gpu"] = c4_on_one_gpu()
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (world > 1 and wl != "C2W") else "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -554,6 +557,39 @@ def c5_on_one_gpu(local, torch):
     return out
 
 
+def c4_on_one_gpu():
+    """configs[3] (C4: Hex8 + EAS(21) NeoHooke, nu = 0.499, 96^3) and its E9 variant on ONE GPU: the fused K+R sweep
+    as element kernel + gathers, each phase timed with CUDA events on the handle's stream (best of 3 x 10 launches,
+    the protocol of tools/config_times.py).  SURVEY 8d targets: 107 Melem/s (E21), 196 (E9)."""
+    import ikarus_b200 as ik
+    from ikarus_b200 import _capi as capi, meshes
+
+    out = {}
+    n = 96
+    mat = ik.Materials.NeoHooke(ik.toLamesFirstParameterAndShearModulus(emodul=1000.0, nu=0.499))
+    for key, m, target in (("E21", 21, 107.0), ("E9", 9, 196.0)):
+        slab = meshes.structured_q1((n, n, n), (1.0, 1.0, 1.0))
+        flags = meshes.clamp_face_flags((n, n, n), 0, 0)
+        fes = ik.makeFE(dict(dim=3, order=1, n_dof=slab.n_dof), ik.skills(ik.nonLinearElastic(mat), ik.eas(m)),
+                        slab.corner_coords, slab.elem_dofs)
+        dv = ik.DirichletValues(slab.n_dof)
+        dv.container()[:] = flags
+        asm = ik.SparseFlatAssembler(fes, dv, mode="resident")
+        d = 0.05 * slab.h * np.random.default_rng(44).uniform(-1, 1, slab.n_dof)
+        d[flags] = 0
+        req = ik.FERequirements(d, 0.0)
+        asm.bind(req, ik.elastoStatics, ik.DBCOption.Full)
+        asm._assemble(req, capi.MATRIX | capi.VECTOR, ik.DBCOption.Full)
+        asm._check(asm._lib.ikb_sync(asm._h))
+        te = min(asm.timePhase("elements", ik.DBCOption.Full, 10) for _ in range(3))
+        tg = min(asm.timePhase("gather", ik.DBCOption.Full, 10) for _ in range(3))
+        out[key] = {"workload": f"C4 Hex8+EAS{m} NeoHooke nu=0.499 {n}^3", "elements": len(fes), "dofs": slab.n_dof,
+                    "elements_ms": te, "gather_ms": tg, "value": len(fes) / (te + tg) / 1e3, "unit": UNIT,
+                    "survey_8d_target": target}
+        del asm
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -566,6 +602,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5-on-one-GPU figure of the N=1 run")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (Hex8 + EAS) figures of the N=1 run")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 10)  # each step is 1-2 s of CPU work

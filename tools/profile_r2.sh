@@ -4,7 +4,7 @@
 set -x
 PART=${1:-all}   # gpurun brings back at most 64 MiB: run "a" and "b" in separate calls
 NCU="ncu --clock-control none"
-B="python bench.py --steps 5 --warmup 3 --no-cpu --no-c5"
+B="python bench.py --steps 5 --warmup 3 --no-cpu --no-c5 --no-c4"
 [ "$PART" = b ] || $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/launches_r2.csv $B --no-newton > gpurun_out/launches_r2.log 2>&1
 [ "$PART" = b ] || $NCU --set full --import-source on -k regex:'elem_h8_mma|gather_pull' -s 6 -c 2 -o gpurun_out/prof_r2_c2 $B --no-newton > /dev/null 2>&1
 [ "$PART" = b ] || IKB_ELEM=fma $NCU --set full --import-source on -k regex:'elem_q1' -s 3 -c 1 -o gpurun_out/prof_r2_c2_fma $B --no-newton > /dev/null 2>&1
