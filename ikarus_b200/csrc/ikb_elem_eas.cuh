@@ -103,6 +103,9 @@ struct EasCfg {
   static constexpr int ES0 = (REC0 > SCR ? REC0 : SCR) + M * M;
   static constexpr int ES = ES0 + ((N % 16) - (ES0 % 16) + 16) % 16;
   static constexpr int EPW = 32 / N;
+  // Gauss-point loops of passes A, B, C: two points per trip for the small ansaetze (instruction-level parallelism for a
+  // kernel that runs one warp per scheduler); E21 has no registers to spare
+  static constexpr int GUNROLL = (M <= 9) ? 2 : 1;
   static constexpr int EPC0 = (100 * 1024) / (ES * 8);
   static constexpr int EPC1 = (EPC0 / EPW) * EPW;
   static constexpr int EPC2 = EPC1 > 128 / N ? 128 / N : EPC1;
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
 #pragma unroll
       for (int k = 0; k < M; ++k) drow[k] = 0.0;
       const int rj = T::rowRt(j), mj = T::monoRt(j);
-#pragma unroll 1
+#pragma unroll(C::GUNROLL)
       for (int g = 0; g < N; ++g) {
         const double* gp = rec + g * C::GPS;
         double sm[C::NMONO];
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
   for (int j = 0; j < M; ++j)
 #pragma unroll
     for (int c = 0; c < D; ++c) Lr[j][c] = 0.0;
-#pragma unroll 1
+#pragma unroll(C::GUNROLL)
   for (int g = 0; g < N; ++g) {
     const double* gp = rec + g * C::GPS;
     double sm[C::NMONO];
@@ -716,7 +719,7 @@ __global__ void __launch_bounds__(EasCfg<D, FORM, M>::TPB) elem_eas_kernel(EasAr
     for (int k = 0; k < NK; ++k)
 #pragma unroll
       for (int q = 0; q < DD; ++q) acc[k][q] = 0.0;
-#pragma unroll 1
+#pragma unroll(C::GUNROLL)
     for (int g = 0; g < N; ++g) {
       const double* gp = rec + g * C::GPS;
       const double c1 = gp[C::O_C1], c2 = gp[C::O_C2];
